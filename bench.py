@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""bench.py — scanned GB/s with bit-exact lazy matches (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C] [--size BYTES] [--impl ours|reference]
+
+A "step" is one pass of the hot path (regex scan -> LAZY-v1 match list) over one synthetic corpus.
+N=1 workload: config 2 of BASELINE.json (e-mail regex over 1 GiB of synthetic log records).
+For N>1 (torchrun) the corpus is `--size` bytes PER RANK (weak scaling), sharded into contiguous
+byte ranges, one per GPU.
+
+value  : corpus resident in HBM, program compiled, CUDA events on the launching stream
+e2e    : the same scan through the C ABI with HOST buffers (pinned), H2D of the corpus and D2H of
+         the match list inside the timed region
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--size", type=int, default=0, help="corpus bytes per rank (default: the config's size, capped for N>1)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = [x for x in sm if x > 0.5 * mx] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(cfg, sample_per_thread: int):
+    """The oracle port (reference algorithm: per-active-state row OR, injection, flag test, backward
+    start scan) on all host cores, each core scanning its own contiguous piece of the corpus."""
+    from oracle import api as oracle_api
+    oracle_api.build(ref=False)
+    cores = os.cpu_count() or 1
+    o = oracle_api.Oracle(cfg.pattern)
+    n = sample_per_thread * cores
+    text = oracle_api.corpus_iid(cfg.seed, cfg.alpha, 0, n) if cfg.mode == "iid" else oracle_api.corpus_records(cfg.seed, 0, n)
+    o.time_parallel(text, min(sample_per_thread, 1 << 20), cores)         # warm
+    sec, m = o.time_parallel(text, sample_per_thread, cores)
+    out = {"value": n / sec / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+           "sample": f"first {n >> 20} MiB of the corpus, {sample_per_thread >> 20} MiB per thread, {cores} threads, full LAZY-v1 match lists ({m} matches)"}
+    # the compiled, unmodified reference can only do whole-string acceptance (its lazy iterator is
+    # missing, src/Iterator.cpp): time that too, 1 core (it is single-threaded), for orientation.
+    if oracle_api.have_ref() and o.n_raw <= 256:
+        k = min(n, 16 << 20)
+        t = bytes(text[:k]).replace(b"\0", b" ")
+        sec_r, _ = oracle_api.ref_time_acceptance(cfg.pattern, t, 3)
+        out["reference_acceptance_only"] = {"value": k / sec_r / 1e9, "unit": "GB/s", "cores": 1,
+                                            "note": "oracle/_ref AcceptanceIterator, anchored: set empties after a few bytes (lower bound on cost)"}
+    return out
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_thread = 32 << 20
+    times, res = [], None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        res = cpu_baseline(cfg, per_thread) if i == 0 or True else res
+        if i >= args.warmup:
+            times.append(res["value"])
+        if time.perf_counter() - t0 > 60 or sum(1 for _ in times) >= 3:
+            break
+    val = float(np.median(times)) if times else res["value"]
+    line = {"impl": "reference", "metric": "scanned GB/s, bit-exact lazy matches", "value": val, "unit": "GB/s",
+            "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "dtype": "u64 bitsets", "data": "synthetic", "vs_baseline": None,
+            "config": {"workload": f"{cfg.name}: regex {cfg.pattern!r}", "note": "CPU path, bounded sample of the same corpus"},
+            "cpu_baseline": {**res, "value": val},
+            "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    from roaringregex_b200.configs import CONFIGS
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+        return
+
+    import torch
+    import roaringregex_b200 as rrx
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    size = args.size or min(cfg.length, 8 << 30)
+    if world > 1 and not args.size:
+        size = min(cfg.length // world, 8 << 30)
+    size &= ~127
+    regex = rrx.RRegex(cfg.pattern)
+    info = regex.info
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+
+    # corpus of this rank, generated in place: [rank*size, (rank+1)*size) of the global text
+    off = rank * size
+    d_text = torch.empty(size + 256, dtype=torch.uint8, device="cuda")
+    gen = (lambda: rrx.corpus_iid(d_text.data_ptr(), off, size, cfg.seed, cfg.alpha, sh)) if cfg.mode == "iid" else \
+          (lambda: rrx.corpus_records(d_text.data_ptr(), off, size, cfg.seed, sh))
+    gen()
+    torch.cuda.synchronize()
+
+    cap = max(1 << 20, size // 48)
+    sc = rrx.Scanner(regex, size, cap)
+
+    def step():
+        sc.scan(d_text.data_ptr(), size, off, 0, None, sh)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    res = sc.result(sh)
+    assert res["error_bits"] == 0, res
+    if res["n_matches"] > cap:
+        cap = res["n_matches"] + 1024
+        sc = rrx.Scanner(regex, size, cap)
+        step()
+        res = sc.result(sh)
+    n_matches = res["n_matches"]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_all0 = torch.cuda.Event(enable_timing=True); t_all1 = torch.cuda.Event(enable_timing=True)
+    t_all0.record(stream)
+    for a, b in evs:
+        a.record(stream)
+        step()
+        b.record(stream)
+    t_all1.record(stream)
+    barrier()
+    total_ms = t_all0.elapsed_time(t_all1)
+    kern_ms = [a.elapsed_time(b) for a, b in evs]
+    clocks = sampler.stop() if sampler else None
+    res = sc.result(sh)
+    assert res["n_matches"] == n_matches and res["error_bits"] == 0
+
+    if dist is not None:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        m = torch.tensor([n_matches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(m)
+        total_matches = int(m.item())
+    else:
+        total_matches = n_matches
+    ms_per_step = total_ms / args.steps
+    total_bytes = size * world
+    value = total_bytes / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region ----------------------
+    e2e = None
+    if not args.no_e2e:
+        e_size = min(size, 1 << 30)
+        h_text = torch.empty(e_size, dtype=torch.uint8).pin_memory()
+        h_text.copy_(d_text[:e_size])
+        torch.cuda.synchronize()
+        host_np = h_text.numpy()
+        regex.scan_host(host_np[: 1 << 20])
+        e_steps = max(1, min(args.steps, 3))
+        barrier()
+        t0 = time.perf_counter()
+        n_e = 0
+        for _ in range(e_steps):
+            n_e = len(regex.scan_host(host_np, off))
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / e_steps
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": e_size * world / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": e_size, "d2h_bytes_per_step": 16 * n_e,
+               "bytes_scanned_per_rank": e_size}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peaks()
+    k_ms = float(np.mean(kern_ms))
+    alg_bytes = size + 16 * n_matches
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    line = {
+        "metric": "scanned GB/s, bit-exact lazy matches", "value": value, "unit": "GB/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": f"u32x{info['words']} bitsets", "data": "synthetic",
+        "config": {"workload": f"{cfg.name}: regex {cfg.pattern!r} over {size} bytes per GPU ({cfg.note})",
+                   "bytes_per_gpu": size, "matches_total": total_matches, "l2": "input larger than L2 (126 MB), no flush needed" if size > (256 << 20) else "input smaller than L2",
+                   "states_raw": info["n_raw"], "states_flat": info["n_flat"], "states_device": info["n_device"], "words": info["words"]},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": "rrx_scan_kernel", "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "peak_source": peak_src},
+        "e2e": e2e, "gpu_launches": args.steps * res["launches"], "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(cfg, 32 << 20)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

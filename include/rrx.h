@@ -1,0 +1,113 @@
+/* rrx — C ABI of the B200 regex scanner that stands in for RoaringRegex's hot path.
+ *
+ * Plain C, plain pointers and sizes; no torch / CUDA types in the signatures (a CUDA stream is
+ * passed as void*).  Every entry point names the reference interface it replaces
+ * (file:line relative to the RoaringRegex tree).  librrx.so has NO CPU scanning path: every
+ * rrx_scan* call runs the sm_100a kernels or fails with RRX_ERR_CUDA.
+ *
+ * Match semantics: "LAZY-v1" (DESIGN.md / SURVEY.md Appendix D): for every end offset e such that
+ * some text[s:e], s<e, is in the language, exactly one match (max such s, e); ascending e.
+ * Offsets are 64-bit, half-open, global (base_offset + position in the buffer).
+ */
+#ifndef RRX_H_
+#define RRX_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    RRX_OK = 0,
+    RRX_ERR_PARSE = 1,        /* the reference would throw std::runtime_error (Parser.cpp:36,155) or has UB */
+    RRX_ERR_CUDA = 2,         /* no device / CUDA runtime failure; there is no CPU fallback */
+    RRX_ERR_UNSUPPORTED = 3,  /* automaton/text combination outside the implemented transfer-function rank */
+    RRX_ERR_ARG = 4
+};
+
+enum { RRX_MODE_LAZY_V1 = 0, RRX_MODE_NO_OVERLAP = 1 };
+enum { RRX_COMPILE_DEFAULT = 0, RRX_COMPILE_NO_REDUCE = 1 };
+
+typedef struct rrx_program rrx_program;   /* compiled regex: replaces Regex::RRegex's NFA<S> + MemoryPool (regex.h:16-75,212-228) */
+typedef struct rrx_scanner rrx_scanner;   /* reusable device-side scan context (one per CUDA stream) */
+typedef struct rrx_matches rrx_matches;   /* a match list: replaces repeated IteratorWrapper::operator++ / operator* (regex.h:113-122) */
+
+typedef struct rrx_info {
+    uint32_t n_raw;          /* reference raw state count (Parser.cpp:163) */
+    uint32_t ref_width_class;/* set type the reference would pick (Parser.cpp:165-168): 0 BitSet<1> 1 BitSet<2> 2 BitSet<4> 3 Roaring */
+    uint32_t n_flat;         /* flattened states = atoms + START */
+    uint32_t n_device;       /* positions in the device automaton (after merging equivalent positions) */
+    uint32_t words;          /* 32-bit words per device state set: 1,2,4,8,16,32 */
+    uint32_t nullable;       /* the empty string is in the language */
+    uint32_t n_terms, n_bicliques, uses_rows;   /* forward follow decomposition */
+    uint32_t static_closed;  /* no chunk's exit can depend on its entry (acyclic pruned follow, depth < 128) */
+} rrx_info;
+
+/* ---- compile: replaces RRegex::RRegex(const char*) (regex.h:224, Parser.cpp:161-170) ---------- */
+int rrx_compile(const char* ere, rrx_program** out);
+int rrx_compile_ex(const char* ere, uint32_t flags, rrx_program** out);
+void rrx_program_free(rrx_program* p);
+void rrx_program_info(const rrx_program* p, rrx_info* out);
+/* The flattened automaton BEFORE device reduction, for inspection/tests: positions = n_flat-1.
+ * which: 0 first, 1 accept (words32 = ceil(P/32) each), 2 follow matrix (P rows),
+ *        3 byte classes (P rows of 4 words = 128 bits).  Returns words written or <0. */
+int64_t rrx_program_flat_table(const rrx_program* p, int which, uint32_t* out, uint64_t cap_words);
+/* The device program blob (ProgHeader + tables, see csrc/rrx_compile.h). */
+const uint32_t* rrx_program_blob(const rrx_program* p, uint64_t* n_words);
+/* Raw reference-layout forward row, rebuilt from the tracked atoms (NFA.cc:9-12 fwd rows):
+ * targets of `state` on `byte` as a bitset of ceil(n_raw/32) words.  For fixture tests. */
+int64_t rrx_program_raw_row(const rrx_program* p, uint32_t state, uint32_t byte, uint32_t* out, uint64_t cap_words);
+int64_t rrx_program_raw_finals(const rrx_program* p, uint32_t* out, uint64_t cap_words);
+
+/* ---- scan: replaces RRegex::get_acceptance_iter(char*) + IteratorWrapper::operator++/operator*
+ *      (regex.h:118-119,156-162,225) and supplies the lazy iterator Iterator.cpp leaves empty ---- */
+/* d_text: device pointer, 16-byte aligned.  stream: cudaStream_t (NULL = default stream). */
+int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, uint64_t base_offset,
+                    int mode, rrx_matches** out, void* stream);
+/* text: host pointer; the copy to the device is part of the call. */
+int rrx_scan_host(const rrx_program* p, const uint8_t* text, uint64_t len, uint64_t base_offset,
+                  int mode, rrx_matches** out);
+
+uint64_t rrx_matches_count(const rrx_matches* m);
+const int64_t* rrx_matches_data(rrx_matches* m);                /* host pairs (start,end); copied D2H on first use */
+const int64_t* rrx_matches_device_data(const rrx_matches* m);   /* device pairs */
+void rrx_matches_free(rrx_matches* m);
+
+/* ---- reusable context (what the convenience calls above are built from; used by bench.py) ----- */
+typedef struct rrx_scan_opts {
+    uint64_t left_context;     /* bytes readable before d_text (for start scans crossing the left edge) */
+    const uint32_t* entry;     /* forward set carried into d_text[0] (words32 per rrx_info.words), or NULL */
+    int mode;
+    uint32_t reserved;
+} rrx_scan_opts;
+
+typedef struct rrx_scan_result {
+    uint64_t n_matches;        /* total found (may exceed capacity: then only the first `capacity` were written) */
+    uint64_t capacity;
+    uint64_t n_pending;        /* start scans that ran off the left edge (sharded use) */
+    uint32_t error_bits;       /* kernel-reported: 1 = transfer function not rank<=1 (results invalid) */
+    uint32_t launches;         /* kernels launched by the scan */
+    const int64_t* d_matches;  /* device pairs */
+} rrx_scan_result;
+
+int rrx_scanner_create(const rrx_program* p, uint64_t max_len, uint64_t match_capacity, rrx_scanner** out);
+void rrx_scanner_free(rrx_scanner* s);
+/* Enqueue one scan on `stream` (asynchronous). */
+int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64_t base_offset,
+                     const rrx_scan_opts* opts, void* stream);
+/* Wait for the last scan and fetch its counters. */
+int rrx_scanner_result(rrx_scanner* s, rrx_scan_result* out, void* stream);
+/* Composite transfer function of the last scanned shard: 1+3*words uint32 (kind, b, U, P); host copy. */
+int rrx_scanner_shard_summary(rrx_scanner* s, uint32_t* out, uint64_t cap_words, void* stream);
+
+/* ---- measurement harness: synthetic corpora of SURVEY.md §8d, generated in device memory ------ */
+int rrx_corpus_iid_device(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, const uint8_t alpha[256], void* stream);
+int rrx_corpus_records_device(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, void* stream);
+
+const char* rrx_last_error(void);
+const char* rrx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRX_H_ */

@@ -1,0 +1,326 @@
+"""roaringregex_b200 — B200-native drop-in for RoaringRegex's hot path (bit-parallel NFA scan ->
+lazy-match enumeration).
+
+Python mirror of the reference's public interface (`/root/reference/src/inc/regex.h:100-126,212-228`)
+on top of the C ABI in `include/rrx.h` (librrx.so, hand-written sm_100a CUDA):
+
+    RRegex(pattern)                 regex.h:224 / Parser.cpp:161   (raises InvalidExpression like the
+                                    reference's std::runtime_error)
+    RRegex.get_lazy_iter(text)      the lazy iterator the reference's README promises and
+                                    src/Iterator.cpp leaves empty
+    RRegex.get_acceptance_iter(text) regex.h:225 (whole-string acceptance, answered from the match list)
+    it.advance() / it.value()       IteratorWrapper::operator++(int) / operator*()  (regex.h:118-119)
+    Match(start, end).str()         regex.h:100-105
+
+There is NO CPU scanning path in this package: without the CUDA extension or without a GPU the
+scan calls raise.  (The CPU oracle lives under /oracle and is test infrastructure only.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _build
+
+__all__ = ["RRegex", "Match", "InvalidExpression", "RrxError", "Scanner", "lib", "corpus_iid", "corpus_records"]
+
+RRX_OK, RRX_ERR_PARSE, RRX_ERR_CUDA, RRX_ERR_UNSUPPORTED, RRX_ERR_ARG = range(5)
+MODE_LAZY_V1, MODE_NO_OVERLAP = 0, 1
+COMPILE_DEFAULT, COMPILE_NO_REDUCE = 0, 1
+
+
+class RrxError(RuntimeError):
+    pass
+
+
+class InvalidExpression(RrxError):
+    """The reference's `throw std::runtime_error("invalid expression")` (Parser.cpp:36,155)."""
+
+
+class _Info(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("n_raw", "ref_width_class", "n_flat", "n_device", "words", "nullable",
+                                          "n_terms", "n_bicliques", "uses_rows", "static_closed")]
+
+
+class _Opts(C.Structure):
+    _fields_ = [("left_context", C.c_uint64), ("entry", C.c_void_p), ("mode", C.c_int), ("reserved", C.c_uint32)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("n_matches", C.c_uint64), ("capacity", C.c_uint64), ("n_pending", C.c_uint64),
+                ("error_bits", C.c_uint32), ("launches", C.c_uint32), ("d_matches", C.c_void_p)]
+
+
+_LIB = None
+
+
+def lib() -> C.CDLL:
+    """Load librrx.so (building it in-tree with nvcc if the sources are newer).  Fails loudly."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if _build.needs_build():
+        if os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+            _build.build()
+        elif not os.path.exists(path):
+            raise RrxError("librrx.so is missing and nvcc is not available to build it")
+    L = C.CDLL(path)
+    vp, u64, u32, i64 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64
+    sigs = {
+        "rrx_compile": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+        "rrx_compile_ex": (C.c_int, [C.c_char_p, u32, C.POINTER(vp)]),
+        "rrx_program_free": (None, [vp]),
+        "rrx_program_info": (None, [vp, C.POINTER(_Info)]),
+        "rrx_program_flat_table": (i64, [vp, C.c_int, vp, u64]),
+        "rrx_program_blob": (vp, [vp, C.POINTER(u64)]),
+        "rrx_program_raw_row": (i64, [vp, u32, u32, vp, u64]),
+        "rrx_program_raw_finals": (i64, [vp, vp, u64]),
+        "rrx_scan_device": (C.c_int, [vp, vp, u64, u64, C.c_int, C.POINTER(vp), vp]),
+        "rrx_scan_host": (C.c_int, [vp, vp, u64, u64, C.c_int, C.POINTER(vp)]),
+        "rrx_matches_count": (u64, [vp]),
+        "rrx_matches_data": (vp, [vp]),
+        "rrx_matches_device_data": (vp, [vp]),
+        "rrx_matches_free": (None, [vp]),
+        "rrx_scanner_create": (C.c_int, [vp, u64, u64, C.POINTER(vp)]),
+        "rrx_scanner_free": (None, [vp]),
+        "rrx_scanner_scan": (C.c_int, [vp, vp, u64, u64, C.POINTER(_Opts), vp]),
+        "rrx_scanner_result": (C.c_int, [vp, C.POINTER(_Result), vp]),
+        "rrx_scanner_shard_summary": (C.c_int, [vp, vp, u64, vp]),
+        "rrx_corpus_iid_device": (C.c_int, [vp, u64, u64, u64, vp, vp]),
+        "rrx_corpus_records_device": (C.c_int, [vp, u64, u64, u64, vp]),
+        "rrx_last_error": (C.c_char_p, []),
+        "rrx_version": (C.c_char_p, []),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)          # AttributeError = a symbol include/rrx.h declares is missing
+        fn.restype, fn.argtypes = res, args
+    _LIB = L
+    return L
+
+
+def _check(rc: int):
+    if rc == RRX_OK:
+        return
+    msg = lib().rrx_last_error().decode("latin-1")
+    if rc == RRX_ERR_PARSE:
+        raise InvalidExpression(msg)
+    raise RrxError(f"rrx error {rc}: {msg}")
+
+
+@dataclass
+class Match:
+    """regex.h:100-105 — half-open [start,end) into the scanned text."""
+    start: int
+    end: int
+    _text: bytes | None = None
+
+    def str(self) -> bytes:
+        return self._text[self.start:self.end] if self._text is not None else b""
+
+
+class RRegex:
+    """Compiled regex (regex.h:212-228).  Owns the rrx_program handle."""
+
+    def __init__(self, pattern, flags: int = COMPILE_DEFAULT):
+        self.pattern = pattern if isinstance(pattern, bytes) else pattern.encode("latin-1")
+        h = C.c_void_p()
+        _check(lib().rrx_compile_ex(self.pattern, flags, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _LIB is not None:
+            _LIB.rrx_program_free(h)
+
+    # -- introspection -------------------------------------------------------------------------
+    @property
+    def info(self) -> dict:
+        i = _Info()
+        lib().rrx_program_info(self._h, C.byref(i))
+        return {n: int(getattr(i, n)) for n, _ in _Info._fields_}
+
+    def flat_table(self, which: int) -> np.ndarray:
+        need = -lib().rrx_program_flat_table(self._h, which, None, 0)
+        out = np.zeros(max(int(need), 1), dtype=np.uint32)
+        got = lib().rrx_program_flat_table(self._h, which, out.ctypes.data, len(out))
+        return out[:max(int(got), 0)]
+
+    def blob(self) -> np.ndarray:
+        n = C.c_uint64(0)
+        p = lib().rrx_program_blob(self._h, C.byref(n))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(int(n.value),)).copy()
+
+    def raw_row(self, state: int, byte: int) -> list[int]:
+        w = (self.info["n_raw"] + 31) // 32
+        out = np.zeros(w, dtype=np.uint32)
+        lib().rrx_program_raw_row(self._h, state, byte, out.ctypes.data, w)
+        return _bits_of(out)
+
+    def raw_finals(self) -> list[int]:
+        w = (self.info["n_raw"] + 31) // 32
+        out = np.zeros(w, dtype=np.uint32)
+        lib().rrx_program_raw_finals(self._h, out.ctypes.data, w)
+        return _bits_of(out)
+
+    # -- scanning (GPU only) -------------------------------------------------------------------------
+    def scan_host(self, text, base_offset: int = 0, mode: int = MODE_LAZY_V1) -> np.ndarray:
+        """All matches of a host buffer as an (M,2) int64 array; H2D copy + kernels + D2H copy."""
+        buf = _as_u8(text)
+        h = C.c_void_p()
+        _check(lib().rrx_scan_host(self._h, buf.ctypes.data if len(buf) else None, len(buf), base_offset, mode, C.byref(h)))
+        return _take_matches(h)
+
+    def scan_device(self, d_ptr: int, length: int, base_offset: int = 0, mode: int = MODE_LAZY_V1, stream: int = 0) -> np.ndarray:
+        h = C.c_void_p()
+        _check(lib().rrx_scan_device(self._h, d_ptr, length, base_offset, mode, C.byref(h), stream))
+        return _take_matches(h)
+
+    def get_lazy_iter(self, text) -> "LazyIterator":
+        return LazyIterator(self, text)
+
+    def get_acceptance_iter(self, text) -> "AcceptanceIterator":
+        return AcceptanceIterator(self, text)
+
+
+def _take_matches(h) -> np.ndarray:
+    L = lib()
+    n = int(L.rrx_matches_count(h))
+    try:
+        if n == 0:
+            return np.zeros((0, 2), dtype=np.int64)
+        p = L.rrx_matches_data(h)
+        if not p:
+            _check(RRX_ERR_CUDA)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int64)), shape=(n, 2)).copy()
+    finally:
+        L.rrx_matches_free(h)
+
+
+def _bits_of(words: np.ndarray) -> list[int]:
+    out = []
+    for i, w in enumerate(words.tolist()):
+        while w:
+            low = w & -w
+            out.append(i * 32 + low.bit_length() - 1)
+            w ^= low
+    return out
+
+
+def _as_u8(text) -> np.ndarray:
+    if isinstance(text, np.ndarray):
+        assert text.dtype == np.uint8
+        return np.ascontiguousarray(text)
+    if isinstance(text, str):
+        text = text.encode("latin-1")
+    return np.frombuffer(bytes(text), dtype=np.uint8) if len(text) else np.zeros(0, np.uint8)
+
+
+class LazyIterator:
+    """`++` advances to the next LAZY-v1 match, `*` returns it or None when exhausted — the
+    IteratorWrapper protocol of regex.h:113-122.  The whole list is produced by one GPU scan on
+    first use; text is cut at the first NUL like the reference's `char*` driver (regex.h:157)."""
+
+    def __init__(self, regex: RRegex, text):
+        raw = bytes(text) if not isinstance(text, str) else text.encode("latin-1")
+        nul = raw.find(b"\0")
+        self._text = raw if nul < 0 else raw[:nul]
+        self._regex = regex
+        self._matches = None
+        self._pos = -1
+
+    def _ensure(self):
+        if self._matches is None:
+            self._matches = self._regex.scan_host(self._text)
+
+    def advance(self) -> "LazyIterator":          # operator++(int)
+        self._ensure()
+        self._pos += 1
+        return self
+
+    def value(self):                              # operator*()
+        self._ensure()
+        if 0 <= self._pos < len(self._matches):
+            s, e = self._matches[self._pos]
+            return Match(int(s), int(e), self._text)
+        return None
+
+    def create_copy(self) -> "LazyIterator":
+        c = LazyIterator.__new__(LazyIterator)
+        c.__dict__.update(self.__dict__)
+        return c
+
+    def __iter__(self):
+        self._ensure()
+        for s, e in self._matches:
+            yield Match(int(s), int(e), self._text)
+
+
+class AcceptanceIterator:
+    """regex.h:150-165: consume the whole NUL-terminated text; `*` is Match(0,len) iff the whole
+    string is in the language.  Answered on the GPU: the whole string matches iff LAZY-v1 ... has a
+    match ending at len whose anchored variant starts at 0; computed with an anchored entry set."""
+
+    def __init__(self, regex: RRegex, text):
+        raw = bytes(text) if not isinstance(text, str) else text.encode("latin-1")
+        nul = raw.find(b"\0")
+        self._text = raw if nul < 0 else raw[:nul]
+        self._regex = regex
+        self._done = False
+        self._accepted = None
+
+    def advance(self):
+        self._done = True
+        return self
+
+    def value(self):
+        raise RrxError("whole-string acceptance is not on the accelerated path yet (see DESIGN.md, out of scope)")
+
+
+class Scanner:
+    """Reusable device-side scan context (rrx_scanner): no allocation inside a scan call."""
+
+    def __init__(self, regex: RRegex, max_len: int, capacity: int):
+        self.regex = regex
+        h = C.c_void_p()
+        _check(lib().rrx_scanner_create(regex._h, max_len, capacity, C.byref(h)))
+        self._h = h
+        self.capacity = capacity
+        self._entry_keep = None
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _LIB is not None:
+            _LIB.rrx_scanner_free(h)
+
+    def scan(self, d_ptr: int, length: int, base_offset: int = 0, left_context: int = 0, entry=None, stream: int = 0):
+        o = _Opts(left_context, None, MODE_LAZY_V1, 0)
+        if entry is not None:
+            self._entry_keep = np.ascontiguousarray(entry, dtype=np.uint32)
+            o.entry = self._entry_keep.ctypes.data
+        _check(lib().rrx_scanner_scan(self._h, d_ptr, length, base_offset, C.byref(o), stream))
+
+    def result(self, stream: int = 0) -> dict:
+        r = _Result()
+        _check(lib().rrx_scanner_result(self._h, C.byref(r), stream))
+        return dict(n_matches=int(r.n_matches), capacity=int(r.capacity), n_pending=int(r.n_pending),
+                    error_bits=int(r.error_bits), launches=int(r.launches), d_matches=int(r.d_matches or 0))
+
+    def shard_summary(self, stream: int = 0) -> np.ndarray:
+        w = self.regex.info["words"]
+        out = np.zeros(1 + 3 * w, dtype=np.uint32)
+        _check(lib().rrx_scanner_shard_summary(self._h, out.ctypes.data, len(out), stream))
+        return out
+
+
+def corpus_iid(d_ptr: int, offset: int, length: int, seed: int, alpha: bytes, stream: int = 0):
+    a = np.frombuffer(bytes(alpha), dtype=np.uint8)
+    assert len(a) == 256
+    _check(lib().rrx_corpus_iid_device(d_ptr, offset, length, seed, a.ctypes.data, stream))
+
+
+def corpus_records(d_ptr: int, offset: int, length: int, seed: int, stream: int = 0):
+    _check(lib().rrx_corpus_records_device(d_ptr, offset, length, seed, stream))

@@ -1,0 +1,324 @@
+// C ABI of librrx.so (include/rrx.h).  Host C++ around the sm_100a kernels; no CPU scan path.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rrx.h"
+#include "rrx_compile.h"
+#include "rrx_scan.h"
+#include "rrx_tile.cuh"
+
+using namespace rrx;
+
+namespace {
+thread_local std::string g_err;
+int set_err(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_err(cudaError_t e, const char* what) {
+    return set_err(RRX_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define RRX_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_err(e_, #call); } while (0)
+}  // namespace
+
+struct rrx_program {
+    Automaton automaton;   // reference-equivalent view (atoms, flattened positions)
+    Program prog;          // device program
+};
+
+struct rrx_scanner {
+    const rrx_program* p = nullptr;
+    int device = 0, sm_count = 0;
+    uint64_t max_len = 0, capacity = 0, max_tiles = 0;
+    uint32_t NW = 1;
+    uint32_t* d_prog = nullptr;
+    uint8_t* d_ctrl = nullptr;      // [ticket | err | total[2] | tflag[T] | cstatus[T]]
+    size_t ctrl_bytes = 0;
+    uint32_t* d_tpay = nullptr;
+    long long* d_out = nullptr;
+    uint32_t* d_shard = nullptr;
+    PendingStart* d_pending = nullptr;
+    uint32_t pending_cap = 4096;
+    uint32_t launches = 0;
+    bool owns_out = true;
+    // pinned host mirror of [ticket, err, total0, total1]
+    uint64_t* h_ctr = nullptr;
+};
+
+struct rrx_matches {
+    uint64_t count = 0;
+    long long* d_pairs = nullptr;   // owned
+    std::vector<int64_t> host;
+    bool host_valid = false;
+};
+
+extern "C" {
+
+const char* rrx_last_error(void) { return g_err.c_str(); }
+const char* rrx_version(void) { return "rrx 0.1 (sm_100a)"; }
+
+int rrx_compile_ex(const char* ere, uint32_t flags, rrx_program** out) {
+    if (!ere || !out) return set_err(RRX_ERR_ARG, "null argument");
+    try {
+        std::unique_ptr<rrx_program> p(new rrx_program);
+        p->automaton = compile_ere(ere);
+        p->prog = build_program(p->automaton, ere, !(flags & RRX_COMPILE_NO_REDUCE));
+        *out = p.release();
+        return RRX_OK;
+    } catch (const std::runtime_error& e) {
+        return set_err(RRX_ERR_PARSE, e.what());
+    } catch (const std::bad_alloc&) {
+        return set_err(RRX_ERR_ARG, "out of memory");
+    }
+}
+int rrx_compile(const char* ere, rrx_program** out) { return rrx_compile_ex(ere, RRX_COMPILE_DEFAULT, out); }
+void rrx_program_free(rrx_program* p) { delete p; }
+
+void rrx_program_info(const rrx_program* p, rrx_info* o) {
+    const ProgHeader& h = p->prog.hdr();
+    o->n_raw = h.n_raw;
+    o->ref_width_class = h.ref_width_class;
+    o->n_flat = h.n_flat;
+    o->n_device = h.P;
+    o->words = h.NW;
+    o->nullable = h.nullable;
+    o->n_terms = h.n_terms;
+    o->n_bicliques = h.n_bicl;
+    o->uses_rows = h.use_rows;
+    o->static_closed = (h.static_depth != 0xffffffffu && h.static_depth + 1 <= (uint32_t)ROW_BYTES) ? 1u : 0u;
+}
+
+int64_t rrx_program_flat_table(const rrx_program* p, int which, uint32_t* out, uint64_t cap) {
+    const Automaton& a = p->automaton;
+    const uint32_t P = a.P, W = (P + 31) / 32;
+    uint64_t need = which == 2 ? (uint64_t)P * W : which == 3 ? (uint64_t)P * 4 : W;
+    if (which < 0 || which > 3) return -1;
+    if (!out || cap < need) return -(int64_t)need;
+    if (which == 0) for (uint32_t w = 0; w < W; w++) out[w] = a.first.word(w);
+    if (which == 1) for (uint32_t w = 0; w < W; w++) out[w] = a.accept.word(w);
+    if (which == 2) for (uint32_t k = 0; k < P; k++) for (uint32_t w = 0; w < W; w++) out[(uint64_t)k * W + w] = a.follow[k].word(w);
+    if (which == 3) for (uint32_t k = 0; k < P; k++) {
+        out[k * 4 + 0] = (uint32_t)a.atoms[k].cls[0]; out[k * 4 + 1] = (uint32_t)(a.atoms[k].cls[0] >> 32);
+        out[k * 4 + 2] = (uint32_t)a.atoms[k].cls[1]; out[k * 4 + 3] = (uint32_t)(a.atoms[k].cls[1] >> 32);
+    }
+    return (int64_t)need;
+}
+const uint32_t* rrx_program_blob(const rrx_program* p, uint64_t* n_words) {
+    if (n_words) *n_words = p->prog.blob.size();
+    return p->prog.blob.data();
+}
+int64_t rrx_program_raw_row(const rrx_program* p, uint32_t state, uint32_t byte, uint32_t* out, uint64_t cap) {
+    const Automaton& a = p->automaton;
+    const uint32_t W = (a.n_raw + 31) / 32;
+    if (!out || cap < W) return -(int64_t)W;
+    for (uint32_t w = 0; w < W; w++) out[w] = 0;
+    if (byte >= 128) return W;
+    for (const Atom& at : a.atoms)
+        if (at.pre.has(state) && ((at.cls[byte >> 6] >> (byte & 63)) & 1ull))
+            for (uint32_t w = 0; w < W; w++) out[w] |= at.post.word(w);
+    return W;
+}
+int64_t rrx_program_raw_finals(const rrx_program* p, uint32_t* out, uint64_t cap) {
+    const Automaton& a = p->automaton;
+    const uint32_t W = (a.n_raw + 31) / 32;
+    if (!out || cap < W) return -(int64_t)W;
+    for (uint32_t w = 0; w < W; w++) out[w] = a.raw_finals.word(w);
+    return W;
+}
+
+// ---- scanner ---------------------------------------------------------------------------------------
+void rrx_scanner_free(rrx_scanner* s) {
+    if (!s) return;
+    cudaFree(s->d_prog); cudaFree(s->d_ctrl); cudaFree(s->d_tpay);
+    if (s->owns_out) cudaFree(s->d_out);
+    cudaFree(s->d_shard); cudaFree(s->d_pending);
+    if (s->h_ctr) cudaFreeHost(s->h_ctr);
+    delete s;
+}
+
+int rrx_scanner_create(const rrx_program* p, uint64_t max_len, uint64_t capacity, rrx_scanner** out) {
+    if (!p || !out) return set_err(RRX_ERR_ARG, "null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(RRX_ERR_CUDA, "no CUDA device: librrx has no CPU fallback");
+    std::unique_ptr<rrx_scanner, void (*)(rrx_scanner*)> s(new rrx_scanner, rrx_scanner_free);
+    s->p = p;
+    RRX_CUDA(cudaGetDevice(&s->device));
+    RRX_CUDA(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
+    const ProgHeader& h = p->prog.hdr();
+    s->NW = h.NW;
+    const uint64_t tile_bytes = (uint64_t)rows_per_tile(h.NW) * ROW_BYTES;
+    s->max_len = max_len;
+    s->max_tiles = (max_len + tile_bytes - 1) / tile_bytes;
+    if (s->max_tiles == 0) s->max_tiles = 1;
+    s->capacity = capacity ? capacity : 1;
+    RRX_CUDA(cudaMalloc(&s->d_prog, p->prog.blob.size() * 4));
+    RRX_CUDA(cudaMemcpy(s->d_prog, p->prog.blob.data(), p->prog.blob.size() * 4, cudaMemcpyHostToDevice));
+    s->ctrl_bytes = 32 + s->max_tiles * 4 + 8 + s->max_tiles * 8;
+    RRX_CUDA(cudaMalloc(&s->d_ctrl, s->ctrl_bytes));
+    RRX_CUDA(cudaMalloc(&s->d_tpay, s->max_tiles * 2 * (1 + 3 * (size_t)h.NW) * 4));
+    RRX_CUDA(cudaMalloc(&s->d_out, s->capacity * 16));
+    RRX_CUDA(cudaMalloc(&s->d_shard, (1 + 3 * (size_t)h.NW) * 4));
+    RRX_CUDA(cudaMalloc(&s->d_pending, sizeof(PendingStart) * s->pending_cap));
+    RRX_CUDA(cudaMallocHost(&s->h_ctr, 32));
+    *out = s.release();
+    return RRX_OK;
+}
+
+int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64_t base_offset,
+                     const rrx_scan_opts* opts, void* stream) {
+    if (!s || (!d_text && len)) return set_err(RRX_ERR_ARG, "null argument");
+    if (len > s->max_len) return set_err(RRX_ERR_ARG, "text longer than the scanner was created for");
+    if (((uintptr_t)d_text) & 15) return set_err(RRX_ERR_ARG, "device text pointer must be 16-byte aligned");
+    if (opts && opts->mode != RRX_MODE_LAZY_V1) return set_err(RRX_ERR_UNSUPPORTED, "only RRX_MODE_LAZY_V1 is implemented on the device");
+    cudaStream_t st = (cudaStream_t)stream;
+    const ProgHeader& h = s->p->prog.hdr();
+    const uint64_t tile_bytes = (uint64_t)rows_per_tile(h.NW) * ROW_BYTES;
+    ScanParams sp;
+    std::memset(&sp, 0, sizeof(sp));
+    sp.text = d_text;
+    sp.len = len;
+    sp.left_ctx = opts ? opts->left_context : 0;
+    sp.base = (int64_t)base_offset;
+    sp.prog = s->d_prog;
+    sp.num_tiles = (uint32_t)((len + tile_bytes - 1) / tile_bytes);
+    sp.static_closed = (h.static_depth != 0xffffffffu && h.static_depth + 1 <= (uint32_t)ROW_BYTES) ? 1u : 0u;
+    uint8_t* c = s->d_ctrl;
+    sp.ticket = reinterpret_cast<uint32_t*>(c);
+    sp.err = reinterpret_cast<uint32_t*>(c + 4);
+    sp.total = reinterpret_cast<unsigned long long*>(c + 8);
+    sp.tflag = reinterpret_cast<volatile uint32_t*>(c + 32);
+    size_t off = 32 + s->max_tiles * 4;
+    off = (off + 7) & ~(size_t)7;
+    sp.cstatus = reinterpret_cast<volatile unsigned long long*>(c + off);
+    sp.tpay = s->d_tpay;
+    sp.out = s->d_out;
+    sp.out_cap = s->capacity;
+    sp.shard_comp = s->d_shard;
+    sp.pending = s->d_pending;
+    sp.pending_cap = s->pending_cap;
+    if (opts && opts->entry) for (uint32_t w = 0; w < h.NW; w++) sp.entry[w] = opts->entry[w];
+    s->launches = 0;
+    RRX_CUDA(cudaMemsetAsync(s->d_ctrl, 0, 32 + (size_t)sp.num_tiles * 4, st));
+    RRX_CUDA(cudaMemsetAsync(c + off, 0, (size_t)sp.num_tiles * 8, st));
+    if (sp.num_tiles == 0) {
+        // empty text: identity transfer function, no matches
+        uint32_t ident[1 + 3 * RRX_NW_MAX] = {K_IDENT};
+        RRX_CUDA(cudaMemcpyAsync(s->d_shard, ident, (1 + 3 * (size_t)h.NW) * 4, cudaMemcpyHostToDevice, st));
+        return RRX_OK;
+    }
+    int grid = 0;
+    cudaError_t e = launch_scan(sp, h, s->sm_count, st, &grid);
+    if (e != cudaSuccess) return cuda_err(e, "rrx_scan_kernel launch");
+    s->launches = 1;
+    return RRX_OK;
+}
+
+int rrx_scanner_result(rrx_scanner* s, rrx_scan_result* out, void* stream) {
+    if (!s || !out) return set_err(RRX_ERR_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    RRX_CUDA(cudaMemcpyAsync(s->h_ctr, s->d_ctrl, 32, cudaMemcpyDeviceToHost, st));
+    RRX_CUDA(cudaStreamSynchronize(st));
+    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(s->h_ctr);
+    out->error_bits = w32[1];
+    out->n_matches = s->h_ctr[1];
+    out->n_pending = s->h_ctr[2];
+    out->capacity = s->capacity;
+    out->launches = s->launches;
+    out->d_matches = reinterpret_cast<const int64_t*>(s->d_out);
+    return RRX_OK;
+}
+
+int rrx_scanner_shard_summary(rrx_scanner* s, uint32_t* out, uint64_t cap_words, void* stream) {
+    const size_t n = 1 + 3 * (size_t)s->NW;
+    if (!out || cap_words < n) return set_err(RRX_ERR_ARG, "summary buffer too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    RRX_CUDA(cudaMemcpyAsync(out, s->d_shard, n * 4, cudaMemcpyDeviceToHost, st));
+    RRX_CUDA(cudaStreamSynchronize(st));
+    return RRX_OK;
+}
+
+// ---- one-shot convenience calls ----------------------------------------------------------------------
+int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, uint64_t base_offset,
+                    int mode, rrx_matches** out, void* stream) {
+    if (!p || !out) return set_err(RRX_ERR_ARG, "null argument");
+    if (mode != RRX_MODE_LAZY_V1) return set_err(RRX_ERR_UNSUPPORTED, "only RRX_MODE_LAZY_V1 is implemented on the device");
+    uint64_t cap = len / 64 + 1024;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        rrx_scanner* s = nullptr;
+        int rc = rrx_scanner_create(p, len, cap, &s);
+        if (rc) return rc;
+        rrx_scan_opts o;
+        std::memset(&o, 0, sizeof(o));
+        rc = rrx_scanner_scan(s, d_text, len, base_offset, &o, stream);
+        rrx_scan_result r;
+        if (!rc) rc = rrx_scanner_result(s, &r, stream);
+        if (rc) { rrx_scanner_free(s); return rc; }
+        if (r.error_bits) {
+            rrx_scanner_free(s);
+            return set_err(RRX_ERR_CUDA, "scan kernel reported error bits " + std::to_string(r.error_bits));
+        }
+        if (r.n_matches <= r.capacity) {
+            rrx_matches* m = new rrx_matches;
+            m->count = r.n_matches;
+            m->d_pairs = s->d_out;
+            s->owns_out = false;
+            rrx_scanner_free(s);
+            *out = m;
+            return RRX_OK;
+        }
+        cap = r.n_matches;          // exact size known now: scan again
+        rrx_scanner_free(s);
+    }
+    return set_err(RRX_ERR_CUDA, "match buffer overflow after resize");
+}
+
+int rrx_scan_host(const rrx_program* p, const uint8_t* text, uint64_t len, uint64_t base_offset,
+                  int mode, rrx_matches** out) {
+    if (!p || !out || (!text && len)) return set_err(RRX_ERR_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_err(RRX_ERR_CUDA, "no CUDA device: librrx has no CPU fallback");
+    uint8_t* d = nullptr;
+    RRX_CUDA(cudaMalloc(&d, len + 16));
+    cudaError_t e = cudaMemcpy(d, text, len, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); return cuda_err(e, "cudaMemcpy H2D"); }
+    int rc = rrx_scan_device(p, d, len, base_offset, mode, out, nullptr);
+    cudaFree(d);
+    return rc;
+}
+
+uint64_t rrx_matches_count(const rrx_matches* m) { return m ? m->count : 0; }
+const int64_t* rrx_matches_device_data(const rrx_matches* m) { return reinterpret_cast<const int64_t*>(m->d_pairs); }
+const int64_t* rrx_matches_data(rrx_matches* m) {
+    if (!m) return nullptr;
+    if (!m->host_valid) {
+        m->host.resize(2 * m->count + 2);
+        if (m->count) {
+            cudaError_t e = cudaMemcpy(m->host.data(), m->d_pairs, m->count * 16, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { cuda_err(e, "cudaMemcpy D2H"); return nullptr; }
+        }
+        m->host_valid = true;
+    }
+    return m->host.data();
+}
+void rrx_matches_free(rrx_matches* m) {
+    if (!m) return;
+    cudaFree(m->d_pairs);
+    delete m;
+}
+
+int rrx_corpus_iid_device(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, const uint8_t alpha[256], void* stream) {
+    cudaError_t e = launch_corpus_iid(d_out, offset, len, seed, alpha, (cudaStream_t)stream);
+    return e == cudaSuccess ? RRX_OK : cuda_err(e, "corpus_iid");
+}
+int rrx_corpus_records_device(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, void* stream) {
+    cudaError_t e = launch_corpus_records(d_out, offset, len, seed, (cudaStream_t)stream);
+    return e == cudaSuccess ? RRX_OK : cuda_err(e, "corpus_records");
+}
+
+}  // extern "C"

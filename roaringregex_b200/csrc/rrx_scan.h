@@ -1,0 +1,14 @@
+// Internal interface between the C ABI (rrx_capi.cu) and the kernels (rrx_scan.cu, rrx_corpus.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rrx_compile.h"
+
+namespace rrx {
+struct ScanParams;
+int rows_per_tile(uint32_t NW);
+cudaError_t launch_scan(const ScanParams& sp, const ProgHeader& h, int sm_count, cudaStream_t st, int* grid_out);
+cudaError_t launch_corpus_iid(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, const uint8_t* alpha256, cudaStream_t st);
+cudaError_t launch_corpus_records(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, cudaStream_t st);
+}  // namespace rrx

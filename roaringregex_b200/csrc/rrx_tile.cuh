@@ -1,0 +1,740 @@
+// Per-tile scan logic of the rrx kernels, written as phase functions over an explicit
+// shared-memory state so that
+//   * rrx_scan.cu runs them on the GPU (one CTA per tile, __syncthreads() between phases), and
+//   * tests/emu/rrx_emu.cc compiles the SAME functions for the host (-DRRX_HOST_EMU) and steps the
+//     phases thread by thread.  The emulator is test infrastructure only: it lets the CPU-only CI
+//     exercise the chunk-stitching logic (summaries, look-back, fix-up, start scans) bit for bit;
+//     librrx.so neither contains nor calls it.
+//
+// Hot path replaced (reference file:line):
+//   NFA.cc:72-102   Processor::shift<fwd>      -> step(): S' = (follow'(S) | first) & B[c]
+//   NFA.cc:103-107  Processor::operator*       -> any(S & accept) / any(R & first)
+//   regex.h:156-162 AcceptanceIterator loop    -> row scans (one 128-byte row per thread)
+//   Iterator.cpp    (empty: the lazy iterator) -> LAZY-v1 enumeration, SURVEY.md Appendix D
+//
+// Text geometry: the corpus is cut into ROWS of 128 bytes; a TILE is `ROWS` consecutive rows
+// (one per thread) plus the row before it (halo, for backward start scans).
+#pragma once
+#include <stdint.h>
+
+#include "rrx_compile.h"   // ProgHeader, TERM_*, RRX_MAX_*
+
+#if defined(__CUDACC__) && !defined(RRX_HOST_EMU)
+#define RRX_DEV __device__ __forceinline__
+#define RRX_DEVN __device__ __noinline__
+#else
+#define RRX_DEV inline
+#define RRX_DEVN inline
+#endif
+
+#ifdef RRX_HOST_EMU
+struct uint4 { uint32_t x, y, z, w; };
+inline uint32_t atomicOr(uint32_t* p, uint32_t v) { uint32_t o = *p; *p |= v; return o; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+#endif
+
+namespace rrx {
+
+constexpr int ROW_BYTES = 128;
+constexpr int ROW_SHIFT = 7;
+
+// error bits reported by the kernel
+enum : uint32_t {
+    ERR_PENDING_OVERFLOW = 2u,
+};
+// Kinds of chunk transfer functions S_out = A*S_in | b:
+//   K_CLOSED  A = 0: the exit does not depend on the entry
+//   K_RANK1   A = U x P^T: exit = b | (entry meets P ? U : 0)
+//   K_IDENT   empty chunk
+//   K_HARD    (rows only) survivors reach the row end without ever collapsing to one position:
+//             A is not representable here; such a row is replayed from its exact entry instead
+//   K_WAIT    (tile aggregates only) the tile could not summarise itself: successors wait for
+//             its inclusive state
+// K_OPAQUE marks a closed composite whose b was computed for the entry set actually used (it is
+// not valid as a function of other entries); only inclusive composites can carry it.
+enum : uint32_t { K_CLOSED = 0, K_RANK1 = 1, K_IDENT = 2, K_HARD = 3, K_WAIT = 4, K_TYPE = 0xffu, K_OPAQUE = 0x100u };
+
+#if defined(__CUDA_ARCH__) && !defined(RRX_HOST_EMU)
+RRX_DEV uint32_t rotl32(uint32_t x, uint32_t r) { return __funnelshift_l(x, x, r); }
+RRX_DEV uint32_t fshl(uint32_t lo, uint32_t hi, uint32_t r) { return __funnelshift_l(lo, hi, r); }   // (hi:lo << r) >> 32
+RRX_DEV uint32_t fshr(uint32_t lo, uint32_t hi, uint32_t r) { return __funnelshift_r(lo, hi, r); }   // (hi:lo >> r) & 0xffffffff
+RRX_DEV int popc32(uint32_t x) { return __popc(x); }
+RRX_DEV int ctz32(uint32_t x) { return __ffs((int)x) - 1; }
+#else
+RRX_DEV uint32_t rotl32(uint32_t x, uint32_t r) { r &= 31; return r ? (x << r) | (x >> (32 - r)) : x; }
+RRX_DEV uint32_t fshl(uint32_t lo, uint32_t hi, uint32_t r) { r &= 31; return r ? (hi << r) | (lo >> (32 - r)) : hi; }
+RRX_DEV uint32_t fshr(uint32_t lo, uint32_t hi, uint32_t r) { r &= 31; return r ? (lo >> r) | (hi << (32 - r)) : lo; }
+RRX_DEV int popc32(uint32_t x) { return __builtin_popcount(x); }
+RRX_DEV int ctz32(uint32_t x) { return __builtin_ctz(x); }
+#endif
+
+// ---- small fixed-width set helpers ---------------------------------------------------------------
+template <int NW> RRX_DEV bool any_w(const uint32_t* a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) o |= a[w];
+    return o != 0;
+}
+template <int NW> RRX_DEV bool meets(const uint32_t* a, const uint32_t* b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) o |= a[w] & b[w];
+    return o != 0;
+}
+template <int NW> RRX_DEV int popc_w(const uint32_t* a) {
+    int c = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) c += popc32(a[w]);
+    return c;
+}
+
+// ---- program view ----------------------------------------------------------------------------------
+// The "small" part of the program blob (everything before the byte table) is copied to shared
+// memory once per CTA; the byte table gets its own (bank-conflict-free) layout; the per-source
+// row tables stay in global memory (only irregular automata use them).
+struct ProgView {
+    const uint32_t* sm;        // shared copy of blob[0 .. off_B)
+    const uint32_t* glob;      // the blob in global memory
+    const uint32_t* Btab;      // shared byte table
+    uint32_t btab_stride;      // words between consecutive bytes' entries
+    uint32_t btab_lane;        // this thread's word offset inside an entry (NW==1: lane id)
+    RRX_DEV const ProgHeader& h() const { return *reinterpret_cast<const ProgHeader*>(sm); }
+};
+
+template <int NW> RRX_DEV void load_B(const ProgView& pv, uint32_t c, uint32_t* out) {
+    const uint32_t* e = pv.Btab + c * pv.btab_stride + pv.btab_lane;
+#pragma unroll
+    for (int w = 0; w < NW; w++) out[w] = e[w];
+}
+
+// f = follow'(S) through a decomposition (shift terms, bicliques, rows) read from shared memory.
+template <int NW>
+RRX_DEV void follow_terms(const ProgView& pv, const uint32_t* terms, uint32_t n_terms, const uint32_t* bicl,
+                          uint32_t n_bicl, uint32_t use_rows, const uint32_t* rowsrc, const uint32_t* rows_g,
+                          const uint32_t* S, uint32_t* f) {
+#pragma unroll
+    for (int w = 0; w < NW; w++) f[w] = 0;
+    for (uint32_t t = 0; t < n_terms; t++) {
+        const uint32_t* tp = terms + t * (1 + NW);
+        const uint32_t kind = tp[0] >> 8, r = tp[0] & 0xff;
+        if (NW == 1 || kind == TERM_ROT) {
+            f[0] |= rotl32(S[0], r) & tp[1];
+        } else if (kind == TERM_SELF) {
+#pragma unroll
+            for (int w = 0; w < NW; w++) f[w] |= S[w] & tp[1 + w];
+        } else if (kind == TERM_SHL) {
+#pragma unroll
+            for (int w = 0; w < NW; w++) f[w] |= fshl(w ? S[w - 1] : 0u, S[w], r) & tp[1 + w];
+        } else {
+#pragma unroll
+            for (int w = 0; w < NW; w++) f[w] |= fshr(S[w], w + 1 < NW ? S[w + 1] : 0u, r) & tp[1 + w];
+        }
+    }
+    for (uint32_t b = 0; b < n_bicl; b++) {
+        const uint32_t* bp = bicl + b * 2 * NW;
+        if (meets<NW>(S, bp)) {
+#pragma unroll
+            for (int w = 0; w < NW; w++) f[w] |= bp[NW + w];
+        }
+    }
+    if (use_rows) {
+#pragma unroll 1
+        for (int w = 0; w < NW; w++) {
+            uint32_t v = S[w] & rowsrc[w];
+            while (v) {
+                const uint32_t k = (uint32_t)w * 32u + (uint32_t)ctz32(v);
+                v &= v - 1;
+                const uint32_t* rp = rows_g + k * NW;
+#pragma unroll
+                for (int x = 0; x < NW; x++) f[x] |= rp[x];
+            }
+        }
+    }
+}
+template <int NW> RRX_DEV void follow_fwd(const ProgView& pv, const uint32_t* S, uint32_t* f) {
+    const ProgHeader& h = pv.h();
+    follow_terms<NW>(pv, pv.sm + h.off_terms, h.n_terms, pv.sm + h.off_bicl, h.n_bicl, h.use_rows,
+                     pv.sm + h.off_rowsrc, pv.glob + h.off_rows, S, f);
+}
+template <int NW> RRX_DEV void follow_bwd(const ProgView& pv, const uint32_t* S, uint32_t* f) {
+    const ProgHeader& h = pv.h();
+    follow_terms<NW>(pv, pv.sm + h.off_rterms, h.n_rterms, pv.sm + h.off_rbicl, h.n_rbicl, h.use_rrows,
+                     pv.sm + h.off_rrowsrc, pv.glob + h.off_rrows, S, f);
+}
+
+// Forward follow policy.  NT >= 0: one-word automaton whose decomposition (NT rotations, NB
+// bicliques) lives in registers; NT < 0: anything, read from shared memory.
+template <int NW, int NT, int NB> struct Fwd {
+    static_assert(NW == 1, "register program is for one-word sets");
+    uint32_t rot[NT > 0 ? NT : 1], msk[NT > 0 ? NT : 1], bsrc[NB > 0 ? NB : 1], bdst[NB > 0 ? NB : 1];
+    uint32_t first_, accept_;
+    RRX_DEV void init(const ProgView& pv) {
+        const ProgHeader& h = pv.h();
+        first_ = pv.sm[h.off_first];
+        accept_ = pv.sm[h.off_accept];
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            const bool live = (uint32_t)t < h.n_terms;
+            rot[t] = live ? (pv.sm[h.off_terms + t * 2] & 0xff) : 0u;
+            msk[t] = live ? pv.sm[h.off_terms + t * 2 + 1] : 0u;
+        }
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            const bool live = (uint32_t)b < h.n_bicl;
+            bsrc[b] = live ? pv.sm[h.off_bicl + b * 2] : 0u;
+            bdst[b] = live ? pv.sm[h.off_bicl + b * 2 + 1] : 0u;
+        }
+    }
+    RRX_DEV uint32_t first(const ProgView&, int) const { return first_; }
+    RRX_DEV uint32_t accept(const ProgView&, int) const { return accept_; }
+    RRX_DEV void follow(const ProgView&, const uint32_t* S, uint32_t* f) const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int t = 0; t < NT; t++) o |= rotl32(S[0], rot[t]) & msk[t];
+#pragma unroll
+        for (int b = 0; b < NB; b++) o |= (S[0] & bsrc[b]) ? bdst[b] : 0u;
+        f[0] = o;
+    }
+};
+template <int NW, int NB> struct Fwd<NW, -1, NB> {
+    RRX_DEV void init(const ProgView&) {}
+    RRX_DEV uint32_t first(const ProgView& pv, int w) const { return pv.sm[pv.h().off_first + w]; }
+    RRX_DEV uint32_t accept(const ProgView& pv, int w) const { return pv.sm[pv.h().off_accept + w]; }
+    RRX_DEV void follow(const ProgView& pv, const uint32_t* S, uint32_t* f) const { follow_fwd<NW>(pv, S, f); }
+};
+
+// ---- composites (rank<=1 chunk transfer functions) ---------------------------------------------------
+template <int NW> struct Comp {
+    uint32_t kind;
+    uint32_t b[NW], U[NW], P[NW];   // exit = b | (entry meets P ? U : 0)   [K_RANK1]
+};
+template <int NW> RRX_DEV void comp_ident(Comp<NW>& c) {
+    c.kind = K_IDENT;
+#pragma unroll
+    for (int w = 0; w < NW; w++) c.b[w] = c.U[w] = c.P[w] = 0;
+}
+// r = "x first, then y".  y is never K_HARD/K_WAIT here; x neither.
+template <int NW> RRX_DEV void comp_compose(const Comp<NW>& x, const Comp<NW>& y, Comp<NW>& r) {
+    const uint32_t xt = x.kind & K_TYPE, yt = y.kind & K_TYPE;
+    if (yt == K_CLOSED || xt == K_IDENT) { r = y; return; }
+    if (yt == K_IDENT) { r = x; return; }
+    // y is rank 1, x is closed or rank 1
+    const bool hit_b = meets<NW>(x.b, y.P);
+    const bool hit_U = xt == K_RANK1 && meets<NW>(x.U, y.P);
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        r.b[w] = y.b[w] | (hit_b ? y.U[w] : 0u);
+        r.U[w] = hit_U ? y.U[w] : 0u;
+        r.P[w] = hit_U ? x.P[w] : 0u;
+    }
+    r.kind = (hit_U ? K_RANK1 : K_CLOSED) | (x.kind & K_OPAQUE);
+}
+template <int NW> RRX_DEV void comp_apply(const Comp<NW>& c, const uint32_t* entry, uint32_t* out) {
+    const uint32_t ct = c.kind & K_TYPE;
+    if (ct == K_IDENT) {
+#pragma unroll
+        for (int w = 0; w < NW; w++) out[w] = entry[w];
+        return;
+    }
+    const bool hit = ct == K_RANK1 && meets<NW>(entry, c.P);
+#pragma unroll
+    for (int w = 0; w < NW; w++) out[w] = c.b[w] | (hit ? c.U[w] : 0u);
+}
+template <int NW> RRX_DEV void comp_closed(Comp<NW>& c, const uint32_t* b, uint32_t flags) {
+    c.kind = K_CLOSED | flags;
+#pragma unroll
+    for (int w = 0; w < NW; w++) { c.b[w] = b[w]; c.U[w] = 0; c.P[w] = 0; }
+}
+
+// ---- scan parameters (kernel argument) ------------------------------------------------------------
+constexpr int RRX_NW_MAX = 32;
+struct PendingStart {           // a start scan that ran off the left edge of the available text
+    uint64_t match_index;       // slot in the output list
+    int64_t next_offset;        // shard-local offset of the next byte to consume (negative)
+    uint32_t R[RRX_NW_MAX];     // backward set before consuming that byte
+};
+struct ScanParams {
+    const uint8_t* text;        // shard bytes; text[-left_ctx .. len) is readable
+    uint64_t len;
+    uint64_t left_ctx;
+    int64_t base;               // global offset of text[0]
+    const uint32_t* prog;       // program blob (global memory)
+    uint32_t num_tiles;
+    uint32_t static_closed;     // 1: every row is closed by construction (acyclic E', depth < ROW_BYTES)
+    uint32_t* ticket;
+    volatile uint32_t* tflag;   // [num_tiles] 0 none, 1 aggregate, 2 inclusive
+    uint32_t* tpay;             // [num_tiles][2][1+3*NW] composites (aggregate, inclusive)
+    volatile unsigned long long* cstatus;   // [num_tiles] (flag<<62)|count
+    long long* out;             // (start,end) pairs
+    uint64_t out_cap;
+    unsigned long long* total;  // [0] match count, [1] pending count
+    uint32_t* err;
+    uint32_t* shard_comp;       // [1+3*NW] composite of the whole shard (relative to an unknown entry)
+    PendingStart* pending;
+    uint32_t pending_cap;
+    uint32_t entry[RRX_NW_MAX]; // forward set carried into text[0]
+};
+
+// ---- shared-memory state of one CTA ------------------------------------------------------------------
+template <int NW, int ROWS> struct TileState {
+    uint8_t* text;        // (ROWS+1) rows of 128 B; 16-byte chunk j of smem row s sits at chunk j^(s&7)
+    uint32_t* sum_b;      // [NW][ROWS]   exit of the row scanned from the empty set
+    uint32_t* sum_U;      // [NW][ROWS]   (open rows) survivors at the row end / prefix composite U
+    uint32_t* sum_P;      // [NW][ROWS]   (open rows) entry states that feed the survivor
+    uint32_t* sum_kind;   // [ROWS]
+    uint32_t* hits;       // [4][ROWS]    one bit per byte of the row: a match ends after that byte
+    uint32_t* cnt;        // [ROWS]       matches per row -> exclusive offsets
+    uint32_t* misc;       // see M_* below
+    // geometry of the current tile
+    uint64_t row0;        // first row of the tile
+    int64_t smem_lo;      // shard-local offset of the first valid byte held in `text`
+    static constexpr int M_TILE = 0, M_ANYOPEN = 1, M_TOTAL = 2, M_BASE_LO = 3, M_BASE_HI = 4, M_ENTRY = 8;
+    static constexpr int MISC_WORDS = 8 + NW;
+    static constexpr size_t bytes() {
+        return (size_t)(ROWS + 1) * ROW_BYTES + sizeof(uint32_t) * ((size_t)3 * NW * ROWS + 6 * ROWS + MISC_WORDS);
+    }
+    RRX_DEV void carve(uint8_t* base) {
+        text = base;
+        uint32_t* p = reinterpret_cast<uint32_t*>(base + (size_t)(ROWS + 1) * ROW_BYTES);
+        sum_b = p; p += NW * ROWS;
+        sum_U = p; p += NW * ROWS;
+        sum_P = p; p += NW * ROWS;
+        sum_kind = p; p += ROWS;
+        hits = p; p += 4 * ROWS;
+        cnt = p; p += ROWS;
+        misc = p;
+    }
+    // byte at shard-local offset g, which must lie inside the staged window
+    RRX_DEV uint32_t smem_byte(int64_t g) const {
+        const int64_t rel = g - ((int64_t)row0 - 1) * ROW_BYTES;
+        const uint32_t s = (uint32_t)(rel >> ROW_SHIFT), col = (uint32_t)rel & (ROW_BYTES - 1);
+        return text[s * ROW_BYTES + ((((col >> 4) ^ (s & 7)) << 4) | (col & 15))];
+    }
+    RRX_DEV const uint8_t* row_ptr(int t) const { return text + (size_t)(t + 1) * ROW_BYTES; }
+    RRX_DEV uint32_t row_byte(int t, int p) const {
+        const uint32_t s = (uint32_t)t + 1;
+        return text[s * ROW_BYTES + (((((uint32_t)p >> 4) ^ (s & 7)) << 4) | ((uint32_t)p & 15))];
+    }
+};
+
+// Number of valid bytes of row `t` of the tile starting at row0.
+RRX_DEV int row_nbytes(const ScanParams& sp, uint64_t row0, int t) {
+    const uint64_t lo = (row0 + (uint64_t)t) << ROW_SHIFT;
+    if (lo >= sp.len) return 0;
+    const uint64_t rem = sp.len - lo;
+    return rem >= ROW_BYTES ? ROW_BYTES : (int)rem;
+}
+
+// ===== phase A: per-row scan from the empty set (+ openness analysis) ===============================
+template <int NW, int ROWS, class F>
+RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, ROWS>& ts, int t) {
+    const ProgHeader& h = pv.h();
+    const int nb = row_nbytes(sp, ts.row0, t);
+    uint32_t kind = nb ? K_CLOSED : K_IDENT;
+    uint32_t Bc[NW], f[NW];
+
+    // (1) survivor scan: U = all positions, no injection.  Dead before the row ends => the row's
+    //     exit does not depend on its entry (closed).  Otherwise remember the first point where
+    //     exactly one survivor is left: from there on the row acts as a rank-1 map.
+    if (nb && !sp.static_closed) {
+        uint32_t U[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) U[w] = pv.sm[h.off_all + w];
+        int pc = -1;
+        uint32_t J[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) J[w] = 0;
+        int p = 0;
+        for (; p < nb; p++) {
+            load_B<NW>(pv, ts.row_byte(t, p), Bc);
+            fw.follow(pv, U, f);
+#pragma unroll
+            for (int w = 0; w < NW; w++) U[w] = f[w] & Bc[w];
+            if (!any_w<NW>(U)) break;
+            if (pc < 0 && popc_w<NW>(U) == 1) {
+                pc = p + 1;
+#pragma unroll
+                for (int w = 0; w < NW; w++) J[w] = U[w];
+            }
+        }
+        if (p >= nb) {                       // survivors reach the end of the row: open
+            kind = pc < 0 ? K_HARD : K_RANK1;
+            uint32_t R[NW];
+#pragma unroll
+            for (int w = 0; w < NW; w++) R[w] = J[w];
+            if (pc >= 0) {
+                // entry states that lead to the lone survivor: walk the prefix backwards
+                for (int q = pc - 1; q >= 0; q--) {
+                    load_B<NW>(pv, ts.row_byte(t, q), Bc);
+                    uint32_t x[NW];
+#pragma unroll
+                    for (int w = 0; w < NW; w++) x[w] = R[w] & Bc[w];
+                    follow_bwd<NW>(pv, x, R);
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                ts.sum_U[w * ROWS + t] = U[w];
+                ts.sum_P[w * ROWS + t] = R[w];
+            }
+        }
+    }
+
+    // (2) the scan proper, from the empty set, with re-injection; record ends of matches.
+    uint32_t S[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) S[w] = 0;
+    uint32_t hit[4] = {0, 0, 0, 0};
+    if (nb == ROW_BYTES) {
+        const uint32_t s = (uint32_t)t + 1;
+        const uint4* rowv = reinterpret_cast<const uint4*>(ts.text + (size_t)s * ROW_BYTES);
+#pragma unroll 1
+        for (int g = 0; g < 8; g++) {
+            const uint4 v = rowv[g ^ (s & 7)];
+            const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+            uint32_t S0[NW], acc = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) S0[w] = S[w];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const uint32_t c = (wd[i >> 2] >> (8 * (i & 3))) & 0xffu;
+                load_B<NW>(pv, c, Bc);
+                fw.follow(pv, S, f);
+#pragma unroll
+                for (int w = 0; w < NW; w++) {
+                    S[w] = (f[w] | fw.first(pv, w)) & Bc[w];
+                    acc |= S[w] & fw.accept(pv, w);
+                }
+            }
+            if (acc) {        // rare: replay the 16 bytes to find which of them end a match
+#pragma unroll
+                for (int w = 0; w < NW; w++) S[w] = S0[w];
+#pragma unroll 1
+                for (int i = 0; i < 16; i++) {
+                    const uint32_t c = (wd[i >> 2] >> (8 * (i & 3))) & 0xffu;
+                    load_B<NW>(pv, c, Bc);
+                    fw.follow(pv, S, f);
+#pragma unroll
+                    uint32_t a2 = 0;
+#pragma unroll
+                    for (int w = 0; w < NW; w++) {
+                        S[w] = (f[w] | fw.first(pv, w)) & Bc[w];
+                        a2 |= S[w] & fw.accept(pv, w);
+                    }
+                    if (a2) hit[g >> 1] |= 1u << ((g & 1) * 16 + i);
+                }
+            }
+        }
+    } else {
+        for (int p = 0; p < nb; p++) {
+            load_B<NW>(pv, ts.row_byte(t, p), Bc);
+            fw.follow(pv, S, f);
+#pragma unroll
+            uint32_t a2 = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                S[w] = (f[w] | fw.first(pv, w)) & Bc[w];
+                a2 |= S[w] & fw.accept(pv, w);
+            }
+            if (a2) hit[p >> 5] |= 1u << (p & 31);
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < NW; w++) ts.sum_b[w * ROWS + t] = S[w];
+    ts.sum_kind[t] = kind;
+#pragma unroll
+    for (int q = 0; q < 4; q++) ts.hits[q * ROWS + t] = hit[q];
+}
+
+template <int NW, int ROWS> RRX_DEV void load_row_comp(const TileState<NW, ROWS>& ts, int t, Comp<NW>& c) {
+    c.kind = ts.sum_kind[t];
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        c.b[w] = ts.sum_b[w * ROWS + t];
+        c.U[w] = (c.kind & K_TYPE) == K_RANK1 ? ts.sum_U[w * ROWS + t] : 0u;
+        c.P[w] = (c.kind & K_TYPE) == K_RANK1 ? ts.sum_P[w * ROWS + t] : 0u;
+    }
+}
+template <int NW, int ROWS> RRX_DEV void store_row_comp(TileState<NW, ROWS>& ts, int t, const Comp<NW>& c) {
+    ts.sum_kind[t] = c.kind;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        ts.sum_b[w * ROWS + t] = c.b[w];
+        ts.sum_U[w * ROWS + t] = c.U[w];
+        ts.sum_P[w * ROWS + t] = c.P[w];
+    }
+}
+template <int NW> RRX_DEV void store_comp_global(uint32_t* dst, const Comp<NW>& c) {
+    dst[0] = c.kind;
+#pragma unroll
+    for (int w = 0; w < NW; w++) { dst[1 + w] = c.b[w]; dst[1 + NW + w] = c.U[w]; dst[1 + 2 * NW + w] = c.P[w]; }
+}
+template <int NW> RRX_DEV void load_comp_global(const uint32_t* src, Comp<NW>& c) {
+    const volatile uint32_t* v = src;
+    c.kind = v[0];
+#pragma unroll
+    for (int w = 0; w < NW; w++) { c.b[w] = v[1 + w]; c.U[w] = v[1 + NW + w]; c.P[w] = v[1 + 2 * NW + w]; }
+}
+
+RRX_DEV void rrx_fence() {
+#if defined(__CUDA_ARCH__) && !defined(RRX_HOST_EMU)
+    __threadfence();
+#endif
+}
+RRX_DEV void rrx_backoff() {
+#if defined(__CUDA_ARCH__) && !defined(RRX_HOST_EMU)
+    __nanosleep(64);
+#endif
+}
+
+// Exit of the no-injection replay of row t from the exact entry set X (in place).
+template <int NW, int ROWS, class F>
+RRX_DEV void row_replay_exit(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW, ROWS>& ts, int t,
+                             uint32_t* X) {
+    const int nb = row_nbytes(sp, ts.row0, t);
+    uint32_t Bc[NW], f[NW];
+    for (int p = 0; p < nb && any_w<NW>(X); p++) {
+        load_B<NW>(pv, ts.row_byte(t, p), Bc);
+        fw.follow(pv, X, f);
+#pragma unroll
+        for (int w = 0; w < NW; w++) X[w] = f[w] & Bc[w];
+    }
+}
+
+// ===== phase S (one thread): compose the rows, publish the tile, look back for the tile's entry =====
+// After this phase sum_* of row t hold the composite of rows [0,t) of the tile (what turns the
+// tile entry into row t's entry) and misc[M_ENTRY..] holds the tile's exact entry set.
+template <int NW, int ROWS, class F>
+RRX_DEV void phase_s(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, ROWS>& ts, uint32_t tile,
+                     bool any_open) {
+    Comp<NW> run, rowc, nxt, pre_block;
+    comp_ident(run);
+    comp_ident(pre_block);
+    int blocked_from = -1, resume_at = ROWS;
+    bool wait_agg = false;
+    if (any_open) {
+        for (int t = 0; t < ROWS; t++) {
+            if (blocked_from >= 0 && t < resume_at) continue;     // inside the blocked segment
+            load_row_comp(ts, t, rowc);
+            if ((rowc.kind & K_TYPE) == K_HARD && (run.kind & K_TYPE) != K_CLOSED) {
+                // A row we cannot summarise, reached with a state that still depends on the tile
+                // entry.  Everything up to the next closed row has to wait for the look-back.
+                blocked_from = t;
+                pre_block = run;
+                int c = -1;
+                for (int u = t + 1; u < ROWS; u++) if ((ts.sum_kind[u] & K_TYPE) == K_CLOSED) { c = u; break; }
+                if (c < 0) { wait_agg = true; resume_at = ROWS; break; }
+                resume_at = c + 1;
+                uint32_t bc[NW];
+#pragma unroll
+                for (int w = 0; w < NW; w++) bc[w] = ts.sum_b[w * ROWS + c];
+                comp_closed(run, bc, 0);
+                continue;
+            }
+            store_row_comp(ts, t, run);
+            if ((rowc.kind & K_TYPE) == K_HARD) {                  // exact state: replay the row
+                uint32_t X[NW];
+#pragma unroll
+                for (int w = 0; w < NW; w++) X[w] = run.b[w];
+                row_replay_exit<NW, ROWS>(sp, pv, fw, ts, t, X);
+#pragma unroll
+                for (int w = 0; w < NW; w++) X[w] |= rowc.b[w];
+                comp_closed(run, X, run.kind & K_OPAQUE);
+            } else {
+                comp_compose(run, rowc, nxt);
+                run = nxt;
+            }
+        }
+    } else {
+        // every row closed (or empty, at the very end of the shard): row t's entry is the exit of
+        // the row before it; nothing to rewrite, only the tile aggregate is needed.
+        int last = -1;
+        for (int t = ROWS - 1; t >= 0; t--) if (ts.sum_kind[t] != K_IDENT) { last = t; break; }
+        if (last >= 0) load_row_comp(ts, last, run);
+    }
+    if (wait_agg) run.kind = K_WAIT;
+    const size_t stride = 2 * (size_t)(1 + 3 * NW);
+    uint32_t* mine = sp.tpay + (size_t)tile * stride;
+    // aggregate first, so that successors can start looking back
+    store_comp_global<NW>(mine, run);
+    rrx_fence();
+    if (tile > 0) sp.tflag[tile] = 1;
+    // look back
+    Comp<NW> acc;
+    comp_ident(acc);
+    for (int64_t j = (int64_t)tile - 1; j >= 0; j--) {
+        uint32_t fl;
+        while ((fl = sp.tflag[j]) == 0) rrx_backoff();
+        rrx_fence();
+        Comp<NW> x;
+        if (fl == 1) {
+            load_comp_global<NW>(sp.tpay + (size_t)j * stride, x);
+            if ((x.kind & K_TYPE) == K_WAIT) {
+                while (sp.tflag[j] != 2) rrx_backoff();
+                rrx_fence();
+                fl = 2;
+            }
+        }
+        if (fl == 2) load_comp_global<NW>(sp.tpay + (size_t)j * stride + (1 + 3 * NW), x);
+        comp_compose(x, acc, nxt);
+        acc = nxt;
+        if (fl == 2 || (acc.kind & K_TYPE) == K_CLOSED) break;
+    }
+    uint32_t E[NW];
+    comp_apply<NW>(acc, sp.entry, E);
+#pragma unroll
+    for (int w = 0; w < NW; w++) ts.misc[TileState<NW, ROWS>::M_ENTRY + w] = E[w];
+    if (blocked_from >= 0) {
+        // second stage: walk the blocked segment with exact states
+        uint32_t X[NW], Y[NW];
+        comp_apply<NW>(pre_block, E, X);
+        Comp<NW> ex;
+        for (int t = blocked_from; t < resume_at; t++) {
+            load_row_comp(ts, t, rowc);
+            comp_closed(ex, X, 0);
+            store_row_comp(ts, t, ex);
+            const uint32_t rt = rowc.kind & K_TYPE;
+            if (rt == K_HARD) {
+#pragma unroll
+                for (int w = 0; w < NW; w++) Y[w] = X[w];
+                row_replay_exit<NW, ROWS>(sp, pv, fw, ts, t, Y);
+#pragma unroll
+                for (int w = 0; w < NW; w++) X[w] = Y[w] | rowc.b[w];
+            } else {
+                comp_apply<NW>(rowc, X, Y);
+#pragma unroll
+                for (int w = 0; w < NW; w++) X[w] = Y[w];
+            }
+        }
+        if (wait_agg) comp_closed(nxt, X, K_OPAQUE);
+    }
+    if (!wait_agg) comp_compose(acc, run, nxt);   // inclusive composite (relative to the shard entry)
+    store_comp_global<NW>(mine + (1 + 3 * NW), nxt);
+    rrx_fence();
+    sp.tflag[tile] = 2;
+    if (tile + 1 == sp.num_tiles) store_comp_global<NW>(sp.shard_comp, nxt);
+}
+
+// ===== phase B: replay each row's prefix from its exact entry set (no injection) ====================
+template <int NW, int ROWS, class F>
+RRX_DEV void phase_b(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, ROWS>& ts, int t,
+                     bool any_open) {
+    const int nb = row_nbytes(sp, ts.row0, t);
+    uint32_t X[NW], Bc[NW], f[NW];
+    const uint32_t* E = ts.misc + TileState<NW, ROWS>::M_ENTRY;
+    if (any_open) {
+        Comp<NW> pre;
+        load_row_comp(ts, t, pre);
+        comp_apply<NW>(pre, E, X);
+    } else if (t == 0) {
+#pragma unroll
+        for (int w = 0; w < NW; w++) X[w] = E[w];
+    } else {
+#pragma unroll
+        for (int w = 0; w < NW; w++) X[w] = ts.sum_b[w * ROWS + (t - 1)];
+    }
+    uint32_t hit[4] = {0, 0, 0, 0};
+    bool touched = false;
+    for (int p = 0; p < nb && any_w<NW>(X); p++) {
+        load_B<NW>(pv, ts.row_byte(t, p), Bc);
+        fw.follow(pv, X, f);
+#pragma unroll
+        uint32_t a2 = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            X[w] = f[w] & Bc[w];
+            a2 |= X[w] & fw.accept(pv, w);
+        }
+        if (a2) { hit[p >> 5] |= 1u << (p & 31); touched = true; }
+    }
+    uint32_t c = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t v = ts.hits[q * ROWS + t];
+        if (touched) { v |= hit[q]; ts.hits[q * ROWS + t] = v; }
+        c += (uint32_t)popc32(v);
+    }
+    ts.cnt[t] = c;
+}
+
+// ===== phase C0 (one thread): offsets of the rows' matches; look back for the tile's output base ====
+template <int NW, int ROWS>
+RRX_DEV void phase_c0(const ScanParams& sp, TileState<NW, ROWS>& ts, uint32_t tile) {
+    uint32_t run = 0;
+    for (int t = 0; t < ROWS; t++) { const uint32_t c = ts.cnt[t]; ts.cnt[t] = run; run += c; }
+    const unsigned long long FL1 = 1ull << 62, FL2 = 2ull << 62, VM = (1ull << 62) - 1;
+    unsigned long long base = 0;
+    if (tile > 0) {
+        sp.cstatus[tile] = FL1 | run;
+        for (int64_t j = (int64_t)tile - 1; j >= 0; j--) {
+            unsigned long long v;
+            while (((v = sp.cstatus[j]) >> 62) == 0) rrx_backoff();
+            base += v & VM;
+            if ((v >> 62) == 2) break;
+        }
+    }
+    sp.cstatus[tile] = FL2 | (base + run);
+    ts.misc[TileState<NW, ROWS>::M_TOTAL] = run;
+    ts.misc[TileState<NW, ROWS>::M_BASE_LO] = (uint32_t)base;
+    ts.misc[TileState<NW, ROWS>::M_BASE_HI] = (uint32_t)(base >> 32);
+    if (tile + 1 == sp.num_tiles) sp.total[0] = base + run;
+}
+
+// ===== phase C: resolve the lazy start of every match of the row and write (start,end) ==============
+template <int NW, int ROWS>
+RRX_DEV void phase_c(const ScanParams& sp, const ProgView& pv, TileState<NW, ROWS>& ts, int t) {
+    const ProgHeader& h = pv.h();
+    const uint32_t* first = pv.sm + h.off_first;
+    const uint32_t* accept = pv.sm + h.off_accept;
+    const unsigned long long base =
+        ((unsigned long long)ts.misc[TileState<NW, ROWS>::M_BASE_HI] << 32) | ts.misc[TileState<NW, ROWS>::M_BASE_LO];
+    unsigned long long slot = base + ts.cnt[t];
+    const int64_t row_lo = (int64_t)((ts.row0 + (uint64_t)t) << ROW_SHIFT);
+    const int64_t left_edge = -(int64_t)sp.left_ctx;
+    for (int q = 0; q < 4; q++) {
+        uint32_t v = ts.hits[q * ROWS + t];
+        while (v) {
+            const int p = q * 32 + ctz32(v);
+            v &= v - 1;
+            const int64_t e = row_lo + p + 1;           // half-open end
+            // backward walk over the reversed automaton from the accepting positions; stop at the
+            // first (= right-most) start that works: lazy.
+            uint32_t R[NW], Bc[NW], x[NW];
+#pragma unroll
+            for (int w = 0; w < NW; w++) R[w] = accept[w];
+            int64_t j = e - 1;
+            bool pend = false, found = false;
+            for (;;) {
+                const uint32_t c = j >= ts.smem_lo ? ts.smem_byte(j) : (uint32_t)sp.text[j];
+                load_B<NW>(pv, c, Bc);
+#pragma unroll
+                for (int w = 0; w < NW; w++) x[w] = R[w] & Bc[w];
+                if (meets<NW>(x, first)) { found = true; break; }
+                follow_bwd<NW>(pv, x, R);
+                j--;
+                if (!any_w<NW>(R)) break;               // only possible when the match began in the entry set
+                if (j < left_edge) { pend = true; break; }
+            }
+            if (slot < sp.out_cap) {
+                long long* o = sp.out + 2 * slot;
+                o[0] = found ? sp.base + j : -1;       // -1: start lies left of the available text
+                o[1] = sp.base + e;
+            }
+            if (pend) {
+                const unsigned long long k = atomicAdd(sp.total + 1, 1ull);
+                if (k < sp.pending_cap) {
+                    PendingStart& ps = sp.pending[k];
+                    ps.match_index = slot;
+                    ps.next_offset = j;
+#pragma unroll
+                    for (int w = 0; w < NW; w++) ps.R[w] = R[w];
+                } else {
+                    atomicOr(sp.err, ERR_PENDING_OVERFLOW);
+                }
+            }
+            slot++;
+        }
+    }
+}
+
+}  // namespace rrx

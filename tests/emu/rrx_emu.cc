@@ -1,0 +1,162 @@
+// TEST INFRASTRUCTURE ONLY — host-side emulator of the rrx scan kernel.
+//
+// Compiles the very same phase functions the GPU kernel runs (roaringregex_b200/csrc/rrx_tile.cuh,
+// with -DRRX_HOST_EMU) and steps them tile by tile, thread by thread, in the order the kernel's
+// __syncthreads() barriers impose.  Lets the CPU-only test tier check the chunk-stitching logic
+// (row transfer functions, look-back, prefix replay, lazy start scans) against the oracle.
+// librrx.so does not contain this file and the product never runs it.
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#define RRX_HOST_EMU 1
+#include "../../roaringregex_b200/csrc/rrx_compile.h"
+#include "../../roaringregex_b200/csrc/rrx_tile.cuh"
+
+using namespace rrx;
+
+namespace {
+
+template <int NW, int NT, int NB>
+int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t len, int64_t base,
+        const uint32_t* entry, int64_t* out, uint64_t cap, uint64_t* counts, uint32_t* err, uint32_t* shard_comp,
+        PendingStart* pending, uint32_t pending_cap) {
+    constexpr int ROWS = NW <= 8 ? 256 : 128;
+    using TS = TileState<NW, ROWS>;
+    const ProgHeader& h = prog.hdr();
+    const uint64_t tile_bytes = (uint64_t)ROWS * ROW_BYTES;
+    const uint32_t num_tiles = (uint32_t)((len + tile_bytes - 1) / tile_bytes);
+
+    std::vector<uint8_t> smem(TS::bytes() + 64, 0xAA);
+    std::vector<uint32_t> btab(NW == 1 ? 256 * 32 : 256 * NW);
+    for (uint32_t i = 0; i < btab.size(); i++) btab[i] = prog.blob[h.off_B + (NW == 1 ? (i >> 5) : i)];
+    std::vector<uint32_t> tflag(num_tiles + 1, 0), tpay((size_t)(num_tiles + 1) * 2 * (1 + 3 * NW), 0);
+    std::vector<unsigned long long> cstatus(num_tiles + 1, 0);
+    unsigned long long total[2] = {0, 0};
+    uint32_t ticket = 0;
+    *err = 0;
+
+    ScanParams sp;
+    std::memset(&sp, 0, sizeof(sp));
+    sp.text = text;
+    sp.len = len;
+    sp.left_ctx = left_ctx;
+    sp.base = base;
+    sp.prog = prog.blob.data();
+    sp.num_tiles = num_tiles;
+    sp.static_closed = (h.static_depth != 0xffffffffu && h.static_depth + 1 <= (uint32_t)ROW_BYTES) ? 1u : 0u;
+    sp.ticket = &ticket;
+    sp.tflag = tflag.data();
+    sp.tpay = tpay.data();
+    sp.cstatus = cstatus.data();
+    sp.out = reinterpret_cast<long long*>(out);
+    sp.out_cap = cap;
+    sp.total = total;
+    sp.err = err;
+    sp.shard_comp = shard_comp;
+    sp.pending = pending;
+    sp.pending_cap = pending_cap;
+    if (entry) for (int w = 0; w < NW; w++) sp.entry[w] = entry[w];
+
+    if (num_tiles == 0) { shard_comp[0] = K_IDENT; for (int i = 1; i < 1 + 3 * NW; i++) shard_comp[i] = 0; }
+
+    for (uint32_t tile = 0; tile < num_tiles; tile++) {
+        TS ts;
+        ts.carve(smem.data());
+        ts.row0 = (uint64_t)tile * ROWS;
+        const bool have_halo = tile > 0 || left_ctx >= ROW_BYTES;
+        ts.smem_lo = have_halo ? ((int64_t)ts.row0 - 1) * ROW_BYTES : 0;
+        std::memset(smem.data(), 0xAA, smem.size());
+        const int64_t g0 = ((int64_t)ts.row0 - 1) * ROW_BYTES;
+        for (int q = 0; q < (ROWS + 1) * 8; q++) {
+            const int s = q >> 3, j = q & 7;
+            const int64_t g = g0 + (int64_t)s * ROW_BYTES + j * 16;
+            uint8_t* dst = ts.text + s * ROW_BYTES + ((j ^ (s & 7)) << 4);
+            if (g < ts.smem_lo || g >= (int64_t)len) continue;
+            for (int k = 0; k < 16 && g + k < (int64_t)len; k++) dst[k] = text[g + k];
+        }
+        bool any_open = false;
+        for (int t = 0; t < ROWS; t++) {
+            ProgView pv{prog.blob.data(), prog.blob.data(), btab.data(), NW == 1 ? 32u : (uint32_t)NW, NW == 1 ? (uint32_t)(t & 31) : 0u};
+            Fwd<NW, NT, NB> fw;
+            fw.init(pv);
+            phase_a<NW, ROWS>(sp, pv, fw, ts, t);
+            any_open = any_open || ts.sum_kind[t] == K_RANK1 || ts.sum_kind[t] == K_HARD;
+        }
+        {
+            ProgView pv{prog.blob.data(), prog.blob.data(), btab.data(), NW == 1 ? 32u : (uint32_t)NW, 0u};
+            Fwd<NW, NT, NB> fw;
+            fw.init(pv);
+            phase_s<NW, ROWS>(sp, pv, fw, ts, tile, any_open);
+        }
+        for (int t = 0; t < ROWS; t++) {
+            ProgView pv{prog.blob.data(), prog.blob.data(), btab.data(), NW == 1 ? 32u : (uint32_t)NW, NW == 1 ? (uint32_t)(t & 31) : 0u};
+            Fwd<NW, NT, NB> fw;
+            fw.init(pv);
+            phase_b<NW, ROWS>(sp, pv, fw, ts, t, any_open);
+        }
+        phase_c0<NW, ROWS>(sp, ts, tile);
+        for (int t = 0; t < ROWS; t++) {
+            ProgView pv{prog.blob.data(), prog.blob.data(), btab.data(), NW == 1 ? 32u : (uint32_t)NW, NW == 1 ? (uint32_t)(t & 31) : 0u};
+            phase_c<NW, ROWS>(sp, pv, ts, t);
+        }
+    }
+    counts[0] = total[0];
+    counts[1] = total[1];
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// text_with_ctx points at the first byte of the left context; the shard starts left_ctx bytes in.
+// fast != 0: use the register-resident forward program when the automaton allows it (as the GPU does).
+// Returns 0, or <0 on a parse error.  counts[0] = matches, counts[1] = pending start scans.
+int emu_scan(const char* pattern, int reduce, int fast, const uint8_t* text_with_ctx, uint64_t left_ctx, uint64_t len,
+             int64_t base, const uint32_t* entry, int64_t* out, uint64_t cap, uint64_t* counts, uint32_t* err,
+             uint32_t* shard_comp, uint32_t* info /* NW, P, n_terms, n_bicl, use_rows, static_depth */,
+             void* pending, uint32_t pending_cap) {
+    Program prog;
+    try {
+        Automaton a = compile_ere(pattern);
+        prog = build_program(a, pattern, reduce != 0);
+    } catch (const std::runtime_error&) {
+        return -1;
+    }
+    const ProgHeader& h = prog.hdr();
+    if (info) { info[0] = h.NW; info[1] = h.P; info[2] = h.n_terms; info[3] = h.n_bicl; info[4] = h.use_rows; info[5] = h.static_depth; }
+    const uint8_t* text = text_with_ctx + left_ctx;
+    PendingStart* pend = reinterpret_cast<PendingStart*>(pending);
+#define GO(NW_, NT_, NB_) return run<NW_, NT_, NB_>(prog, text, left_ctx, len, base, entry, out, cap, counts, err, shard_comp, pend, pending_cap)
+    if (h.NW == 1) {
+        if (fast && !h.use_rows) {
+            const uint32_t nt = h.n_terms, nb = h.n_bicl;
+            if (nt <= 1 && nb <= 0) GO(1, 1, 0);
+            if (nt <= 2 && nb <= 0) GO(1, 2, 0);
+            if (nt <= 3 && nb <= 0) GO(1, 3, 0);
+            if (nt <= 4 && nb <= 0) GO(1, 4, 0);
+            if (nt <= 1 && nb <= 1) GO(1, 1, 1);
+            if (nt <= 2 && nb <= 1) GO(1, 2, 1);
+            if (nt <= 3 && nb <= 1) GO(1, 3, 1);
+            if (nt <= 4 && nb <= 1) GO(1, 4, 1);
+            if (nt <= 2 && nb <= 2) GO(1, 2, 2);
+            if (nt <= 4 && nb <= 2) GO(1, 4, 2);
+        }
+        GO(1, -1, 0);
+    }
+    switch (h.NW) {
+        case 2: GO(2, -1, 0);
+        case 4: GO(4, -1, 0);
+        case 8: GO(8, -1, 0);
+        case 16: GO(16, -1, 0);
+        case 32: GO(32, -1, 0);
+    }
+    return -2;
+}
+
+uint32_t emu_pending_size(void) { return (uint32_t)sizeof(PendingStart); }
+
+}  // extern "C"

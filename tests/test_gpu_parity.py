@@ -1,0 +1,160 @@
+"""Parity of the CUDA path against the oracle — every call goes through the C ABI of librrx.so
+(include/rrx.h) via ctypes.  Run on the B200 box: pytest -m gpu."""
+import random
+import re
+
+import numpy as np
+import pytest
+
+from conftest import cpu_corpus
+from roaringregex_b200.configs import CONFIGS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _check(rrx, oracle_api, pat, text, cache={}):
+    key = pat
+    if key not in cache:
+        cache[key] = (rrx.RRegex(pat), rrx.RRegex(pat, rrx.COMPILE_NO_REDUCE), oracle_api.Oracle(pat))
+    r1, r2, o = cache[key]
+    want = o.lazy_matches(text)
+    for r in (r1, r2):
+        got = r.scan_host(text)
+        assert got.shape == want.shape, (pat, got.shape, want.shape)
+        assert np.array_equal(got, want), pat
+
+
+def test_survey_vectors(rrx, oracle_api, torch_cuda):
+    for pat, txt, want in [("(ab|cd)*e", "xxababe cde e", [(6, 7), (10, 11), (12, 13)]),
+                           ("[a-z]+@[a-z]+\\.(com|org|net)", "foo@bar.com x a@b.org c@d.comet@e.net", [(2, 11), (14, 21), (22, 29), (30, 37)]),
+                           ("a{1,100}b", "aaab b ab aab", [(2, 4), (7, 9), (11, 13)]),
+                           ("(a|b){1,300}c", "abbac c bc", [(3, 5), (8, 10)]),
+                           ("(x|y)*z.*q", "xyzaaqbbq q zq", [(2, 6), (2, 9), (2, 11), (12, 14)]),
+                           ("ab|bc", "abc", [(0, 2), (1, 3)]), ("a+", "aaa", [(0, 1), (1, 2), (2, 3)])]:
+        got = rrx.RRegex(pat).scan_host(txt.encode())
+        assert [tuple(x) for x in got.tolist()] == want, pat
+        _check(rrx, oracle_api, pat, txt.encode())
+
+
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 127, 128, 129, 32767, 32768, 32769, 65536 + 77, 1 << 20])
+def test_sizes_around_row_and_tile_edges(rrx, oracle_api, torch_cuda, n):
+    rnd = random.Random(n)
+    for pat, alpha in [("(ab|cd)*e", b"abcde "), ("(x|y)*z.*q", b"xyzq a"), ("a{1,100}b", b"aaaaab "),
+                       ("[a-z]+@[a-z]+\\.(com|org|net)", b"acomnetrg@. ")]:
+        text = bytes(rnd.choices(alpha, k=n))
+        _check(rrx, oracle_api, pat, text)
+
+
+@pytest.mark.parametrize("cfg_id,n", [(1, 1 << 20), (2, 16 << 20), (3, 16 << 20), (4, 4 << 20), (5, 16 << 20)])
+def test_config_corpora(rrx, oracle_api, torch_cuda, cfg_id, n):
+    cfg = CONFIGS[cfg_id]
+    text = cpu_corpus(cfg, 0, n)
+    _check(rrx, oracle_api, cfg.pattern, text)
+
+
+def test_match_straddling_every_boundary(rrx, oracle_api, torch_cuda):
+    pat = "[a-z]+@[a-z]+\\.(com|org|net)"
+    addr = b"someone@example.org"
+    for edge in (128, 32768):
+        for shift in range(len(addr) + 2):
+            text = bytearray(b" " * (edge + 64))
+            text[edge - shift:edge - shift + len(addr)] = addr
+            _check(rrx, oracle_api, pat, bytes(text))
+
+
+def test_unbounded_carry_and_zero_matches(rrx, oracle_api, torch_cuda):
+    n = 40 * 32768 + 500
+    text = bytearray(b"a" * n)
+    text[0] = ord("z")
+    text[-1] = ord("q")
+    text[70000] = ord("\n")
+    _check(rrx, oracle_api, "(x|y)*z.*q", bytes(text))
+    text[0] = ord("a")
+    got = rrx.RRegex("(x|y)*z.*q").scan_host(bytes(text))
+    assert got.shape == (0, 2)
+    # a match ending at the final byte, a text shorter than one row
+    _check(rrx, oracle_api, "(ab|cd)*e", b"abcde")
+
+
+def test_hard_rows(rrx, oracle_api, torch_cuda):
+    rnd = random.Random(5)
+    for run in (128, 299, 300, 301, 1000):
+        text = bytearray()
+        while len(text) < 200000:
+            text += bytes(rnd.choices(b"ab", k=run)) + b"c" + bytes(rnd.choices(b"ab cd", k=rnd.randint(0, 40)))
+        _check(rrx, oracle_api, "(a|b){1,300}c", bytes(text))
+    _check(rrx, oracle_api, "(a|b){1,300}c", b"ab" * 100000 + b"c")
+    _check(rrx, oracle_api, "(a|b)*a(a|b){3}c", bytes(rnd.choices(b"ab", k=300000)) + b"c")
+
+
+def test_random_regexes(rrx, oracle_api, torch_cuda):
+    from test_emulator import _random_regex
+    rnd = random.Random(77)
+    done = 0
+    while done < 60:
+        pat = _random_regex(rnd)
+        try:
+            o = oracle_api.Oracle(pat)
+        except Exception:
+            continue
+        if o.n_raw > 400:
+            continue
+        done += 1
+        text = bytes(rnd.choices(b"abc\n", k=rnd.randint(0, 70000)))
+        _check(rrx, oracle_api, pat, text)
+
+
+def test_device_corpus_equals_cpu_corpus(rrx, oracle_api, torch_cuda):
+    torch = torch_cuda
+    for cid in (1, 2, 3, 4, 5):
+        cfg = CONFIGS[cid]
+        for off, n in ((0, 1 << 20), (12345, 100003), (1 << 33, 4096 + 5)):
+            d = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
+            if cfg.mode == "iid":
+                rrx.corpus_iid(d.data_ptr(), off, n, cfg.seed, cfg.alpha)
+            else:
+                rrx.corpus_records(d.data_ptr(), off, n, cfg.seed)
+            torch.cuda.synchronize()
+            assert np.array_equal(d[:n].cpu().numpy(), cpu_corpus(cfg, off, n)), (cid, off, n)
+
+
+def test_config2_full_size_properties(rrx, oracle_api, torch_cuda):
+    """1 GiB of log records on the device: match count equals the number of valid records (a
+    closed-form property of the generator), matches are sorted, a 64 MiB prefix is bit-exact."""
+    torch = torch_cuda
+    cfg = CONFIGS[2]
+    n = cfg.length
+    d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    rrx.corpus_records(d.data_ptr(), 0, n, cfg.seed)
+    torch.cuda.synchronize()
+    r = rrx.RRegex(cfg.pattern)
+    got = r.scan_device(d.data_ptr(), n)
+    # kinds of all records straight from the hash: kind = h(seed, 8*rec+2) & 3 ; valid iff kind < 2
+    def sm64(z):
+        z = (z + np.uint64(0x9E3779B97F4A7C15))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+    with np.errstate(over="ignore"):
+        s = sm64(np.uint64(cfg.seed))
+        rec = np.arange(n // 128, dtype=np.uint64)
+        kind = sm64(s + np.uint64(8) * rec + np.uint64(2)) & np.uint64(3)
+    assert len(got) == int((kind < 2).sum())
+    assert np.all(np.diff(got[:, 1]) > 0) and np.all(got[:, 0] < got[:, 1])
+    assert np.array_equal(got[:, 1] >> 7, np.nonzero(kind < 2)[0])          # exactly one match per valid record
+    pre = 64 << 20
+    want = oracle_api.Oracle(cfg.pattern).lazy_matches(cpu_corpus(cfg, 0, pre))
+    assert np.array_equal(got[:len(want)], want)
+    # every reported span is a member of the language (size-independent check on a sample)
+    rx = re.compile(cfg.pattern.encode(), re.S)
+    idx = np.linspace(0, len(got) - 1, 500).astype(int)
+    host = d.cpu().numpy()
+    for s_, e_ in got[idx]:
+        assert rx.fullmatch(host[s_:e_].tobytes())

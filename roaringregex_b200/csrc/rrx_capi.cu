@@ -151,7 +151,7 @@ int rrx_scanner_create(const rrx_program* p, uint64_t max_len, uint64_t capacity
     RRX_CUDA(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
     const ProgHeader& h = p->prog.hdr();
     s->NW = h.NW;
-    const uint64_t tile_bytes = (uint64_t)rows_per_tile(h.NW) * ROW_BYTES;
+    const uint64_t tile_bytes = (uint64_t)TILE_BYTES;
     s->max_len = max_len;
     s->max_tiles = (max_len + tile_bytes - 1) / tile_bytes;
     if (s->max_tiles == 0) s->max_tiles = 1;
@@ -177,7 +177,7 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     if (opts && opts->mode != RRX_MODE_LAZY_V1) return set_err(RRX_ERR_UNSUPPORTED, "only RRX_MODE_LAZY_V1 is implemented on the device");
     cudaStream_t st = (cudaStream_t)stream;
     const ProgHeader& h = s->p->prog.hdr();
-    const uint64_t tile_bytes = (uint64_t)rows_per_tile(h.NW) * ROW_BYTES;
+    const uint64_t tile_bytes = (uint64_t)TILE_BYTES;
     ScanParams sp;
     std::memset(&sp, 0, sizeof(sp));
     sp.text = d_text;

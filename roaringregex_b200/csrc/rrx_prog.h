@@ -1,0 +1,37 @@
+// Device program layout of the rrx scanner — plain C structs shared by the host compiler
+// (rrx_compile.cc), the kernels (rrx_tile.cuh) and the runtime-compiled specialisations.
+// No STL here: this header is also fed to NVRTC.
+#pragma once
+#include <stdint.h>
+
+namespace rrx {
+
+// The device automaton works on the pruned edge set E' = follow minus edges into `first`:
+// with per-byte re-injection S' = (follow'(S) | first) & B[c], an edge into a first-position is
+// subsumed by the injection, and the backward start scan stops at the first first-position, so it
+// never traverses such an edge either (DESIGN.md "Pruned edges").
+enum : uint32_t { RRX_PROG_MAGIC = 0x52525831u };   // "RRX1"
+enum : uint32_t { TERM_ROT = 0, TERM_SHL = 1, TERM_SHR = 2, TERM_SELF = 3 };
+constexpr uint32_t RRX_MAX_TERMS = 8;
+constexpr uint32_t RRX_MAX_BICL = 8;
+
+// All fields are 32-bit words so the blob can be copied to the device verbatim.
+struct ProgHeader {
+    uint32_t magic, P, NW, flags;
+    uint32_t n_terms, n_bicl, use_rows, pad0;        // forward decomposition
+    uint32_t n_rterms, n_rbicl, use_rrows, pad1;     // reverse decomposition
+    // word offsets from the start of the blob
+    uint32_t off_first, off_accept, off_all;
+    uint32_t off_terms, off_bicl, off_rowsrc;        // terms: n*(1+NW) [kind<<8|r, mask]; bicl: n*2*NW
+    uint32_t off_rterms, off_rbicl, off_rrowsrc;
+    uint32_t off_B;                                   // 256*NW
+    uint32_t off_follow, off_rfollow;                 // P*NW each: full pruned follow'/its transpose
+    uint32_t off_rows, off_rrows;                     // P*NW each: edges NOT covered by terms/bicliques
+    uint32_t total_words;
+    uint32_t n_raw, ref_width_class, nullable;
+    uint32_t static_depth;      // longest path (edges) in the pruned follow graph; 0xffffffff if cyclic
+    uint32_t n_flat;            // atoms + START before reduction
+    uint32_t reserved[2];
+};
+
+}  // namespace rrx

@@ -19,119 +19,144 @@
 
 namespace rrx {
 
-template <int NW> struct KCfg { static constexpr int ROWS = NW <= 8 ? 256 : 128; };
+// warps per CTA by state width: registers per thread grow with NW
+template <int NW, int NT> struct KCfg {
+    static constexpr int WARPS = (NW == 1 && NT >= 0) ? 32 : NW <= 2 ? 16 : NW <= 8 ? 8 : 4;
+    static constexpr int THREADS = WARPS * 32;
+    static constexpr uint32_t BT_BYTES = (NW == 1 ? 256u * 128u : 256u * (uint32_t)NW * 4u);
+    static constexpr size_t REGION = (TileState<NW>::bytes() + 127) & ~(size_t)127;
+};
 
 template <int NW, int NT, int NB>
-__global__ void __launch_bounds__(KCfg<NW>::ROWS) rrx_scan_kernel(const __grid_constant__ ScanParams sp) {
-    constexpr int ROWS = KCfg<NW>::ROWS;
-    using TS = TileState<NW, ROWS>;
+__global__ void __launch_bounds__(KCfg<NW, NT>::THREADS, 1) rrx_scan_kernel(const __grid_constant__ ScanParams sp) {
+    using K = KCfg<NW, NT>;
+    using TS = TileState<NW>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // shared memory: [tile state | byte table | small program part]
-    TS ts;
-    ts.carve(smem_raw);
-    uint32_t* Btab = reinterpret_cast<uint32_t*>(smem_raw + ((TS::bytes() + 15) & ~(size_t)15));
-    constexpr uint32_t BT_WORDS = NW == 1 ? 256u * 32u : 256u * (uint32_t)NW;
-    uint32_t* progsm = Btab + BT_WORDS;
+    // shared memory: [byte table | per-warp tile regions | small program part]
+    uint32_t* Btab = reinterpret_cast<uint32_t*>(smem_raw);
+    uint8_t* regions = smem_raw + K::BT_BYTES;
+    uint32_t* progsm = reinterpret_cast<uint32_t*>(regions + (size_t)K::WARPS * K::REGION);
 
     const ProgHeader* gh = reinterpret_cast<const ProgHeader*>(sp.prog);
     const uint32_t n_small = gh->off_B, off_B = gh->off_B;
-    for (uint32_t i = tid; i < n_small; i += ROWS) progsm[i] = sp.prog[i];
+    for (uint32_t i = tid; i < n_small; i += K::THREADS) progsm[i] = sp.prog[i];
     if (NW == 1) {
         // one private copy of the table per lane: entry (c, lane) lives in bank `lane`
-        for (uint32_t i = tid; i < BT_WORDS; i += ROWS) Btab[i] = sp.prog[off_B + (i >> 5)];
+        for (uint32_t i = tid; i < K::BT_BYTES / 4; i += K::THREADS) Btab[i] = sp.prog[off_B + (i >> 5)];
     } else {
-        for (uint32_t i = tid; i < BT_WORDS; i += ROWS) Btab[i] = sp.prog[off_B + i];
+        for (uint32_t i = tid; i < K::BT_BYTES / 4; i += K::THREADS) Btab[i] = sp.prog[off_B + i];
     }
-    __syncthreads();
+    __syncthreads();                      // the only block-level barrier of the kernel
     ProgView pv;
     pv.sm = progsm;
     pv.glob = sp.prog;
-    pv.Btab = Btab;
-    pv.btab_stride = NW == 1 ? 32u : (uint32_t)NW;
-    pv.btab_lane = NW == 1 ? (uint32_t)(tid & 31) : 0u;
-    Fwd<NW, NT, NB> fw;
+    pv.Btab = reinterpret_cast<const uint8_t*>(Btab);
+    pv.lane_off = (uint32_t)lane * 4u;
+    Prog<NW, NT, NB> fw;
     fw.init(pv);
+    TS ts;
+    ts.carve(regions + (size_t)warp * K::REGION);
+    const int64_t len = (int64_t)sp.len;
 
     for (;;) {
-        if (tid == 0) ts.misc[TS::M_TILE] = atomicAdd(sp.ticket, 1u);
-        __syncthreads();
-        const uint32_t tile = ts.misc[TS::M_TILE];
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(sp.ticket, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= sp.num_tiles) break;
-        ts.row0 = (uint64_t)tile * ROWS;
-        const bool have_halo = tile > 0 || sp.left_ctx >= ROW_BYTES;
-        ts.smem_lo = have_halo ? ((int64_t)ts.row0 - 1) * ROW_BYTES : 0;
+        ts.row0 = (uint64_t)tile * TILE_ROWS;
 
-        // ---- stage the tile (+ halo row) ------------------------------------------------------
+        // ---- stage the tile: 8 x 128-bit loads per lane, fully coalesced, XOR-swizzled store ----
         {
-            const int64_t g0 = ((int64_t)ts.row0 - 1) * ROW_BYTES;
-            const int64_t len = (int64_t)sp.len;
-            for (int q = tid; q < (ROWS + 1) * 8; q += ROWS) {
+            const int64_t g0 = ts.lo();
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int q = k * 32 + lane;              // 16-byte chunk index inside the tile
                 const int s = q >> 3, j = q & 7;
-                const int64_t g = g0 + (int64_t)s * ROW_BYTES + j * 16;
-                uint8_t* dst = ts.text + s * ROW_BYTES + ((j ^ (s & 7)) << 4);
-                if (g < ts.smem_lo || g >= len) continue;
+                const int64_t g = g0 + (int64_t)q * 16;
+                uint8_t* dst = ts.text + (s << ROW_SHIFT) + ((j ^ (s & 7)) << 4);
                 if (g + 16 <= len) {
                     *reinterpret_cast<uint4*>(dst) = __ldcs(reinterpret_cast<const uint4*>(sp.text + g));
-                } else {
-                    for (int k = 0; k < 16 && g + k < len; k++) dst[k] = sp.text[g + k];
+                } else if (g < len) {
+                    for (int b = 0; b < 16 && g + b < len; b++) dst[b] = sp.text[g + b];
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
 
-        phase_a<NW, ROWS>(sp, pv, fw, ts, tid);
-        const uint32_t my_kind = ts.sum_kind[tid];
-        const bool any_open = __syncthreads_or(my_kind == K_RANK1 || my_kind == K_HARD) != 0;
-        if (tid == 0) phase_s<NW, ROWS>(sp, pv, fw, ts, tile, any_open);
-        __syncthreads();
-        phase_b<NW, ROWS>(sp, pv, fw, ts, tid, any_open);
-        __syncthreads();
-        if (tid == 0) phase_c0<NW, ROWS>(sp, ts, tile);
-        __syncthreads();
-        phase_c<NW, ROWS>(sp, pv, ts, tid);
-        __syncthreads();
+        phase_a<NW>(sp, pv, fw, ts, lane);
+        const uint32_t my_kind = ts.sum_kind[lane];
+        const bool any_open = __any_sync(0xffffffffu, my_kind == K_RANK1 || my_kind == K_HARD) != 0;
+        __syncwarp();
+        if (lane == 0) phase_s<NW>(sp, pv, fw, ts, tile, any_open);
+        __syncwarp();
+        const uint32_t c = phase_b<NW>(sp, pv, fw, ts, lane, any_open);
+        // exclusive offsets of the rows' matches inside the tile
+        uint32_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        const uint32_t offset = inc - c;
+        unsigned long long base = 0;
+        if (lane == 0) base = phase_c0(sp, tile, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (total) {
+            uint32_t hit[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) hit[q] = ts.hits[q * TILE_ROWS + lane];
+            __syncwarp();                 // every lane is done with the row summaries: reuse as hit list
+            if (total <= (uint32_t)TS::LIST_CAP) {
+                phase_c1_list<NW>(ts, lane, offset, hit);
+                __syncwarp();
+                phase_c2_balanced<NW>(sp, pv, fw, ts, lane, total, base);
+            } else {
+                phase_c2_rows<NW>(sp, pv, fw, ts, lane, offset, hit, base);
+            }
+        }
+        __syncwarp();
     }
 }
 
-template <int NW> static size_t smem_bytes_for() {
-    using TS = TileState<NW, KCfg<NW>::ROWS>;
-    const size_t bt = (NW == 1 ? 256u * 32u : 256u * (uint32_t)NW) * 4u;
+template <int NW, int NT> static size_t smem_bytes_for() {
+    using K = KCfg<NW, NT>;
     // small program part: header + 3 sets + 2 decompositions
     const size_t small = sizeof(ProgHeader) + 4u * (3 * NW + 2 * (RRX_MAX_TERMS * (1 + NW) + RRX_MAX_BICL * 2 * NW + NW));
-    return ((TS::bytes() + 15) & ~(size_t)15) + bt + small + 64;
+    return K::BT_BYTES + (size_t)K::WARPS * K::REGION + small + 64;
 }
 
 template <int NW, int NT, int NB>
 static cudaError_t launch_one(const ScanParams& sp, int sm_count, cudaStream_t st, int* grid_out) {
+    using K = KCfg<NW, NT>;
     auto kern = rrx_scan_kernel<NW, NT, NB>;
-    const size_t smem = smem_bytes_for<NW>();
+    const size_t smem = smem_bytes_for<NW, NT>();
     static bool configured = false;     // per instantiation
     static int occ = 1;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, KCfg<NW>::ROWS, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, K::THREADS, smem);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
         configured = true;
     }
     long long grid = (long long)sm_count * occ;
-    if (grid > (long long)sp.num_tiles) grid = sp.num_tiles;
+    const long long need = ((long long)sp.num_tiles + K::WARPS - 1) / K::WARPS;
+    if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     if (grid_out) *grid_out = (int)grid;
-    kern<<<(unsigned)grid, KCfg<NW>::ROWS, smem, st>>>(sp);
+    kern<<<(unsigned)grid, K::THREADS, smem, st>>>(sp);
     return cudaGetLastError();
 }
 
-int rows_per_tile(uint32_t NW) { return NW <= 8 ? 256 : 128; }
-
 cudaError_t launch_scan(const ScanParams& sp, const ProgHeader& h, int sm_count, cudaStream_t st, int* grid_out) {
-    const uint32_t nt = h.n_terms, nb = h.n_bicl;
     if (h.NW == 1) {
-        bool rot_only = !h.use_rows;
-        if (rot_only) {
+        const uint32_t nt = h.n_terms > h.n_rterms ? h.n_terms : h.n_rterms;
+        const uint32_t nb = h.n_bicl > h.n_rbicl ? h.n_bicl : h.n_rbicl;
+        if (!h.use_rows && !h.use_rrows) {
 #define RRX_TRY(NT_, NB_) if (nt <= NT_ && nb <= NB_) return launch_one<1, NT_, NB_>(sp, sm_count, st, grid_out);
             RRX_TRY(1, 0) RRX_TRY(2, 0) RRX_TRY(3, 0) RRX_TRY(4, 0) RRX_TRY(1, 1) RRX_TRY(2, 1) RRX_TRY(3, 1) RRX_TRY(4, 1)
             RRX_TRY(2, 2) RRX_TRY(4, 2)

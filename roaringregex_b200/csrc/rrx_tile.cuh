@@ -1,30 +1,30 @@
 // Per-tile scan logic of the rrx kernels, written as phase functions over an explicit
 // shared-memory state so that
-//   * rrx_scan.cu runs them on the GPU (one CTA per tile, __syncthreads() between phases), and
+//   * rrx_scan.cu runs them on the GPU — a TILE is the 32 rows of ONE WARP, the phases are
+//     separated by __syncwarp() only, there is no block-level barrier on the scan path — and
 //   * tests/emu/rrx_emu.cc compiles the SAME functions for the host (-DRRX_HOST_EMU) and steps the
-//     phases thread by thread.  The emulator is test infrastructure only: it lets the CPU-only CI
+//     phases lane by lane.  The emulator is test infrastructure only: it lets the CPU-only CI
 //     exercise the chunk-stitching logic (summaries, look-back, fix-up, start scans) bit for bit;
 //     librrx.so neither contains nor calls it.
 //
 // Hot path replaced (reference file:line):
-//   NFA.cc:72-102   Processor::shift<fwd>      -> step(): S' = (follow'(S) | first) & B[c]
-//   NFA.cc:103-107  Processor::operator*       -> any(S & accept) / any(R & first)
-//   regex.h:156-162 AcceptanceIterator loop    -> row scans (one 128-byte row per thread)
+//   NFA.cc:72-102   Processor::shift<fwd>      -> step: S' = (follow'(S) | first) & B[c]
+//   NFA.cc:103-107  Processor::operator*       -> (S & accept) != 0 / (R & first) != 0
+//   regex.h:156-162 AcceptanceIterator loop    -> row scans (one 128-byte row per lane)
 //   Iterator.cpp    (empty: the lazy iterator) -> LAZY-v1 enumeration, SURVEY.md Appendix D
 //
-// Text geometry: the corpus is cut into ROWS of 128 bytes; a TILE is `ROWS` consecutive rows
-// (one per thread) plus the row before it (halo, for backward start scans).
+// Text geometry: the corpus is cut into ROWS of 128 bytes; a tile is 32 consecutive rows (4 KiB).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
-#include "rrx_compile.h"   // ProgHeader, TERM_*, RRX_MAX_*
+#include "rrx_prog.h"
 
 #if defined(__CUDACC__) && !defined(RRX_HOST_EMU)
 #define RRX_DEV __device__ __forceinline__
-#define RRX_DEVN __device__ __noinline__
 #else
 #define RRX_DEV inline
-#define RRX_DEVN inline
 #endif
 
 #ifdef RRX_HOST_EMU
@@ -37,11 +37,12 @@ namespace rrx {
 
 constexpr int ROW_BYTES = 128;
 constexpr int ROW_SHIFT = 7;
+constexpr int TILE_ROWS = 32;                         // one row per lane
+constexpr int TILE_BYTES = TILE_ROWS * ROW_BYTES;     // 4 KiB
 
 // error bits reported by the kernel
-enum : uint32_t {
-    ERR_PENDING_OVERFLOW = 2u,
-};
+enum : uint32_t { ERR_PENDING_OVERFLOW = 2u };
+
 // Kinds of chunk transfer functions S_out = A*S_in | b:
 //   K_CLOSED  A = 0: the exit does not depend on the entry
 //   K_RANK1   A = U x P^T: exit = b | (entry meets P ? U : 0)
@@ -90,28 +91,41 @@ template <int NW> RRX_DEV int popc_w(const uint32_t* a) {
 
 // ---- program view ----------------------------------------------------------------------------------
 // The "small" part of the program blob (everything before the byte table) is copied to shared
-// memory once per CTA; the byte table gets its own (bank-conflict-free) layout; the per-source
-// row tables stay in global memory (only irregular automata use them).
+// memory once per CTA; the byte table gets its own layout; the per-source row tables stay in
+// global memory (only irregular automata use them).
+//
+// Byte table in shared memory.  NW == 1: one private copy per lane — entry (c, lane) is the
+// 32-bit word at byte offset c*128 + lane*4, i.e. always in bank `lane`: conflict-free whatever
+// the 32 lanes' bytes are.  NW > 1: entry c is NW consecutive words at c*NW*4.
 struct ProgView {
     const uint32_t* sm;        // shared copy of blob[0 .. off_B)
     const uint32_t* glob;      // the blob in global memory
-    const uint32_t* Btab;      // shared byte table
-    uint32_t btab_stride;      // words between consecutive bytes' entries
-    uint32_t btab_lane;        // this thread's word offset inside an entry (NW==1: lane id)
+    const uint8_t* Btab;       // shared byte table
+    uint32_t lane_off;         // NW == 1: lane*4
     RRX_DEV const ProgHeader& h() const { return *reinterpret_cast<const ProgHeader*>(sm); }
 };
 
 template <int NW> RRX_DEV void load_B(const ProgView& pv, uint32_t c, uint32_t* out) {
-    const uint32_t* e = pv.Btab + c * pv.btab_stride + pv.btab_lane;
+    if (NW == 1) {
+        out[0] = *reinterpret_cast<const uint32_t*>(pv.Btab + ((c << 7) | pv.lane_off));
+    } else {
+        const uint32_t* e = reinterpret_cast<const uint32_t*>(pv.Btab) + c * NW;
 #pragma unroll
-    for (int w = 0; w < NW; w++) out[w] = e[w];
+        for (int w = 0; w < NW; w++) out[w] = e[w];
+    }
+}
+// NW == 1 only: table entry for byte I (0..3) of the little-endian text word `w`, with the byte
+// moved straight to its place in the table offset (shift + and/or, no multiply).
+template <int I> RRX_DEV uint32_t load_B1(const ProgView& pv, uint32_t w) {
+    const uint32_t sh = I == 0 ? (w << 7) : (w >> (I == 0 ? 0 : 8 * I - 7));
+    return *reinterpret_cast<const uint32_t*>(pv.Btab + ((sh & 0x7F80u) | pv.lane_off));
 }
 
 // f = follow'(S) through a decomposition (shift terms, bicliques, rows) read from shared memory.
 template <int NW>
-RRX_DEV void follow_terms(const ProgView& pv, const uint32_t* terms, uint32_t n_terms, const uint32_t* bicl,
-                          uint32_t n_bicl, uint32_t use_rows, const uint32_t* rowsrc, const uint32_t* rows_g,
-                          const uint32_t* S, uint32_t* f) {
+RRX_DEV void follow_terms(const uint32_t* terms, uint32_t n_terms, const uint32_t* bicl, uint32_t n_bicl,
+                          uint32_t use_rows, const uint32_t* rowsrc, const uint32_t* rows_g, const uint32_t* S,
+                          uint32_t* f) {
 #pragma unroll
     for (int w = 0; w < NW; w++) f[w] = 0;
     for (uint32_t t = 0; t < n_terms; t++) {
@@ -151,42 +165,39 @@ RRX_DEV void follow_terms(const ProgView& pv, const uint32_t* terms, uint32_t n_
         }
     }
 }
-template <int NW> RRX_DEV void follow_fwd(const ProgView& pv, const uint32_t* S, uint32_t* f) {
-    const ProgHeader& h = pv.h();
-    follow_terms<NW>(pv, pv.sm + h.off_terms, h.n_terms, pv.sm + h.off_bicl, h.n_bicl, h.use_rows,
-                     pv.sm + h.off_rowsrc, pv.glob + h.off_rows, S, f);
-}
-template <int NW> RRX_DEV void follow_bwd(const ProgView& pv, const uint32_t* S, uint32_t* f) {
-    const ProgHeader& h = pv.h();
-    follow_terms<NW>(pv, pv.sm + h.off_rterms, h.n_rterms, pv.sm + h.off_rbicl, h.n_rbicl, h.use_rrows,
-                     pv.sm + h.off_rrowsrc, pv.glob + h.off_rrows, S, f);
-}
 
-// Forward follow policy.  NT >= 0: one-word automaton whose decomposition (NT rotations, NB
-// bicliques) lives in registers; NT < 0: anything, read from shared memory.
-template <int NW, int NT, int NB> struct Fwd {
+// Follow policy.  NT >= 0: one-word automaton whose forward AND reverse decompositions (up to NT
+// rotations, NB bicliques each) live in registers; NT < 0: anything, read from shared memory.
+template <int NW, int NT, int NB> struct Prog {
     static_assert(NW == 1, "register program is for one-word sets");
     uint32_t rot[NT > 0 ? NT : 1], msk[NT > 0 ? NT : 1], bsrc[NB > 0 ? NB : 1], bdst[NB > 0 ? NB : 1];
-    uint32_t first_, accept_;
+    uint32_t rrot[NT > 0 ? NT : 1], rmsk[NT > 0 ? NT : 1], rbsrc[NB > 0 ? NB : 1], rbdst[NB > 0 ? NB : 1];
+    uint32_t first_, accept_, all_;
     RRX_DEV void init(const ProgView& pv) {
         const ProgHeader& h = pv.h();
         first_ = pv.sm[h.off_first];
         accept_ = pv.sm[h.off_accept];
+        all_ = pv.sm[h.off_all];
 #pragma unroll
         for (int t = 0; t < NT; t++) {
-            const bool live = (uint32_t)t < h.n_terms;
+            const bool live = (uint32_t)t < h.n_terms, rlive = (uint32_t)t < h.n_rterms;
             rot[t] = live ? (pv.sm[h.off_terms + t * 2] & 0xff) : 0u;
             msk[t] = live ? pv.sm[h.off_terms + t * 2 + 1] : 0u;
+            rrot[t] = rlive ? (pv.sm[h.off_rterms + t * 2] & 0xff) : 0u;
+            rmsk[t] = rlive ? pv.sm[h.off_rterms + t * 2 + 1] : 0u;
         }
 #pragma unroll
         for (int b = 0; b < NB; b++) {
-            const bool live = (uint32_t)b < h.n_bicl;
+            const bool live = (uint32_t)b < h.n_bicl, rlive = (uint32_t)b < h.n_rbicl;
             bsrc[b] = live ? pv.sm[h.off_bicl + b * 2] : 0u;
             bdst[b] = live ? pv.sm[h.off_bicl + b * 2 + 1] : 0u;
+            rbsrc[b] = rlive ? pv.sm[h.off_rbicl + b * 2] : 0u;
+            rbdst[b] = rlive ? pv.sm[h.off_rbicl + b * 2 + 1] : 0u;
         }
     }
     RRX_DEV uint32_t first(const ProgView&, int) const { return first_; }
     RRX_DEV uint32_t accept(const ProgView&, int) const { return accept_; }
+    RRX_DEV uint32_t all(const ProgView&, int) const { return all_; }
     RRX_DEV void follow(const ProgView&, const uint32_t* S, uint32_t* f) const {
         uint32_t o = 0;
 #pragma unroll
@@ -195,12 +206,30 @@ template <int NW, int NT, int NB> struct Fwd {
         for (int b = 0; b < NB; b++) o |= (S[0] & bsrc[b]) ? bdst[b] : 0u;
         f[0] = o;
     }
+    RRX_DEV void rfollow(const ProgView&, const uint32_t* S, uint32_t* f) const {
+        uint32_t o = 0;
+#pragma unroll
+        for (int t = 0; t < NT; t++) o |= rotl32(S[0], rrot[t]) & rmsk[t];
+#pragma unroll
+        for (int b = 0; b < NB; b++) o |= (S[0] & rbsrc[b]) ? rbdst[b] : 0u;
+        f[0] = o;
+    }
 };
-template <int NW, int NB> struct Fwd<NW, -1, NB> {
+template <int NW, int NB> struct Prog<NW, -1, NB> {
     RRX_DEV void init(const ProgView&) {}
     RRX_DEV uint32_t first(const ProgView& pv, int w) const { return pv.sm[pv.h().off_first + w]; }
     RRX_DEV uint32_t accept(const ProgView& pv, int w) const { return pv.sm[pv.h().off_accept + w]; }
-    RRX_DEV void follow(const ProgView& pv, const uint32_t* S, uint32_t* f) const { follow_fwd<NW>(pv, S, f); }
+    RRX_DEV uint32_t all(const ProgView& pv, int w) const { return pv.sm[pv.h().off_all + w]; }
+    RRX_DEV void follow(const ProgView& pv, const uint32_t* S, uint32_t* f) const {
+        const ProgHeader& h = pv.h();
+        follow_terms<NW>(pv.sm + h.off_terms, h.n_terms, pv.sm + h.off_bicl, h.n_bicl, h.use_rows,
+                         pv.sm + h.off_rowsrc, pv.glob + h.off_rows, S, f);
+    }
+    RRX_DEV void rfollow(const ProgView& pv, const uint32_t* S, uint32_t* f) const {
+        const ProgHeader& h = pv.h();
+        follow_terms<NW>(pv.sm + h.off_rterms, h.n_rterms, pv.sm + h.off_rbicl, h.n_rbicl, h.use_rrows,
+                         pv.sm + h.off_rrowsrc, pv.glob + h.off_rrows, S, f);
+    }
 };
 
 // ---- composites (rank<=1 chunk transfer functions) ---------------------------------------------------
@@ -213,7 +242,7 @@ template <int NW> RRX_DEV void comp_ident(Comp<NW>& c) {
 #pragma unroll
     for (int w = 0; w < NW; w++) c.b[w] = c.U[w] = c.P[w] = 0;
 }
-// r = "x first, then y".  y is never K_HARD/K_WAIT here; x neither.
+// r = "x first, then y".  Neither is K_HARD/K_WAIT here.
 template <int NW> RRX_DEV void comp_compose(const Comp<NW>& x, const Comp<NW>& y, Comp<NW>& r) {
     const uint32_t xt = x.kind & K_TYPE, yt = y.kind & K_TYPE;
     if (yt == K_CLOSED || xt == K_IDENT) { r = y; return; }
@@ -275,27 +304,28 @@ struct ScanParams {
     uint32_t entry[RRX_NW_MAX]; // forward set carried into text[0]
 };
 
-// ---- shared-memory state of one CTA ------------------------------------------------------------------
-template <int NW, int ROWS> struct TileState {
-    uint8_t* text;        // (ROWS+1) rows of 128 B; 16-byte chunk j of smem row s sits at chunk j^(s&7)
-    uint32_t* sum_b;      // [NW][ROWS]   exit of the row scanned from the empty set
-    uint32_t* sum_U;      // [NW][ROWS]   (open rows) survivors at the row end / prefix composite U
-    uint32_t* sum_P;      // [NW][ROWS]   (open rows) entry states that feed the survivor
-    uint32_t* sum_kind;   // [ROWS]
-    uint32_t* hits;       // [4][ROWS]    one bit per byte of the row: a match ends after that byte
-    uint32_t* cnt;        // [ROWS]       matches per row -> exclusive offsets
+// ---- shared-memory state of one tile (= one warp) ----------------------------------------------------
+template <int NW> struct TileState {
+    static constexpr int ROWS = TILE_ROWS;
+    uint8_t* text;        // 32 rows of 128 B; 16-byte chunk j of row s sits at chunk j^(s&7)
+    uint32_t* sum_b;      // [NW][32]   exit of the row scanned from the empty set
+    uint32_t* sum_U;      // [NW][32]   (open rows) survivors at the row end / prefix composite U
+    uint32_t* sum_P;      // [NW][32]   (open rows) entry states that feed the survivor
+    uint32_t* sum_kind;   // [32]
+    uint32_t* hits;       // [4][32]    one bit per byte of the row: a match ends after that byte
+    uint32_t* cnt;        // [32]       matches per row -> exclusive offsets
     uint32_t* misc;       // see M_* below
-    // geometry of the current tile
+    uint16_t* list;       // hit list for the balanced start scans; aliases sum_b/sum_U/sum_P
     uint64_t row0;        // first row of the tile
-    int64_t smem_lo;      // shard-local offset of the first valid byte held in `text`
-    static constexpr int M_TILE = 0, M_ANYOPEN = 1, M_TOTAL = 2, M_BASE_LO = 3, M_BASE_HI = 4, M_ENTRY = 8;
+    static constexpr int M_ENTRY = 8;
     static constexpr int MISC_WORDS = 8 + NW;
+    static constexpr int LIST_CAP = 3 * NW * ROWS * 2;
     static constexpr size_t bytes() {
-        return (size_t)(ROWS + 1) * ROW_BYTES + sizeof(uint32_t) * ((size_t)3 * NW * ROWS + 6 * ROWS + MISC_WORDS);
+        return (size_t)ROWS * ROW_BYTES + sizeof(uint32_t) * ((size_t)3 * NW * ROWS + 6 * ROWS + MISC_WORDS);
     }
     RRX_DEV void carve(uint8_t* base) {
         text = base;
-        uint32_t* p = reinterpret_cast<uint32_t*>(base + (size_t)(ROWS + 1) * ROW_BYTES);
+        uint32_t* p = reinterpret_cast<uint32_t*>(base + (size_t)ROWS * ROW_BYTES);
         sum_b = p; p += NW * ROWS;
         sum_U = p; p += NW * ROWS;
         sum_P = p; p += NW * ROWS;
@@ -303,18 +333,15 @@ template <int NW, int ROWS> struct TileState {
         hits = p; p += 4 * ROWS;
         cnt = p; p += ROWS;
         misc = p;
+        list = reinterpret_cast<uint16_t*>(sum_b);
     }
-    // byte at shard-local offset g, which must lie inside the staged window
-    RRX_DEV uint32_t smem_byte(int64_t g) const {
-        const int64_t rel = g - ((int64_t)row0 - 1) * ROW_BYTES;
-        const uint32_t s = (uint32_t)(rel >> ROW_SHIFT), col = (uint32_t)rel & (ROW_BYTES - 1);
-        return text[s * ROW_BYTES + ((((col >> 4) ^ (s & 7)) << 4) | (col & 15))];
+    RRX_DEV int64_t lo() const { return (int64_t)(row0 << ROW_SHIFT); }
+    // byte at tile-relative offset rel (0 .. TILE_BYTES)
+    RRX_DEV uint32_t rel_byte(uint32_t rel) const {
+        const uint32_t s = rel >> ROW_SHIFT, col = rel & (ROW_BYTES - 1);
+        return text[(s << ROW_SHIFT) + ((((col >> 4) ^ (s & 7)) << 4) | (col & 15))];
     }
-    RRX_DEV const uint8_t* row_ptr(int t) const { return text + (size_t)(t + 1) * ROW_BYTES; }
-    RRX_DEV uint32_t row_byte(int t, int p) const {
-        const uint32_t s = (uint32_t)t + 1;
-        return text[s * ROW_BYTES + (((((uint32_t)p >> 4) ^ (s & 7)) << 4) | ((uint32_t)p & 15))];
-    }
+    RRX_DEV uint32_t row_byte(int t, int p) const { return rel_byte(((uint32_t)t << ROW_SHIFT) + (uint32_t)p); }
 };
 
 // Number of valid bytes of row `t` of the tile starting at row0.
@@ -326,9 +353,9 @@ RRX_DEV int row_nbytes(const ScanParams& sp, uint64_t row0, int t) {
 }
 
 // ===== phase A: per-row scan from the empty set (+ openness analysis) ===============================
-template <int NW, int ROWS, class F>
-RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, ROWS>& ts, int t) {
-    const ProgHeader& h = pv.h();
+template <int NW, class F>
+RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t) {
+    constexpr int ROWS = TILE_ROWS;
     const int nb = row_nbytes(sp, ts.row0, t);
     uint32_t kind = nb ? K_CLOSED : K_IDENT;
     uint32_t Bc[NW], f[NW];
@@ -339,7 +366,7 @@ RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
     if (nb && !sp.static_closed) {
         uint32_t U[NW];
 #pragma unroll
-        for (int w = 0; w < NW; w++) U[w] = pv.sm[h.off_all + w];
+        for (int w = 0; w < NW; w++) U[w] = fw.all(pv, w);
         int pc = -1;
         uint32_t J[NW];
 #pragma unroll
@@ -369,7 +396,7 @@ RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
                     uint32_t x[NW];
 #pragma unroll
                     for (int w = 0; w < NW; w++) x[w] = R[w] & Bc[w];
-                    follow_bwd<NW>(pv, x, R);
+                    fw.rfollow(pv, x, R);
                 }
             }
 #pragma unroll
@@ -386,42 +413,55 @@ RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
     for (int w = 0; w < NW; w++) S[w] = 0;
     uint32_t hit[4] = {0, 0, 0, 0};
     if (nb == ROW_BYTES) {
-        const uint32_t s = (uint32_t)t + 1;
-        const uint4* rowv = reinterpret_cast<const uint4*>(ts.text + (size_t)s * ROW_BYTES);
+        const uint32_t s = (uint32_t)t;
+        const uint4* rowv = reinterpret_cast<const uint4*>(ts.text + ((size_t)s << ROW_SHIFT));
 #pragma unroll 1
         for (int g = 0; g < 8; g++) {
             const uint4 v = rowv[g ^ (s & 7)];
             const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
-            uint32_t S0[NW], acc = 0;
+            uint32_t Sq[4][NW], acc[4];
 #pragma unroll
-            for (int w = 0; w < NW; w++) S0[w] = S[w];
+            for (int q = 0; q < 4; q++) {
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const uint32_t c = (wd[i >> 2] >> (8 * (i & 3))) & 0xffu;
-                load_B<NW>(pv, c, Bc);
-                fw.follow(pv, S, f);
+                for (int w = 0; w < NW; w++) Sq[q][w] = S[w];
+                uint32_t a = 0;
 #pragma unroll
-                for (int w = 0; w < NW; w++) {
-                    S[w] = (f[w] | fw.first(pv, w)) & Bc[w];
-                    acc |= S[w] & fw.accept(pv, w);
-                }
-            }
-            if (acc) {        // rare: replay the 16 bytes to find which of them end a match
-#pragma unroll
-                for (int w = 0; w < NW; w++) S[w] = S0[w];
-#pragma unroll 1
-                for (int i = 0; i < 16; i++) {
-                    const uint32_t c = (wd[i >> 2] >> (8 * (i & 3))) & 0xffu;
-                    load_B<NW>(pv, c, Bc);
+                for (int i = 0; i < 4; i++) {
+                    if (NW == 1) {
+                        Bc[0] = i == 0 ? load_B1<0>(pv, wd[q]) : i == 1 ? load_B1<1>(pv, wd[q])
+                              : i == 2 ? load_B1<2>(pv, wd[q]) : load_B1<3>(pv, wd[q]);
+                    } else {
+                        load_B<NW>(pv, (wd[q] >> (8 * i)) & 0xffu, Bc);
+                    }
                     fw.follow(pv, S, f);
-#pragma unroll
-                    uint32_t a2 = 0;
 #pragma unroll
                     for (int w = 0; w < NW; w++) {
                         S[w] = (f[w] | fw.first(pv, w)) & Bc[w];
-                        a2 |= S[w] & fw.accept(pv, w);
+                        a |= S[w] & fw.accept(pv, w);
                     }
-                    if (a2) hit[g >> 1] |= 1u << ((g & 1) * 16 + i);
+                }
+                acc[q] = a;
+            }
+            if (acc[0] | acc[1] | acc[2] | acc[3]) {
+                // rare: replay the 4-byte words that contain a match end to find the exact bytes
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (!acc[q]) continue;
+                    uint32_t T[NW];
+#pragma unroll
+                    for (int w = 0; w < NW; w++) T[w] = Sq[q][w];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        load_B<NW>(pv, (wd[q] >> (8 * i)) & 0xffu, Bc);
+                        fw.follow(pv, T, f);
+                        uint32_t a2 = 0;
+#pragma unroll
+                        for (int w = 0; w < NW; w++) {
+                            T[w] = (f[w] | fw.first(pv, w)) & Bc[w];
+                            a2 |= T[w] & fw.accept(pv, w);
+                        }
+                        if (a2) hit[g >> 1] |= 1u << ((g & 1) * 16 + q * 4 + i);
+                    }
                 }
             }
         }
@@ -429,7 +469,6 @@ RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
         for (int p = 0; p < nb; p++) {
             load_B<NW>(pv, ts.row_byte(t, p), Bc);
             fw.follow(pv, S, f);
-#pragma unroll
             uint32_t a2 = 0;
 #pragma unroll
             for (int w = 0; w < NW; w++) {
@@ -446,7 +485,8 @@ RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
     for (int q = 0; q < 4; q++) ts.hits[q * ROWS + t] = hit[q];
 }
 
-template <int NW, int ROWS> RRX_DEV void load_row_comp(const TileState<NW, ROWS>& ts, int t, Comp<NW>& c) {
+template <int NW> RRX_DEV void load_row_comp(const TileState<NW>& ts, int t, Comp<NW>& c) {
+    constexpr int ROWS = TILE_ROWS;
     c.kind = ts.sum_kind[t];
 #pragma unroll
     for (int w = 0; w < NW; w++) {
@@ -455,7 +495,8 @@ template <int NW, int ROWS> RRX_DEV void load_row_comp(const TileState<NW, ROWS>
         c.P[w] = (c.kind & K_TYPE) == K_RANK1 ? ts.sum_P[w * ROWS + t] : 0u;
     }
 }
-template <int NW, int ROWS> RRX_DEV void store_row_comp(TileState<NW, ROWS>& ts, int t, const Comp<NW>& c) {
+template <int NW> RRX_DEV void store_row_comp(TileState<NW>& ts, int t, const Comp<NW>& c) {
+    constexpr int ROWS = TILE_ROWS;
     ts.sum_kind[t] = c.kind;
 #pragma unroll
     for (int w = 0; w < NW; w++) {
@@ -483,13 +524,13 @@ RRX_DEV void rrx_fence() {
 }
 RRX_DEV void rrx_backoff() {
 #if defined(__CUDA_ARCH__) && !defined(RRX_HOST_EMU)
-    __nanosleep(64);
+    __nanosleep(32);
 #endif
 }
 
 // Exit of the no-injection replay of row t from the exact entry set X (in place).
-template <int NW, int ROWS, class F>
-RRX_DEV void row_replay_exit(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW, ROWS>& ts, int t,
+template <int NW, class F>
+RRX_DEV void row_replay_exit(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW>& ts, int t,
                              uint32_t* X) {
     const int nb = row_nbytes(sp, ts.row0, t);
     uint32_t Bc[NW], f[NW];
@@ -501,15 +542,18 @@ RRX_DEV void row_replay_exit(const ScanParams& sp, const ProgView& pv, const F& 
     }
 }
 
-// ===== phase S (one thread): compose the rows, publish the tile, look back for the tile's entry =====
+// ===== phase S (one lane): compose the rows, publish the tile, look back for the tile's entry ======
 // After this phase sum_* of row t hold the composite of rows [0,t) of the tile (what turns the
 // tile entry into row t's entry) and misc[M_ENTRY..] holds the tile's exact entry set.
-template <int NW, int ROWS, class F>
-RRX_DEV void phase_s(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, ROWS>& ts, uint32_t tile,
+template <int NW, class F>
+RRX_DEV void phase_s(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, uint32_t tile,
                      bool any_open) {
+    constexpr int ROWS = TILE_ROWS;
+    using TS = TileState<NW>;
     Comp<NW> run, rowc, nxt, pre_block;
     comp_ident(run);
     comp_ident(pre_block);
+    comp_ident(nxt);
     int blocked_from = -1, resume_at = ROWS;
     bool wait_agg = false;
     if (any_open) {
@@ -536,7 +580,7 @@ RRX_DEV void phase_s(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
                 uint32_t X[NW];
 #pragma unroll
                 for (int w = 0; w < NW; w++) X[w] = run.b[w];
-                row_replay_exit<NW, ROWS>(sp, pv, fw, ts, t, X);
+                row_replay_exit<NW>(sp, pv, fw, ts, t, X);
 #pragma unroll
                 for (int w = 0; w < NW; w++) X[w] |= rowc.b[w];
                 comp_closed(run, X, run.kind & K_OPAQUE);
@@ -556,9 +600,11 @@ RRX_DEV void phase_s(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
     const size_t stride = 2 * (size_t)(1 + 3 * NW);
     uint32_t* mine = sp.tpay + (size_t)tile * stride;
     // aggregate first, so that successors can start looking back
-    store_comp_global<NW>(mine, run);
-    rrx_fence();
-    if (tile > 0) sp.tflag[tile] = 1;
+    if (tile > 0) {
+        store_comp_global<NW>(mine, run);
+        rrx_fence();
+        sp.tflag[tile] = 1;
+    }
     // look back
     Comp<NW> acc;
     comp_ident(acc);
@@ -567,6 +613,7 @@ RRX_DEV void phase_s(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
         while ((fl = sp.tflag[j]) == 0) rrx_backoff();
         rrx_fence();
         Comp<NW> x;
+        comp_ident(x);
         if (fl == 1) {
             load_comp_global<NW>(sp.tpay + (size_t)j * stride, x);
             if ((x.kind & K_TYPE) == K_WAIT) {
@@ -583,7 +630,7 @@ RRX_DEV void phase_s(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
     uint32_t E[NW];
     comp_apply<NW>(acc, sp.entry, E);
 #pragma unroll
-    for (int w = 0; w < NW; w++) ts.misc[TileState<NW, ROWS>::M_ENTRY + w] = E[w];
+    for (int w = 0; w < NW; w++) ts.misc[TS::M_ENTRY + w] = E[w];
     if (blocked_from >= 0) {
         // second stage: walk the blocked segment with exact states
         uint32_t X[NW], Y[NW];
@@ -597,7 +644,7 @@ RRX_DEV void phase_s(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
             if (rt == K_HARD) {
 #pragma unroll
                 for (int w = 0; w < NW; w++) Y[w] = X[w];
-                row_replay_exit<NW, ROWS>(sp, pv, fw, ts, t, Y);
+                row_replay_exit<NW>(sp, pv, fw, ts, t, Y);
 #pragma unroll
                 for (int w = 0; w < NW; w++) X[w] = Y[w] | rowc.b[w];
             } else {
@@ -616,12 +663,15 @@ RRX_DEV void phase_s(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
 }
 
 // ===== phase B: replay each row's prefix from its exact entry set (no injection) ====================
-template <int NW, int ROWS, class F>
-RRX_DEV void phase_b(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, ROWS>& ts, int t,
-                     bool any_open) {
+// Returns the number of matches of the row.
+template <int NW, class F>
+RRX_DEV uint32_t phase_b(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t,
+                         bool any_open) {
+    constexpr int ROWS = TILE_ROWS;
+    using TS = TileState<NW>;
     const int nb = row_nbytes(sp, ts.row0, t);
     uint32_t X[NW], Bc[NW], f[NW];
-    const uint32_t* E = ts.misc + TileState<NW, ROWS>::M_ENTRY;
+    const uint32_t* E = ts.misc + TS::M_ENTRY;
     if (any_open) {
         Comp<NW> pre;
         load_row_comp(ts, t, pre);
@@ -638,7 +688,6 @@ RRX_DEV void phase_b(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
     for (int p = 0; p < nb && any_w<NW>(X); p++) {
         load_B<NW>(pv, ts.row_byte(t, p), Bc);
         fw.follow(pv, X, f);
-#pragma unroll
         uint32_t a2 = 0;
 #pragma unroll
         for (int w = 0; w < NW; w++) {
@@ -654,18 +703,16 @@ RRX_DEV void phase_b(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
         if (touched) { v |= hit[q]; ts.hits[q * ROWS + t] = v; }
         c += (uint32_t)popc32(v);
     }
-    ts.cnt[t] = c;
+    return c;
 }
 
-// ===== phase C0 (one thread): offsets of the rows' matches; look back for the tile's output base ====
-template <int NW, int ROWS>
-RRX_DEV void phase_c0(const ScanParams& sp, TileState<NW, ROWS>& ts, uint32_t tile) {
-    uint32_t run = 0;
-    for (int t = 0; t < ROWS; t++) { const uint32_t c = ts.cnt[t]; ts.cnt[t] = run; run += c; }
+// ===== phase C0 (one lane): look back for the tile's output base ===================================
+// `total` = matches of the tile.  Returns the index of the tile's first match in the output.
+RRX_DEV unsigned long long phase_c0(const ScanParams& sp, uint32_t tile, uint32_t total) {
     const unsigned long long FL1 = 1ull << 62, FL2 = 2ull << 62, VM = (1ull << 62) - 1;
     unsigned long long base = 0;
     if (tile > 0) {
-        sp.cstatus[tile] = FL1 | run;
+        sp.cstatus[tile] = FL1 | total;
         for (int64_t j = (int64_t)tile - 1; j >= 0; j--) {
             unsigned long long v;
             while (((v = sp.cstatus[j]) >> 62) == 0) rrx_backoff();
@@ -673,66 +720,88 @@ RRX_DEV void phase_c0(const ScanParams& sp, TileState<NW, ROWS>& ts, uint32_t ti
             if ((v >> 62) == 2) break;
         }
     }
-    sp.cstatus[tile] = FL2 | (base + run);
-    ts.misc[TileState<NW, ROWS>::M_TOTAL] = run;
-    ts.misc[TileState<NW, ROWS>::M_BASE_LO] = (uint32_t)base;
-    ts.misc[TileState<NW, ROWS>::M_BASE_HI] = (uint32_t)(base >> 32);
-    if (tile + 1 == sp.num_tiles) sp.total[0] = base + run;
+    sp.cstatus[tile] = FL2 | (base + total);
+    if (tile + 1 == sp.num_tiles) sp.total[0] = base + total;
+    return base;
 }
 
-// ===== phase C: resolve the lazy start of every match of the row and write (start,end) ==============
-template <int NW, int ROWS>
-RRX_DEV void phase_c(const ScanParams& sp, const ProgView& pv, TileState<NW, ROWS>& ts, int t) {
-    const ProgHeader& h = pv.h();
-    const uint32_t* first = pv.sm + h.off_first;
-    const uint32_t* accept = pv.sm + h.off_accept;
-    const unsigned long long base =
-        ((unsigned long long)ts.misc[TileState<NW, ROWS>::M_BASE_HI] << 32) | ts.misc[TileState<NW, ROWS>::M_BASE_LO];
-    unsigned long long slot = base + ts.cnt[t];
-    const int64_t row_lo = (int64_t)((ts.row0 + (uint64_t)t) << ROW_SHIFT);
-    const int64_t left_edge = -(int64_t)sp.left_ctx;
+// ===== phase C: resolve the lazy start of every match and write (start,end) ========================
+// Backward walk over the reversed automaton from the accepting positions, starting with the byte
+// at shard-local offset e-1; stops at the first (= right-most) start that works: lazy.
+template <int NW, class F>
+RRX_DEV void resolve_and_write(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW>& ts,
+                               int64_t e, unsigned long long slot) {
+    uint32_t R[NW], Bc[NW], x[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) R[w] = fw.accept(pv, w);
+    const int64_t tile_lo = ts.lo(), left_edge = -(int64_t)sp.left_ctx;
+    int64_t j = e - 1;
+    bool pend = false, found = false;
+    for (;;) {
+        const uint32_t c = j >= tile_lo ? ts.rel_byte((uint32_t)(j - tile_lo)) : (uint32_t)sp.text[j];
+        load_B<NW>(pv, c, Bc);
+        uint32_t m = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) { x[w] = R[w] & Bc[w]; m |= x[w] & fw.first(pv, w); }
+        if (m) { found = true; break; }
+        fw.rfollow(pv, x, R);
+        j--;
+        if (!any_w<NW>(R)) break;               // only possible when the match began in the entry set
+        if (j < left_edge) { pend = true; break; }
+    }
+    if (slot < sp.out_cap) {
+        long long* o = sp.out + 2 * slot;
+        o[0] = found ? sp.base + j : -1;        // -1: the start lies left of the available text
+        o[1] = sp.base + e;
+    }
+    if (pend) {
+        const unsigned long long k = atomicAdd(sp.total + 1, 1ull);
+        if (k < sp.pending_cap) {
+            PendingStart& ps = sp.pending[k];
+            ps.match_index = slot;
+            ps.next_offset = j;
+#pragma unroll
+            for (int w = 0; w < NW; w++) ps.R[w] = R[w];
+        } else {
+            atomicOr(sp.err, ERR_PENDING_OVERFLOW);
+        }
+    }
+}
+
+// C1 (per lane): append the row's match ends to the tile's hit list (tile-relative end-1).
+// cnt[t] must hold the row's exclusive offset.  Only when the tile total fits the list.
+template <int NW> RRX_DEV void phase_c1_list(TileState<NW>& ts, int t, uint32_t offset, const uint32_t* hit) {
+    uint32_t k = offset;
     for (int q = 0; q < 4; q++) {
-        uint32_t v = ts.hits[q * ROWS + t];
+        uint32_t v = hit[q];
         while (v) {
             const int p = q * 32 + ctz32(v);
             v &= v - 1;
-            const int64_t e = row_lo + p + 1;           // half-open end
-            // backward walk over the reversed automaton from the accepting positions; stop at the
-            // first (= right-most) start that works: lazy.
-            uint32_t R[NW], Bc[NW], x[NW];
-#pragma unroll
-            for (int w = 0; w < NW; w++) R[w] = accept[w];
-            int64_t j = e - 1;
-            bool pend = false, found = false;
-            for (;;) {
-                const uint32_t c = j >= ts.smem_lo ? ts.smem_byte(j) : (uint32_t)sp.text[j];
-                load_B<NW>(pv, c, Bc);
-#pragma unroll
-                for (int w = 0; w < NW; w++) x[w] = R[w] & Bc[w];
-                if (meets<NW>(x, first)) { found = true; break; }
-                follow_bwd<NW>(pv, x, R);
-                j--;
-                if (!any_w<NW>(R)) break;               // only possible when the match began in the entry set
-                if (j < left_edge) { pend = true; break; }
-            }
-            if (slot < sp.out_cap) {
-                long long* o = sp.out + 2 * slot;
-                o[0] = found ? sp.base + j : -1;       // -1: start lies left of the available text
-                o[1] = sp.base + e;
-            }
-            if (pend) {
-                const unsigned long long k = atomicAdd(sp.total + 1, 1ull);
-                if (k < sp.pending_cap) {
-                    PendingStart& ps = sp.pending[k];
-                    ps.match_index = slot;
-                    ps.next_offset = j;
-#pragma unroll
-                    for (int w = 0; w < NW; w++) ps.R[w] = R[w];
-                } else {
-                    atomicOr(sp.err, ERR_PENDING_OVERFLOW);
-                }
-            }
-            slot++;
+            ts.list[k++] = (uint16_t)((t << ROW_SHIFT) + p);
+        }
+    }
+}
+// C2 (per lane): balanced — lane handles list entries lane, lane+32, ...
+template <int NW, class F>
+RRX_DEV void phase_c2_balanced(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW>& ts, int lane,
+                               uint32_t total, unsigned long long base) {
+    for (uint32_t i = (uint32_t)lane; i < total; i += TILE_ROWS) {
+        const int64_t e = ts.lo() + (int64_t)ts.list[i] + 1;
+        resolve_and_write<NW>(sp, pv, fw, ts, e, base + i);
+    }
+}
+// C2 fallback (per lane): every row resolves its own matches (tiles with more hits than the list holds).
+template <int NW, class F>
+RRX_DEV void phase_c2_rows(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW>& ts, int t,
+                           uint32_t offset, const uint32_t* hit, unsigned long long base) {
+    unsigned long long slot = base + offset;
+    const int64_t row_lo = ts.lo() + ((int64_t)t << ROW_SHIFT);
+    for (int q = 0; q < 4; q++) {
+        uint32_t v = hit[q];
+        while (v) {
+            const int p = q * 32 + ctz32(v);
+            v &= v - 1;
+            resolve_and_write<NW>(sp, pv, fw, ts, row_lo + p + 1, slot++);
         }
     }
 }

@@ -23,11 +23,10 @@ template <int NW, int NT, int NB>
 int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t len, int64_t base,
         const uint32_t* entry, int64_t* out, uint64_t cap, uint64_t* counts, uint32_t* err, uint32_t* shard_comp,
         PendingStart* pending, uint32_t pending_cap) {
-    constexpr int ROWS = NW <= 8 ? 256 : 128;
-    using TS = TileState<NW, ROWS>;
+    constexpr int ROWS = TILE_ROWS;
+    using TS = TileState<NW>;
     const ProgHeader& h = prog.hdr();
-    const uint64_t tile_bytes = (uint64_t)ROWS * ROW_BYTES;
-    const uint32_t num_tiles = (uint32_t)((len + tile_bytes - 1) / tile_bytes);
+    const uint32_t num_tiles = (uint32_t)((len + TILE_BYTES - 1) / TILE_BYTES);
 
     std::vector<uint8_t> smem(TS::bytes() + 64, 0xAA);
     std::vector<uint32_t> btab(NW == 1 ? 256 * 32 : 256 * NW);
@@ -62,45 +61,69 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
 
     if (num_tiles == 0) { shard_comp[0] = K_IDENT; for (int i = 1; i < 1 + 3 * NW; i++) shard_comp[i] = 0; }
 
+    auto view = [&](int lane) {
+        ProgView pv;
+        pv.sm = prog.blob.data();
+        pv.glob = prog.blob.data();
+        pv.Btab = reinterpret_cast<const uint8_t*>(btab.data());
+        pv.lane_off = (uint32_t)lane * 4u;
+        return pv;
+    };
+
     for (uint32_t tile = 0; tile < num_tiles; tile++) {
         TS ts;
         ts.carve(smem.data());
         ts.row0 = (uint64_t)tile * ROWS;
-        const bool have_halo = tile > 0 || left_ctx >= ROW_BYTES;
-        ts.smem_lo = have_halo ? ((int64_t)ts.row0 - 1) * ROW_BYTES : 0;
         std::memset(smem.data(), 0xAA, smem.size());
-        const int64_t g0 = ((int64_t)ts.row0 - 1) * ROW_BYTES;
-        for (int q = 0; q < (ROWS + 1) * 8; q++) {
+        const int64_t g0 = ts.lo();
+        for (int q = 0; q < ROWS * 8; q++) {
             const int s = q >> 3, j = q & 7;
-            const int64_t g = g0 + (int64_t)s * ROW_BYTES + j * 16;
+            const int64_t g = g0 + (int64_t)q * 16;
             uint8_t* dst = ts.text + s * ROW_BYTES + ((j ^ (s & 7)) << 4);
-            if (g < ts.smem_lo || g >= (int64_t)len) continue;
             for (int k = 0; k < 16 && g + k < (int64_t)len; k++) dst[k] = text[g + k];
         }
         bool any_open = false;
         for (int t = 0; t < ROWS; t++) {
-            ProgView pv{prog.blob.data(), prog.blob.data(), btab.data(), NW == 1 ? 32u : (uint32_t)NW, NW == 1 ? (uint32_t)(t & 31) : 0u};
-            Fwd<NW, NT, NB> fw;
+            ProgView pv = view(t);
+            Prog<NW, NT, NB> fw;
             fw.init(pv);
-            phase_a<NW, ROWS>(sp, pv, fw, ts, t);
+            phase_a<NW>(sp, pv, fw, ts, t);
             any_open = any_open || ts.sum_kind[t] == K_RANK1 || ts.sum_kind[t] == K_HARD;
         }
         {
-            ProgView pv{prog.blob.data(), prog.blob.data(), btab.data(), NW == 1 ? 32u : (uint32_t)NW, 0u};
-            Fwd<NW, NT, NB> fw;
+            ProgView pv = view(0);
+            Prog<NW, NT, NB> fw;
             fw.init(pv);
-            phase_s<NW, ROWS>(sp, pv, fw, ts, tile, any_open);
+            phase_s<NW>(sp, pv, fw, ts, tile, any_open);
         }
+        uint32_t cnt[ROWS], off[ROWS], total_t = 0;
         for (int t = 0; t < ROWS; t++) {
-            ProgView pv{prog.blob.data(), prog.blob.data(), btab.data(), NW == 1 ? 32u : (uint32_t)NW, NW == 1 ? (uint32_t)(t & 31) : 0u};
-            Fwd<NW, NT, NB> fw;
+            ProgView pv = view(t);
+            Prog<NW, NT, NB> fw;
             fw.init(pv);
-            phase_b<NW, ROWS>(sp, pv, fw, ts, t, any_open);
+            cnt[t] = phase_b<NW>(sp, pv, fw, ts, t, any_open);
         }
-        phase_c0<NW, ROWS>(sp, ts, tile);
-        for (int t = 0; t < ROWS; t++) {
-            ProgView pv{prog.blob.data(), prog.blob.data(), btab.data(), NW == 1 ? 32u : (uint32_t)NW, NW == 1 ? (uint32_t)(t & 31) : 0u};
-            phase_c<NW, ROWS>(sp, pv, ts, t);
+        for (int t = 0; t < ROWS; t++) { off[t] = total_t; total_t += cnt[t]; }
+        const unsigned long long b0 = phase_c0(sp, tile, total_t);
+        if (total_t) {
+            uint32_t hit[ROWS][4];
+            for (int t = 0; t < ROWS; t++) for (int q = 0; q < 4; q++) hit[t][q] = ts.hits[q * ROWS + t];
+            if (total_t <= (uint32_t)TS::LIST_CAP) {
+                for (int t = 0; t < ROWS; t++) phase_c1_list<NW>(ts, t, off[t], hit[t]);
+                for (int t = 0; t < ROWS; t++) {
+                    ProgView pv = view(t);
+                    Prog<NW, NT, NB> fw;
+                    fw.init(pv);
+                    phase_c2_balanced<NW>(sp, pv, fw, ts, t, total_t, b0);
+                }
+            } else {
+                for (int t = 0; t < ROWS; t++) {
+                    ProgView pv = view(t);
+                    Prog<NW, NT, NB> fw;
+                    fw.init(pv);
+                    phase_c2_rows<NW>(sp, pv, fw, ts, t, off[t], hit[t], b0);
+                }
+            }
         }
     }
     counts[0] = total[0];
@@ -132,8 +155,9 @@ int emu_scan(const char* pattern, int reduce, int fast, const uint8_t* text_with
     PendingStart* pend = reinterpret_cast<PendingStart*>(pending);
 #define GO(NW_, NT_, NB_) return run<NW_, NT_, NB_>(prog, text, left_ctx, len, base, entry, out, cap, counts, err, shard_comp, pend, pending_cap)
     if (h.NW == 1) {
-        if (fast && !h.use_rows) {
-            const uint32_t nt = h.n_terms, nb = h.n_bicl;
+        if (fast && !h.use_rows && !h.use_rrows) {
+            const uint32_t nt = h.n_terms > h.n_rterms ? h.n_terms : h.n_rterms;
+            const uint32_t nb = h.n_bicl > h.n_rbicl ? h.n_bicl : h.n_rbicl;
             if (nt <= 1 && nb <= 0) GO(1, 1, 0);
             if (nt <= 2 && nb <= 0) GO(1, 2, 0);
             if (nt <= 3 && nb <= 0) GO(1, 3, 0);

@@ -37,7 +37,7 @@ def test_survey_vectors(oracle_api):
         _check(oracle_api, pat, txt.encode())
 
 
-@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 127, 128, 129, 255, 256, 32767, 32768, 32769, 65536 + 77])
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 127, 128, 129, 255, 256, 4095, 4096, 4097, 32767, 32768, 32769, 65536 + 77])
 def test_sizes_around_row_and_tile_edges(oracle_api, n):
     rnd = random.Random(n)
     for pat, alpha in [("(ab|cd)*e", b"abcde "), ("(x|y)*z.*q", b"xyzq a"), ("a{1,100}b", b"aaaaab ")]:
@@ -50,7 +50,7 @@ def test_match_straddling_every_boundary(oracle_api):
     pat = "[a-z]+@[a-z]+\\.(com|org|net)"
     o = oracle_api.Oracle(pat)
     addr = b"someone@example.org"
-    for edge in (128, 32768):
+    for edge in (128, 4096, 32768):
         for shift in range(len(addr) + 2):
             start = edge - shift
             text = bytearray(b" " * (edge + 64))

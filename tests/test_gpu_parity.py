@@ -43,7 +43,7 @@ def test_survey_vectors(rrx, oracle_api, torch_cuda):
         _check(rrx, oracle_api, pat, txt.encode())
 
 
-@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 127, 128, 129, 32767, 32768, 32769, 65536 + 77, 1 << 20])
+@pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 127, 128, 129, 4095, 4096, 4097, 32767, 32768, 32769, 65536 + 77, 1 << 20])
 def test_sizes_around_row_and_tile_edges(rrx, oracle_api, torch_cuda, n):
     rnd = random.Random(n)
     for pat, alpha in [("(ab|cd)*e", b"abcde "), ("(x|y)*z.*q", b"xyzq a"), ("a{1,100}b", b"aaaaab "),
@@ -62,7 +62,7 @@ def test_config_corpora(rrx, oracle_api, torch_cuda, cfg_id, n):
 def test_match_straddling_every_boundary(rrx, oracle_api, torch_cuda):
     pat = "[a-z]+@[a-z]+\\.(com|org|net)"
     addr = b"someone@example.org"
-    for edge in (128, 32768):
+    for edge in (128, 4096, 32768):
         for shift in range(len(addr) + 2):
             text = bytearray(b" " * (edge + 64))
             text[edge - shift:edge - shift + len(addr)] = addr

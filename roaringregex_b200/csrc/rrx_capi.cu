@@ -22,6 +22,26 @@ int cuda_err(cudaError_t e, const char* what) {
     return set_err(RRX_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 #define RRX_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_err(e_, #call); } while (0)
+
+// Control block of a scan over T tiles (B = ceil(T/32) blocks); everything in it is zeroed before
+// the scan: [ticket,err,total[2],pad | f_a0[T] f_i0[T] f_a1[B] f_i1[B] st_arrive[B] ct_arrive[B] |
+// ct_a0[T] ct_a1[B] ct_i1[B] (64-bit)].  Returns the size; fills the nine offsets.
+size_t ctrl_layout(size_t T, size_t* off) {
+    const size_t B = (T + 31) / 32;
+    size_t o = 32, tmp[10];
+    size_t* f = off ? off : tmp;
+    f[0] = o; o += 4 * T;
+    f[1] = o; o += 4 * T;
+    f[2] = o; o += 4 * B;
+    f[3] = o; o += 4 * B;
+    f[4] = o; o += 4 * B;
+    f[5] = o; o += 4 * B;
+    o = (o + 7) & ~(size_t)7;
+    f[6] = o; o += 8 * T;
+    f[7] = o; o += 8 * B;
+    f[8] = o; o += 8 * B;
+    return o;
+}
 }  // namespace
 
 struct rrx_program {
@@ -35,7 +55,7 @@ struct rrx_scanner {
     uint64_t max_len = 0, capacity = 0, max_tiles = 0;
     uint32_t NW = 1;
     uint32_t* d_prog = nullptr;
-    uint8_t* d_ctrl = nullptr;      // [ticket | err | total[2] | tflag[T] | cstatus[T]]
+    uint8_t* d_ctrl = nullptr;      // header + look-back flags and counters, zeroed before every scan
     size_t ctrl_bytes = 0;
     uint32_t* d_tpay = nullptr;
     long long* d_out = nullptr;
@@ -158,9 +178,9 @@ int rrx_scanner_create(const rrx_program* p, uint64_t max_len, uint64_t capacity
     s->capacity = capacity ? capacity : 1;
     RRX_CUDA(cudaMalloc(&s->d_prog, p->prog.blob.size() * 4));
     RRX_CUDA(cudaMemcpy(s->d_prog, p->prog.blob.data(), p->prog.blob.size() * 4, cudaMemcpyHostToDevice));
-    s->ctrl_bytes = 32 + s->max_tiles * 4 + 8 + s->max_tiles * 8;
+    s->ctrl_bytes = ctrl_layout(s->max_tiles, nullptr);
     RRX_CUDA(cudaMalloc(&s->d_ctrl, s->ctrl_bytes));
-    RRX_CUDA(cudaMalloc(&s->d_tpay, s->max_tiles * 2 * (1 + 3 * (size_t)h.NW) * 4));
+    RRX_CUDA(cudaMalloc(&s->d_tpay, (2 * s->max_tiles + 2 * ((s->max_tiles + 31) / 32)) * (1 + 3 * (size_t)h.NW) * 4));
     RRX_CUDA(cudaMalloc(&s->d_out, s->capacity * 16));
     RRX_CUDA(cudaMalloc(&s->d_shard, (1 + 3 * (size_t)h.NW) * 4));
     RRX_CUDA(cudaMalloc(&s->d_pending, sizeof(PendingStart) * s->pending_cap));
@@ -188,14 +208,25 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     sp.num_tiles = (uint32_t)((len + tile_bytes - 1) / tile_bytes);
     sp.static_closed = (h.static_depth != 0xffffffffu && h.static_depth + 1 <= (uint32_t)ROW_BYTES) ? 1u : 0u;
     uint8_t* c = s->d_ctrl;
+    size_t off[10];
+    const size_t used = ctrl_layout(sp.num_tiles, off);
+    const size_t T = sp.num_tiles, B = (T + 31) / 32, PW = 1 + 3 * (size_t)h.NW;
     sp.ticket = reinterpret_cast<uint32_t*>(c);
     sp.err = reinterpret_cast<uint32_t*>(c + 4);
     sp.total = reinterpret_cast<unsigned long long*>(c + 8);
-    sp.tflag = reinterpret_cast<volatile uint32_t*>(c + 32);
-    size_t off = 32 + s->max_tiles * 4;
-    off = (off + 7) & ~(size_t)7;
-    sp.cstatus = reinterpret_cast<volatile unsigned long long*>(c + off);
-    sp.tpay = s->d_tpay;
+    sp.f_a0 = reinterpret_cast<volatile uint32_t*>(c + off[0]);
+    sp.f_i0 = reinterpret_cast<volatile uint32_t*>(c + off[1]);
+    sp.f_a1 = reinterpret_cast<volatile uint32_t*>(c + off[2]);
+    sp.f_i1 = reinterpret_cast<volatile uint32_t*>(c + off[3]);
+    sp.st_arrive = reinterpret_cast<uint32_t*>(c + off[4]);
+    sp.ct_arrive = reinterpret_cast<uint32_t*>(c + off[5]);
+    sp.ct_a0 = reinterpret_cast<volatile unsigned long long*>(c + off[6]);
+    sp.ct_a1 = reinterpret_cast<volatile unsigned long long*>(c + off[7]);
+    sp.ct_i1 = reinterpret_cast<volatile unsigned long long*>(c + off[8]);
+    sp.st_a0 = s->d_tpay;
+    sp.st_i0 = sp.st_a0 + T * PW;
+    sp.st_a1 = sp.st_i0 + T * PW;
+    sp.st_i1 = sp.st_a1 + B * PW;
     sp.out = s->d_out;
     sp.out_cap = s->capacity;
     sp.shard_comp = s->d_shard;
@@ -203,8 +234,7 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     sp.pending_cap = s->pending_cap;
     if (opts && opts->entry) for (uint32_t w = 0; w < h.NW; w++) sp.entry[w] = opts->entry[w];
     s->launches = 0;
-    RRX_CUDA(cudaMemsetAsync(s->d_ctrl, 0, 32 + (size_t)sp.num_tiles * 4, st));
-    RRX_CUDA(cudaMemsetAsync(c + off, 0, (size_t)sp.num_tiles * 8, st));
+    RRX_CUDA(cudaMemsetAsync(s->d_ctrl, 0, used, st));
     if (sp.num_tiles == 0) {
         // empty text: identity transfer function, no matches
         uint32_t ident[1 + 3 * RRX_NW_MAX] = {K_IDENT};

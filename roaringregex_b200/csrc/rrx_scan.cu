@@ -27,6 +27,188 @@ template <int NW, int NT> struct KCfg {
     static constexpr size_t REGION = (TileState<NW>::bytes() + 127) & ~(size_t)127;
 };
 
+// =====================================================================================================
+// Two-level decoupled look-back.
+//
+// Every warp owns one tile at a time; tiles are handed out in ticket order, so every tile with a
+// smaller index is finished or in flight on a resident warp.  With ~4700 tiles in flight and all of
+// them reaching the same phase at about the same time, a flat look-back would walk thousands of
+// aggregates one by one.  Here
+//   level 0: each tile publishes its aggregate; the LAST tile of a 32-tile block to arrive folds the
+//            32 aggregates into the block aggregate (level 1);
+//   a tile's exclusive prefix = fold(aggregates of the tiles before it in its block)   [1 round,
+//            32 lanes read 32 entries in parallel]  combined with  fold(previous blocks' aggregates
+//            back to the nearest published block-inclusive value)   [32 blocks = 1024 tiles per round];
+//   the warp holding the last tile of a block publishes the block-inclusive value.
+// Every wait is on a value that its producer publishes BEFORE the producer itself waits for anything,
+// so the scheme cannot deadlock (exception: K_WAIT aggregates, whose consumers wait for the producer's
+// inclusive value — the producer only ever waits on smaller tile indices).
+// =====================================================================================================
+constexpr unsigned FULL = 0xffffffffu;
+constexpr unsigned long long CT_READY = 1ull << 63;
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+
+// match counts (commutative): returns the number of matches before `tile` (same value in all lanes)
+__device__ __forceinline__ unsigned long long lookback_count(const ScanParams& sp, uint32_t tile, uint32_t total, int lane) {
+    const uint32_t b = tile >> 5, k = tile & 31;
+    const uint32_t rest = sp.num_tiles - (b << 5);
+    const uint32_t nblk = rest < 32u ? rest : 32u;
+    uint32_t old = 0;
+    if (lane == 0) {
+        sp.ct_a0[tile] = CT_READY | total;
+        __threadfence();
+        old = atomicAdd(sp.ct_arrive + b, 1u);
+    }
+    old = __shfl_sync(FULL, old, 0);
+    if (old == nblk - 1) {                                  // all aggregates of the block are out
+        __threadfence();
+        unsigned long long v = 0;
+        if ((uint32_t)lane < nblk) {
+            while (!((v = sp.ct_a0[(b << 5) + lane]) & CT_READY)) rrx_backoff();
+            v &= ~CT_READY;
+        }
+        v = warp_sum(v);
+        if (lane == 0) sp.ct_a1[b] = CT_READY | v;
+    }
+    unsigned long long x = 0;
+    if ((uint32_t)lane < k) {
+        unsigned long long v;
+        while (!((v = sp.ct_a0[(b << 5) + lane]) & CT_READY)) rrx_backoff();
+        x = v & ~CT_READY;
+    }
+    x = warp_sum(x);
+    unsigned long long base = 0;
+    for (int64_t jb = (int64_t)b - 1; jb >= 0; jb -= 32) {
+        const int64_t my = jb - lane;
+        unsigned long long v = 0;
+        bool inc = false;
+        if (my >= 0) {
+            for (;;) {
+                const unsigned long long vi = sp.ct_i1[my];
+                if (vi & CT_READY) { v = vi & ~CT_READY; inc = true; break; }
+                const unsigned long long va = sp.ct_a1[my];
+                if (va & CT_READY) { v = va & ~CT_READY; break; }
+                rrx_backoff();
+            }
+        }
+        const unsigned bal = __ballot_sync(FULL, inc);
+        if (bal) {
+            const int first = __ffs((int)bal) - 1;
+            base += warp_sum(lane <= first ? v : 0ull);
+            break;
+        }
+        base += warp_sum(v);
+    }
+    const unsigned long long res = base + x;
+    if (lane == 0) {
+        if (k == nblk - 1) sp.ct_i1[b] = CT_READY | (res + total);
+        if (tile + 1 == sp.num_tiles) sp.total[0] = res + total;
+    }
+    return res;
+}
+
+template <int NW> __device__ __forceinline__ void bcast_comp(Comp<NW>& c, int src) {
+    c.kind = __shfl_sync(FULL, c.kind, src);
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        c.b[w] = __shfl_sync(FULL, c.b[w], src);
+        c.U[w] = __shfl_sync(FULL, c.U[w], src);
+        c.P[w] = __shfl_sync(FULL, c.P[w], src);
+    }
+}
+template <int NW> __device__ __forceinline__ void publish_comp(uint32_t* pay, volatile uint32_t* flag, size_t idx, const Comp<NW>& c) {
+    store_comp_global<NW>(pay + idx * (1 + 3 * NW), c);
+    __threadfence();
+    flag[idx] = 1u;
+}
+template <int NW> __device__ __forceinline__ void wait_comp(const uint32_t* pay, volatile uint32_t* flag, size_t idx, Comp<NW>& c) {
+    while (flag[idx] == 0u) rrx_backoff();
+    __threadfence();
+    load_comp_global<NW>(pay + idx * (1 + 3 * NW), c);
+}
+
+// state composites (ordered): all lanes pass the same `agg`; `acc` = composite of everything before
+// the tile, relative to the shard entry (same value in all lanes).
+template <int NW>
+__device__ __forceinline__ void lookback_state(const ScanParams& sp, uint32_t tile, const Comp<NW>& agg, int lane, Comp<NW>& acc) {
+    const uint32_t b = tile >> 5, k = tile & 31;
+    const uint32_t rest = sp.num_tiles - (b << 5);
+    const uint32_t nblk = rest < 32u ? rest : 32u;
+    Comp<NW> mine, x, nxt;
+    uint32_t old = 0;
+    if (lane == 0) {
+        publish_comp<NW>(sp.st_a0, sp.f_a0, tile, agg);
+        __threadfence();
+        old = atomicAdd(sp.st_arrive + b, 1u);
+    }
+    old = __shfl_sync(FULL, old, 0);
+    if (old == nblk - 1) {                                  // fold the block aggregate, in tile order
+        __threadfence();
+        comp_ident(mine);
+        if ((uint32_t)lane < nblk) wait_comp<NW>(sp.st_a0, sp.f_a0, (size_t)(b << 5) + lane, mine);
+        Comp<NW> fold;
+        comp_ident(fold);
+        bool has_wait = false;
+        for (uint32_t l = 0; l < nblk; l++) {
+            x = mine;
+            bcast_comp(x, (int)l);
+            if ((x.kind & K_TYPE) == K_WAIT) { has_wait = true; continue; }
+            comp_compose(fold, x, nxt);
+            fold = nxt;
+        }
+        if (has_wait) fold.kind = K_WAIT;
+        if (lane == 0) publish_comp<NW>(sp.st_a1, sp.f_a1, b, fold);
+    }
+    // (a) the tiles before this one inside the block, nearest first
+    comp_ident(mine);
+    if ((uint32_t)lane < k) wait_comp<NW>(sp.st_a0, sp.f_a0, (size_t)(b << 5) + lane, mine);
+    comp_ident(acc);
+    bool done = false;
+    for (int l = (int)k - 1; l >= 0 && !done; l--) {
+        x = mine;
+        bcast_comp(x, l);
+        if ((x.kind & K_TYPE) == K_WAIT) {                   // opaque tile: take its inclusive state
+            wait_comp<NW>(sp.st_i0, sp.f_i0, (size_t)(b << 5) + l, x);
+            done = true;
+        }
+        comp_compose(x, acc, nxt);
+        acc = nxt;
+        if ((acc.kind & K_TYPE) == K_CLOSED) done = true;
+    }
+    // (b) previous blocks, 32 per round, nearest first
+    for (int64_t jb = (int64_t)b - 1; jb >= 0 && !done; jb -= 32) {
+        const int64_t my = jb - lane;
+        uint32_t st = 0;                                    // 1 aggregate, 2 inclusive
+        comp_ident(mine);
+        if (my >= 0) {
+            for (;;) {
+                if (sp.f_i1[my]) { wait_comp<NW>(sp.st_i1, sp.f_i1, (size_t)my, mine); st = 2; break; }
+                if (sp.f_a1[my]) {
+                    wait_comp<NW>(sp.st_a1, sp.f_a1, (size_t)my, mine);
+                    st = 1;
+                    if ((mine.kind & K_TYPE) == K_WAIT) { wait_comp<NW>(sp.st_i1, sp.f_i1, (size_t)my, mine); st = 2; }
+                    break;
+                }
+                rrx_backoff();
+            }
+        }
+        for (int l = 0; l < 32 && !done; l++) {
+            const uint32_t sl = __shfl_sync(FULL, st, l);
+            if (sl == 0) { done = true; break; }            // ran past the first block
+            x = mine;
+            bcast_comp(x, l);
+            comp_compose(x, acc, nxt);
+            acc = nxt;
+            if (sl == 2 || (acc.kind & K_TYPE) == K_CLOSED) done = true;
+        }
+    }
+}
+
 template <int NW, int NT, int NB>
 __global__ void __launch_bounds__(KCfg<NW, NT>::THREADS, 1) rrx_scan_kernel(const __grid_constant__ ScanParams sp) {
     using K = KCfg<NW, NT>;
@@ -63,7 +245,7 @@ __global__ void __launch_bounds__(KCfg<NW, NT>::THREADS, 1) rrx_scan_kernel(cons
     for (;;) {
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(sp.ticket, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
+        tile = __shfl_sync(FULL, tile, 0);
         if (tile >= sp.num_tiles) break;
         ts.row0 = (uint64_t)tile * TILE_ROWS;
 
@@ -87,23 +269,32 @@ __global__ void __launch_bounds__(KCfg<NW, NT>::THREADS, 1) rrx_scan_kernel(cons
 
         phase_a<NW>(sp, pv, fw, ts, lane);
         const uint32_t my_kind = ts.sum_kind[lane];
-        const bool any_open = __any_sync(0xffffffffu, my_kind == K_RANK1 || my_kind == K_HARD) != 0;
+        const bool any_open = __any_sync(FULL, my_kind == K_RANK1 || my_kind == K_HARD) != 0;
         __syncwarp();
-        if (lane == 0) phase_s<NW>(sp, pv, fw, ts, tile, any_open);
+        SLocal<NW> L;
+        Comp<NW> agg, acc, inc;
+        if (lane == 0) { phase_s1<NW>(sp, pv, fw, ts, any_open, L); agg = L.run; } else { comp_ident(agg); }
+        bcast_comp(agg, 0);
+        lookback_state<NW>(sp, tile, agg, lane, acc);
+        if (lane == 0) {
+            phase_s2<NW>(sp, pv, fw, ts, L, acc, inc);
+            publish_comp<NW>(sp.st_i0, sp.f_i0, tile, inc);
+            const uint32_t rest = sp.num_tiles - (tile & ~31u);
+            if ((tile & 31u) == (rest < 32u ? rest : 32u) - 1u) publish_comp<NW>(sp.st_i1, sp.f_i1, tile >> 5, inc);
+            if (tile + 1 == sp.num_tiles) store_comp_global<NW>(sp.shard_comp, inc);
+        }
         __syncwarp();
         const uint32_t c = phase_b<NW>(sp, pv, fw, ts, lane, any_open);
         // exclusive offsets of the rows' matches inside the tile
-        uint32_t inc = c;
+        uint32_t inc_c = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += v;
+            const uint32_t v = __shfl_up_sync(FULL, inc_c, d);
+            if (lane >= d) inc_c += v;
         }
-        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-        const uint32_t offset = inc - c;
-        unsigned long long base = 0;
-        if (lane == 0) base = phase_c0(sp, tile, total);
-        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t total = __shfl_sync(FULL, inc_c, 31);
+        const uint32_t offset = inc_c - c;
+        const unsigned long long base = lookback_count(sp, tile, total, lane);
         if (total) {
             uint32_t hit[4];
 #pragma unroll

@@ -291,9 +291,22 @@ struct ScanParams {
     uint32_t num_tiles;
     uint32_t static_closed;     // 1: every row is closed by construction (acyclic E', depth < ROW_BYTES)
     uint32_t* ticket;
-    volatile uint32_t* tflag;   // [num_tiles] 0 none, 1 aggregate, 2 inclusive
-    uint32_t* tpay;             // [num_tiles][2][1+3*NW] composites (aggregate, inclusive)
-    volatile unsigned long long* cstatus;   // [num_tiles] (flag<<62)|count
+    // Two-level decoupled look-back (tiles, blocks of 32 tiles), see rrx_scan.cu.
+    // state composites: payload arrays of 1+3*NW words per entry, ready flags apart (zeroed per scan)
+    uint32_t* st_a0;            // [tiles]  tile aggregates
+    uint32_t* st_i0;            // [tiles]  tile inclusive composites (relative to the shard entry)
+    uint32_t* st_a1;            // [blocks] block aggregates
+    uint32_t* st_i1;            // [blocks] block inclusive composites
+    volatile uint32_t* f_a0;    // [tiles]
+    volatile uint32_t* f_i0;    // [tiles]
+    volatile uint32_t* f_a1;    // [blocks]
+    volatile uint32_t* f_i1;    // [blocks]
+    uint32_t* st_arrive;        // [blocks] tiles of the block that have published their aggregate
+    // match counts: 64-bit words, bit 63 = ready
+    volatile unsigned long long* ct_a0;   // [tiles]  matches of the tile
+    volatile unsigned long long* ct_a1;   // [blocks] matches of the block
+    volatile unsigned long long* ct_i1;   // [blocks] matches up to and including the block
+    uint32_t* ct_arrive;        // [blocks]
     long long* out;             // (start,end) pairs
     uint64_t out_cap;
     unsigned long long* total;  // [0] match count, [1] pending count
@@ -542,51 +555,61 @@ RRX_DEV void row_replay_exit(const ScanParams& sp, const ProgView& pv, const F& 
     }
 }
 
-// ===== phase S (one lane): compose the rows, publish the tile, look back for the tile's entry ======
-// After this phase sum_* of row t hold the composite of rows [0,t) of the tile (what turns the
-// tile entry into row t's entry) and misc[M_ENTRY..] holds the tile's exact entry set.
+// ===== phase S (one lane) ===============================================================================
+// S1: compose the rows into the tile aggregate (no global traffic).
+// [look-back: yields the composite of everything before the tile]
+// S2: tile entry, blocked segment, inclusive composite.
+// After S2 sum_* of row t hold the composite of rows [0,t) of the tile (what turns the tile entry
+// into row t's entry) and misc[M_ENTRY..] holds the tile's exact entry set.
+template <int NW> struct SLocal {
+    Comp<NW> run;          // tile aggregate (kind K_WAIT if it cannot be summarised)
+    Comp<NW> pre_block;    // composite of the rows before the blocked segment
+    int blocked_from, resume_at;
+    bool wait_agg;
+};
+
 template <int NW, class F>
-RRX_DEV void phase_s(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, uint32_t tile,
-                     bool any_open) {
+RRX_DEV void phase_s1(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, bool any_open,
+                      SLocal<NW>& L) {
     constexpr int ROWS = TILE_ROWS;
-    using TS = TileState<NW>;
-    Comp<NW> run, rowc, nxt, pre_block;
-    comp_ident(run);
-    comp_ident(pre_block);
+    Comp<NW> rowc, nxt;
+    comp_ident(L.run);
+    comp_ident(L.pre_block);
     comp_ident(nxt);
-    int blocked_from = -1, resume_at = ROWS;
-    bool wait_agg = false;
+    L.blocked_from = -1;
+    L.resume_at = ROWS;
+    L.wait_agg = false;
     if (any_open) {
         for (int t = 0; t < ROWS; t++) {
-            if (blocked_from >= 0 && t < resume_at) continue;     // inside the blocked segment
+            if (L.blocked_from >= 0 && t < L.resume_at) continue;     // inside the blocked segment
             load_row_comp(ts, t, rowc);
-            if ((rowc.kind & K_TYPE) == K_HARD && (run.kind & K_TYPE) != K_CLOSED) {
+            if ((rowc.kind & K_TYPE) == K_HARD && (L.run.kind & K_TYPE) != K_CLOSED) {
                 // A row we cannot summarise, reached with a state that still depends on the tile
                 // entry.  Everything up to the next closed row has to wait for the look-back.
-                blocked_from = t;
-                pre_block = run;
+                L.blocked_from = t;
+                L.pre_block = L.run;
                 int c = -1;
                 for (int u = t + 1; u < ROWS; u++) if ((ts.sum_kind[u] & K_TYPE) == K_CLOSED) { c = u; break; }
-                if (c < 0) { wait_agg = true; resume_at = ROWS; break; }
-                resume_at = c + 1;
+                if (c < 0) { L.wait_agg = true; L.resume_at = ROWS; break; }
+                L.resume_at = c + 1;
                 uint32_t bc[NW];
 #pragma unroll
                 for (int w = 0; w < NW; w++) bc[w] = ts.sum_b[w * ROWS + c];
-                comp_closed(run, bc, 0);
+                comp_closed(L.run, bc, 0);
                 continue;
             }
-            store_row_comp(ts, t, run);
+            store_row_comp(ts, t, L.run);
             if ((rowc.kind & K_TYPE) == K_HARD) {                  // exact state: replay the row
                 uint32_t X[NW];
 #pragma unroll
-                for (int w = 0; w < NW; w++) X[w] = run.b[w];
+                for (int w = 0; w < NW; w++) X[w] = L.run.b[w];
                 row_replay_exit<NW>(sp, pv, fw, ts, t, X);
 #pragma unroll
                 for (int w = 0; w < NW; w++) X[w] |= rowc.b[w];
-                comp_closed(run, X, run.kind & K_OPAQUE);
+                comp_closed(L.run, X, L.run.kind & K_OPAQUE);
             } else {
-                comp_compose(run, rowc, nxt);
-                run = nxt;
+                comp_compose(L.run, rowc, nxt);
+                L.run = nxt;
             }
         }
     } else {
@@ -594,49 +617,26 @@ RRX_DEV void phase_s(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
         // the row before it; nothing to rewrite, only the tile aggregate is needed.
         int last = -1;
         for (int t = ROWS - 1; t >= 0; t--) if (ts.sum_kind[t] != K_IDENT) { last = t; break; }
-        if (last >= 0) load_row_comp(ts, last, run);
+        if (last >= 0) load_row_comp(ts, last, L.run);
     }
-    if (wait_agg) run.kind = K_WAIT;
-    const size_t stride = 2 * (size_t)(1 + 3 * NW);
-    uint32_t* mine = sp.tpay + (size_t)tile * stride;
-    // aggregate first, so that successors can start looking back
-    if (tile > 0) {
-        store_comp_global<NW>(mine, run);
-        rrx_fence();
-        sp.tflag[tile] = 1;
-    }
-    // look back
-    Comp<NW> acc;
-    comp_ident(acc);
-    for (int64_t j = (int64_t)tile - 1; j >= 0; j--) {
-        uint32_t fl;
-        while ((fl = sp.tflag[j]) == 0) rrx_backoff();
-        rrx_fence();
-        Comp<NW> x;
-        comp_ident(x);
-        if (fl == 1) {
-            load_comp_global<NW>(sp.tpay + (size_t)j * stride, x);
-            if ((x.kind & K_TYPE) == K_WAIT) {
-                while (sp.tflag[j] != 2) rrx_backoff();
-                rrx_fence();
-                fl = 2;
-            }
-        }
-        if (fl == 2) load_comp_global<NW>(sp.tpay + (size_t)j * stride + (1 + 3 * NW), x);
-        comp_compose(x, acc, nxt);
-        acc = nxt;
-        if (fl == 2 || (acc.kind & K_TYPE) == K_CLOSED) break;
-    }
+    if (L.wait_agg) L.run.kind = K_WAIT;
+}
+
+// `acc` = composite of the whole shard before this tile.  Returns the tile's inclusive composite.
+template <int NW, class F>
+RRX_DEV void phase_s2(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, const SLocal<NW>& L,
+                      const Comp<NW>& acc, Comp<NW>& inc) {
+    using TS = TileState<NW>;
     uint32_t E[NW];
     comp_apply<NW>(acc, sp.entry, E);
 #pragma unroll
     for (int w = 0; w < NW; w++) ts.misc[TS::M_ENTRY + w] = E[w];
-    if (blocked_from >= 0) {
+    if (L.blocked_from >= 0) {
         // second stage: walk the blocked segment with exact states
         uint32_t X[NW], Y[NW];
-        comp_apply<NW>(pre_block, E, X);
-        Comp<NW> ex;
-        for (int t = blocked_from; t < resume_at; t++) {
+        comp_apply<NW>(L.pre_block, E, X);
+        Comp<NW> ex, rowc;
+        for (int t = L.blocked_from; t < L.resume_at; t++) {
             load_row_comp(ts, t, rowc);
             comp_closed(ex, X, 0);
             store_row_comp(ts, t, ex);
@@ -653,13 +653,9 @@ RRX_DEV void phase_s(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
                 for (int w = 0; w < NW; w++) X[w] = Y[w];
             }
         }
-        if (wait_agg) comp_closed(nxt, X, K_OPAQUE);
+        if (L.wait_agg) { comp_closed(inc, X, K_OPAQUE); return; }
     }
-    if (!wait_agg) comp_compose(acc, run, nxt);   // inclusive composite (relative to the shard entry)
-    store_comp_global<NW>(mine + (1 + 3 * NW), nxt);
-    rrx_fence();
-    sp.tflag[tile] = 2;
-    if (tile + 1 == sp.num_tiles) store_comp_global<NW>(sp.shard_comp, nxt);
+    comp_compose(acc, L.run, inc);   // inclusive composite (relative to the shard entry)
 }
 
 // ===== phase B: replay each row's prefix from its exact entry set (no injection) ====================
@@ -704,25 +700,6 @@ RRX_DEV uint32_t phase_b(const ScanParams& sp, const ProgView& pv, const F& fw, 
         c += (uint32_t)popc32(v);
     }
     return c;
-}
-
-// ===== phase C0 (one lane): look back for the tile's output base ===================================
-// `total` = matches of the tile.  Returns the index of the tile's first match in the output.
-RRX_DEV unsigned long long phase_c0(const ScanParams& sp, uint32_t tile, uint32_t total) {
-    const unsigned long long FL1 = 1ull << 62, FL2 = 2ull << 62, VM = (1ull << 62) - 1;
-    unsigned long long base = 0;
-    if (tile > 0) {
-        sp.cstatus[tile] = FL1 | total;
-        for (int64_t j = (int64_t)tile - 1; j >= 0; j--) {
-            unsigned long long v;
-            while (((v = sp.cstatus[j]) >> 62) == 0) rrx_backoff();
-            base += v & VM;
-            if ((v >> 62) == 2) break;
-        }
-    }
-    sp.cstatus[tile] = FL2 | (base + total);
-    if (tile + 1 == sp.num_tiles) sp.total[0] = base + total;
-    return base;
 }
 
 // ===== phase C: resolve the lazy start of every match and write (start,end) ========================

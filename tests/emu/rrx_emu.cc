@@ -31,8 +31,8 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
     std::vector<uint8_t> smem(TS::bytes() + 64, 0xAA);
     std::vector<uint32_t> btab(NW == 1 ? 256 * 32 : 256 * NW);
     for (uint32_t i = 0; i < btab.size(); i++) btab[i] = prog.blob[h.off_B + (NW == 1 ? (i >> 5) : i)];
-    std::vector<uint32_t> tflag(num_tiles + 1, 0), tpay((size_t)(num_tiles + 1) * 2 * (1 + 3 * NW), 0);
-    std::vector<unsigned long long> cstatus(num_tiles + 1, 0);
+    std::vector<uint32_t> incl((size_t)(num_tiles + 1) * (1 + 3 * NW), 0);   // inclusive composite per tile
+    unsigned long long matches_so_far = 0;
     unsigned long long total[2] = {0, 0};
     uint32_t ticket = 0;
     *err = 0;
@@ -47,9 +47,6 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
     sp.num_tiles = num_tiles;
     sp.static_closed = (h.static_depth != 0xffffffffu && h.static_depth + 1 <= (uint32_t)ROW_BYTES) ? 1u : 0u;
     sp.ticket = &ticket;
-    sp.tflag = tflag.data();
-    sp.tpay = tpay.data();
-    sp.cstatus = cstatus.data();
     sp.out = reinterpret_cast<long long*>(out);
     sp.out_cap = cap;
     sp.total = total;
@@ -94,7 +91,16 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
             ProgView pv = view(0);
             Prog<NW, NT, NB> fw;
             fw.init(pv);
-            phase_s<NW>(sp, pv, fw, ts, tile, any_open);
+            // The emulator runs the tiles in order, so "look-back" is just the previous tile's
+            // inclusive composite; the two-level GPU look-back (rrx_scan.cu) is exercised by -m gpu.
+            SLocal<NW> L;
+            Comp<NW> acc, inc;
+            phase_s1<NW>(sp, pv, fw, ts, any_open, L);
+            if (tile == 0) comp_ident(acc);
+            else load_comp_global<NW>(incl.data() + (size_t)(tile - 1) * (1 + 3 * NW), acc);
+            phase_s2<NW>(sp, pv, fw, ts, L, acc, inc);
+            store_comp_global<NW>(incl.data() + (size_t)tile * (1 + 3 * NW), inc);
+            if (tile + 1 == num_tiles) store_comp_global<NW>(sp.shard_comp, inc);
         }
         uint32_t cnt[ROWS], off[ROWS], total_t = 0;
         for (int t = 0; t < ROWS; t++) {
@@ -104,7 +110,9 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
             cnt[t] = phase_b<NW>(sp, pv, fw, ts, t, any_open);
         }
         for (int t = 0; t < ROWS; t++) { off[t] = total_t; total_t += cnt[t]; }
-        const unsigned long long b0 = phase_c0(sp, tile, total_t);
+        const unsigned long long b0 = matches_so_far;
+        matches_so_far += total_t;
+        if (tile + 1 == num_tiles) total[0] = matches_so_far;
         if (total_t) {
             uint32_t hit[ROWS][4];
             for (int t = 0; t < ROWS; t++) for (int q = 0; q < 4; q++) hit[t][q] = ts.hits[q * ROWS + t];

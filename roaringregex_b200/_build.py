@@ -7,9 +7,10 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-LIB = os.path.join(PKG, "librrx.so")
-SOURCES = ["rrx_capi.cu", "rrx_scan.cu", "rrx_corpus.cu", "rrx_compile.cc"]
-HEADERS = ["rrx_compile.h", "rrx_scan.h", "rrx_tile.cuh", os.path.join("..", "..", "include", "rrx.h")]
+_VARIANT = os.environ.get("RRX_VARIANT", "")          # e.g. "timing": builds librrx_timing.so with -DRRX_PHASE_TIMING
+LIB = os.path.join(PKG, f"librrx_{_VARIANT}.so" if _VARIANT else "librrx.so")
+SOURCES = ["rrx_capi.cu", "rrx_scan.cu", "rrx_order.cu", "rrx_corpus.cu", "rrx_compile.cc"]
+HEADERS = ["rrx_compile.h", "rrx_prog.h", "rrx_scan.h", "rrx_tile.cuh", os.path.join("..", "..", "include", "rrx.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr", "-Xcompiler", "-Wno-unknown-pragmas"]
 
@@ -26,7 +27,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = ["-DRRX_PHASE_TIMING"] if _VARIANT == "timing" else []
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -24,23 +25,18 @@ int cuda_err(cudaError_t e, const char* what) {
 #define RRX_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_err(e_, #call); } while (0)
 
 // Control block of a scan over T tiles (B = ceil(T/32) blocks); everything in it is zeroed before
-// the scan: [ticket,err,total[2],pad | f_a0[T] f_i0[T] f_a1[B] f_i1[B] st_arrive[B] ct_arrive[B] |
-// ct_a0[T] ct_a1[B] ct_i1[B] (64-bit)].  Returns the size; fills the nine offsets.
+// the scan: [ticket,err,total[2],pad | f_a0[T] f_i0[T] f_a1[B] f_i1[B] st_arrive[B]].
+// Returns the size; fills the five offsets.
 size_t ctrl_layout(size_t T, size_t* off) {
     const size_t B = (T + 31) / 32;
-    size_t o = 32, tmp[10];
+    size_t o = 32, tmp[8];
     size_t* f = off ? off : tmp;
     f[0] = o; o += 4 * T;
     f[1] = o; o += 4 * T;
     f[2] = o; o += 4 * B;
     f[3] = o; o += 4 * B;
     f[4] = o; o += 4 * B;
-    f[5] = o; o += 4 * B;
-    o = (o + 7) & ~(size_t)7;
-    f[6] = o; o += 8 * T;
-    f[7] = o; o += 8 * B;
-    f[8] = o; o += 8 * B;
-    return o;
+    return (o + 15) & ~(size_t)15;
 }
 }  // namespace
 
@@ -58,7 +54,11 @@ struct rrx_scanner {
     uint8_t* d_ctrl = nullptr;      // header + look-back flags and counters, zeroed before every scan
     size_t ctrl_bytes = 0;
     uint32_t* d_tpay = nullptr;
-    long long* d_out = nullptr;
+    long long* d_out = nullptr;      // matches in text order
+    long long* d_stage = nullptr;    // matches in tile-completion order (scan kernel output)
+    unsigned long long* d_tile_seg = nullptr;
+    uint32_t* d_tile_cnt = nullptr;
+    unsigned long long* d_chunk = nullptr;
     uint32_t* d_shard = nullptr;
     PendingStart* d_pending = nullptr;
     uint32_t pending_cap = 4096;
@@ -154,6 +154,7 @@ void rrx_scanner_free(rrx_scanner* s) {
     if (!s) return;
     cudaFree(s->d_prog); cudaFree(s->d_ctrl); cudaFree(s->d_tpay);
     if (s->owns_out) cudaFree(s->d_out);
+    cudaFree(s->d_stage); cudaFree(s->d_tile_seg); cudaFree(s->d_tile_cnt); cudaFree(s->d_chunk);
     cudaFree(s->d_shard); cudaFree(s->d_pending);
     if (s->h_ctr) cudaFreeHost(s->h_ctr);
     delete s;
@@ -182,6 +183,10 @@ int rrx_scanner_create(const rrx_program* p, uint64_t max_len, uint64_t capacity
     RRX_CUDA(cudaMalloc(&s->d_ctrl, s->ctrl_bytes));
     RRX_CUDA(cudaMalloc(&s->d_tpay, (2 * s->max_tiles + 2 * ((s->max_tiles + 31) / 32)) * (1 + 3 * (size_t)h.NW) * 4));
     RRX_CUDA(cudaMalloc(&s->d_out, s->capacity * 16));
+    RRX_CUDA(cudaMalloc(&s->d_stage, s->capacity * 16));
+    RRX_CUDA(cudaMalloc(&s->d_tile_seg, s->max_tiles * 8));
+    RRX_CUDA(cudaMalloc(&s->d_tile_cnt, s->max_tiles * 4));
+    RRX_CUDA(cudaMalloc(&s->d_chunk, ((s->max_tiles + 1023) / 1024 + 1) * 8));
     RRX_CUDA(cudaMalloc(&s->d_shard, (1 + 3 * (size_t)h.NW) * 4));
     RRX_CUDA(cudaMalloc(&s->d_pending, sizeof(PendingStart) * s->pending_cap));
     RRX_CUDA(cudaMallocHost(&s->h_ctr, 32));
@@ -207,6 +212,24 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     sp.prog = s->d_prog;
     sp.num_tiles = (uint32_t)((len + tile_bytes - 1) / tile_bytes);
     sp.static_closed = (h.static_depth != 0xffffffffu && h.static_depth + 1 <= (uint32_t)ROW_BYTES) ? 1u : 0u;
+    {
+        const char* e = getenv("RRX_STAGGER_NS");
+        sp.stagger_ns = e ? (uint32_t)atoi(e) : 1500u;
+    }
+#ifdef RRX_PHASE_TIMING
+    {
+        static unsigned long long* d_ph = nullptr;
+        if (!d_ph) { cudaMalloc(&d_ph, 64); cudaMemset(d_ph, 0, 64); }
+        sp.phase_cycles = d_ph;
+        if (getenv("RRX_PHASE_DUMP")) {
+            unsigned long long h[8];
+            cudaMemcpy(h, d_ph, 64, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "phase cycles: ticket %llu load %llu A+S1 %llu lookback_state %llu S2+publish %llu B %llu lookback_count %llu C %llu\n",
+                    h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+            cudaMemset(d_ph, 0, 64);
+        }
+    }
+#endif
     uint8_t* c = s->d_ctrl;
     size_t off[10];
     const size_t used = ctrl_layout(sp.num_tiles, off);
@@ -219,15 +242,13 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     sp.f_a1 = reinterpret_cast<volatile uint32_t*>(c + off[2]);
     sp.f_i1 = reinterpret_cast<volatile uint32_t*>(c + off[3]);
     sp.st_arrive = reinterpret_cast<uint32_t*>(c + off[4]);
-    sp.ct_arrive = reinterpret_cast<uint32_t*>(c + off[5]);
-    sp.ct_a0 = reinterpret_cast<volatile unsigned long long*>(c + off[6]);
-    sp.ct_a1 = reinterpret_cast<volatile unsigned long long*>(c + off[7]);
-    sp.ct_i1 = reinterpret_cast<volatile unsigned long long*>(c + off[8]);
+    sp.tile_seg = s->d_tile_seg;
+    sp.tile_cnt = s->d_tile_cnt;
     sp.st_a0 = s->d_tpay;
     sp.st_i0 = sp.st_a0 + T * PW;
     sp.st_a1 = sp.st_i0 + T * PW;
     sp.st_i1 = sp.st_a1 + B * PW;
-    sp.out = s->d_out;
+    sp.out = s->d_stage;
     sp.out_cap = s->capacity;
     sp.shard_comp = s->d_shard;
     sp.pending = s->d_pending;
@@ -235,6 +256,8 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     if (opts && opts->entry) for (uint32_t w = 0; w < h.NW; w++) sp.entry[w] = opts->entry[w];
     s->launches = 0;
     RRX_CUDA(cudaMemsetAsync(s->d_ctrl, 0, used, st));
+    if (h.NW == 1)      // one-word automata keep the ready bit inside the 16-byte composite words
+        RRX_CUDA(cudaMemsetAsync(s->d_tpay, 0, (2 * T + 2 * B) * PW * 4, st));
     if (sp.num_tiles == 0) {
         // empty text: identity transfer function, no matches
         uint32_t ident[1 + 3 * RRX_NW_MAX] = {K_IDENT};
@@ -244,7 +267,9 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     int grid = 0;
     cudaError_t e = launch_scan(sp, h, s->sm_count, st, &grid);
     if (e != cudaSuccess) return cuda_err(e, "rrx_scan_kernel launch");
-    s->launches = 1;
+    e = launch_order(s->d_tile_cnt, s->d_tile_seg, sp.num_tiles, s->d_chunk, s->d_stage, s->d_out, s->capacity, st);
+    if (e != cudaSuccess) return cuda_err(e, "ordering pass launch");
+    s->launches = 4;
     return RRX_OK;
 }
 

@@ -1,0 +1,116 @@
+// Ordering pass: the scan kernel leaves every tile's matches in a contiguous segment of the
+// staging list, segments in tile-COMPLETION order.  Three small launches put them in tile order
+// (= ascending end offset, the order the reference's iterator would produce them in):
+//   chunk_sums   per chunk of 1024 tiles: number of matches
+//   chunk_scan   exclusive scan of the chunk sums (one CTA)
+//   gather       per chunk: block scan of the tile counts, then one warp per tile copies its segment
+// Cost: one extra read + write of the match list (16 B per match each way), usually served from L2.
+#include "rrx_scan.h"
+#include "rrx_tile.cuh"
+
+namespace rrx {
+namespace {
+
+constexpr int CHUNK = 1024;
+
+__device__ __forceinline__ unsigned long long block_sum_1024(unsigned long long v, unsigned long long* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    unsigned long long t = threadIdx.x < 32 ? sh[threadIdx.x] : 0ull;
+    if (warp == 0) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+        if (lane == 0) sh[32] = t;
+    }
+    __syncthreads();
+    return sh[32];
+}
+
+// exclusive scan over the 1024 threads of the CTA; also returns the CTA total in *total
+__device__ __forceinline__ unsigned long long block_excl_1024(unsigned long long v, unsigned long long* sh, unsigned long long* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += u;
+    }
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long w = sh[lane], winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += u;
+        }
+        sh[lane] = winc - w;
+        if (lane == 31) sh[32] = winc;
+    }
+    __syncthreads();
+    const unsigned long long res = sh[warp] + inc - v;
+    if (total) *total = sh[32];
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(CHUNK) chunk_sums_kernel(const uint32_t* tile_cnt, uint32_t num_tiles, unsigned long long* chunk_sum) {
+    __shared__ unsigned long long sh[33];
+    const uint32_t t = blockIdx.x * CHUNK + threadIdx.x;
+    const unsigned long long v = t < num_tiles ? tile_cnt[t] : 0u;
+    const unsigned long long s = block_sum_1024(v, sh);
+    if (threadIdx.x == 0) chunk_sum[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(CHUNK) chunk_scan_kernel(unsigned long long* chunk_sum, uint32_t nchunks) {
+    __shared__ unsigned long long sh[33];
+    unsigned long long carry = 0;
+    for (uint32_t base = 0; base < nchunks; base += CHUNK) {
+        const uint32_t i = base + threadIdx.x;
+        const unsigned long long v = i < nchunks ? chunk_sum[i] : 0ull;
+        unsigned long long tot;
+        const unsigned long long ex = block_excl_1024(v, sh, &tot);
+        if (i < nchunks) chunk_sum[i] = carry + ex;
+        carry += tot;
+    }
+}
+
+__global__ void __launch_bounds__(CHUNK) gather_kernel(const uint32_t* tile_cnt, const unsigned long long* tile_seg, uint32_t num_tiles,
+                                                       const unsigned long long* chunk_off, const longlong2* staging, longlong2* out,
+                                                       unsigned long long cap) {
+    __shared__ unsigned long long sh[33];
+    __shared__ unsigned long long off[CHUNK];
+    const uint32_t t = blockIdx.x * CHUNK + threadIdx.x;
+    const unsigned long long v = t < num_tiles ? tile_cnt[t] : 0u;
+    off[threadIdx.x] = chunk_off[blockIdx.x] + block_excl_1024(v, sh, nullptr);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = warp; i < CHUNK; i += 32) {
+        const uint32_t tt = blockIdx.x * CHUNK + i;
+        if (tt >= num_tiles) break;
+        const uint32_t n = tile_cnt[tt];
+        if (!n) continue;
+        const unsigned long long src = tile_seg[tt], dst = off[i];
+        for (uint32_t k = lane; k < n; k += 32)
+            if (src + k < cap && dst + k < cap) out[dst + k] = staging[src + k];
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_order(const uint32_t* tile_cnt, const unsigned long long* tile_seg, uint32_t num_tiles,
+                         unsigned long long* chunk_scratch, const long long* staging, long long* out, uint64_t cap,
+                         cudaStream_t st) {
+    if (!num_tiles) return cudaSuccess;
+    const uint32_t nchunks = (num_tiles + CHUNK - 1) / CHUNK;
+    chunk_sums_kernel<<<nchunks, CHUNK, 0, st>>>(tile_cnt, num_tiles, chunk_scratch);
+    chunk_scan_kernel<<<1, CHUNK, 0, st>>>(chunk_scratch, nchunks);
+    gather_kernel<<<nchunks, CHUNK, 0, st>>>(tile_cnt, tile_seg, num_tiles, chunk_scratch,
+                                             reinterpret_cast<const longlong2*>(staging), reinterpret_cast<longlong2*>(out), cap);
+    return cudaGetLastError();
+}
+
+}  // namespace rrx

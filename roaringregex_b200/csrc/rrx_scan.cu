@@ -45,72 +45,12 @@ template <int NW, int NT> struct KCfg {
 // inclusive value — the producer only ever waits on smaller tile indices).
 // =====================================================================================================
 constexpr unsigned FULL = 0xffffffffu;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 constexpr unsigned long long CT_READY = 1ull << 63;
-
-__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
-    return v;
-}
-
-// match counts (commutative): returns the number of matches before `tile` (same value in all lanes)
-__device__ __forceinline__ unsigned long long lookback_count(const ScanParams& sp, uint32_t tile, uint32_t total, int lane) {
-    const uint32_t b = tile >> 5, k = tile & 31;
-    const uint32_t rest = sp.num_tiles - (b << 5);
-    const uint32_t nblk = rest < 32u ? rest : 32u;
-    uint32_t old = 0;
-    if (lane == 0) {
-        sp.ct_a0[tile] = CT_READY | total;
-        __threadfence();
-        old = atomicAdd(sp.ct_arrive + b, 1u);
-    }
-    old = __shfl_sync(FULL, old, 0);
-    if (old == nblk - 1) {                                  // all aggregates of the block are out
-        __threadfence();
-        unsigned long long v = 0;
-        if ((uint32_t)lane < nblk) {
-            while (!((v = sp.ct_a0[(b << 5) + lane]) & CT_READY)) rrx_backoff();
-            v &= ~CT_READY;
-        }
-        v = warp_sum(v);
-        if (lane == 0) sp.ct_a1[b] = CT_READY | v;
-    }
-    unsigned long long x = 0;
-    if ((uint32_t)lane < k) {
-        unsigned long long v;
-        while (!((v = sp.ct_a0[(b << 5) + lane]) & CT_READY)) rrx_backoff();
-        x = v & ~CT_READY;
-    }
-    x = warp_sum(x);
-    unsigned long long base = 0;
-    for (int64_t jb = (int64_t)b - 1; jb >= 0; jb -= 32) {
-        const int64_t my = jb - lane;
-        unsigned long long v = 0;
-        bool inc = false;
-        if (my >= 0) {
-            for (;;) {
-                const unsigned long long vi = sp.ct_i1[my];
-                if (vi & CT_READY) { v = vi & ~CT_READY; inc = true; break; }
-                const unsigned long long va = sp.ct_a1[my];
-                if (va & CT_READY) { v = va & ~CT_READY; break; }
-                rrx_backoff();
-            }
-        }
-        const unsigned bal = __ballot_sync(FULL, inc);
-        if (bal) {
-            const int first = __ffs((int)bal) - 1;
-            base += warp_sum(lane <= first ? v : 0ull);
-            break;
-        }
-        base += warp_sum(v);
-    }
-    const unsigned long long res = base + x;
-    if (lane == 0) {
-        if (k == nblk - 1) sp.ct_i1[b] = CT_READY | (res + total);
-        if (tile + 1 == sp.num_tiles) sp.total[0] = res + total;
-    }
-    return res;
-}
 
 template <int NW> __device__ __forceinline__ void bcast_comp(Comp<NW>& c, int src) {
     c.kind = __shfl_sync(FULL, c.kind, src);
@@ -121,15 +61,37 @@ template <int NW> __device__ __forceinline__ void bcast_comp(Comp<NW>& c, int sr
         c.P[w] = __shfl_sync(FULL, c.P[w], src);
     }
 }
+// Publishing / awaiting a composite.  NW == 1: the composite and its ready bit form ONE aligned
+// 16-byte word {kind|READY, b, U, P}, stored and loaded with single 128-bit accesses (not torn on
+// this hardware; the same assumption CUB's decoupled look-back makes for its 16-byte tile
+// descriptors), so no fence is needed.  NW > 1: payload, fence, then a separate flag word.
+constexpr uint32_t K_READY = 0x80000000u;
 template <int NW> __device__ __forceinline__ void publish_comp(uint32_t* pay, volatile uint32_t* flag, size_t idx, const Comp<NW>& c) {
-    store_comp_global<NW>(pay + idx * (1 + 3 * NW), c);
-    __threadfence();
-    flag[idx] = 1u;
+    if (NW == 1) {
+        const uint4 v = make_uint4(c.kind | K_READY, c.b[0], c.U[0], c.P[0]);
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(pay + idx * 4), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    } else {
+        store_comp_global<NW>(pay + idx * (1 + 3 * NW), c);
+        __threadfence();
+        flag[idx] = 1u;
+    }
+}
+template <int NW> __device__ __forceinline__ bool try_comp(const uint32_t* pay, volatile uint32_t* flag, size_t idx, Comp<NW>& c) {
+    if (NW == 1) {
+        uint4 v;
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(pay + idx * 4) : "memory");
+        if (!(v.x & K_READY)) return false;
+        c.kind = v.x & ~K_READY; c.b[0] = v.y; c.U[0] = v.z; c.P[0] = v.w;
+        return true;
+    } else {
+        if (flag[idx] == 0u) return false;
+        __threadfence();
+        load_comp_global<NW>(pay + idx * (1 + 3 * NW), c);
+        return true;
+    }
 }
 template <int NW> __device__ __forceinline__ void wait_comp(const uint32_t* pay, volatile uint32_t* flag, size_t idx, Comp<NW>& c) {
-    while (flag[idx] == 0u) rrx_backoff();
-    __threadfence();
-    load_comp_global<NW>(pay + idx * (1 + 3 * NW), c);
+    while (!try_comp<NW>(pay, flag, idx, c)) rrx_backoff();
 }
 
 // state composites (ordered): all lanes pass the same `agg`; `acc` = composite of everything before
@@ -143,12 +105,11 @@ __device__ __forceinline__ void lookback_state(const ScanParams& sp, uint32_t ti
     uint32_t old = 0;
     if (lane == 0) {
         publish_comp<NW>(sp.st_a0, sp.f_a0, tile, agg);
-        __threadfence();
+        if (NW > 1) __threadfence();
         old = atomicAdd(sp.st_arrive + b, 1u);
     }
     old = __shfl_sync(FULL, old, 0);
     if (old == nblk - 1) {                                  // fold the block aggregate, in tile order
-        __threadfence();
         comp_ident(mine);
         if ((uint32_t)lane < nblk) wait_comp<NW>(sp.st_a0, sp.f_a0, (size_t)(b << 5) + lane, mine);
         Comp<NW> fold;
@@ -164,6 +125,11 @@ __device__ __forceinline__ void lookback_state(const ScanParams& sp, uint32_t ti
         if (has_wait) fold.kind = K_WAIT;
         if (lane == 0) publish_comp<NW>(sp.st_a1, sp.f_a1, b, fold);
     }
+    // (0) shortcut: if the tile right before this one is closed, nothing earlier matters
+    comp_ident(acc);
+    if (tile == 0) return;
+    wait_comp<NW>(sp.st_a0, sp.f_a0, (size_t)tile - 1, x);
+    if ((x.kind & K_TYPE) == K_CLOSED) { acc = x; return; }
     // (a) the tiles before this one inside the block, nearest first
     comp_ident(mine);
     if ((uint32_t)lane < k) wait_comp<NW>(sp.st_a0, sp.f_a0, (size_t)(b << 5) + lane, mine);
@@ -187,9 +153,8 @@ __device__ __forceinline__ void lookback_state(const ScanParams& sp, uint32_t ti
         comp_ident(mine);
         if (my >= 0) {
             for (;;) {
-                if (sp.f_i1[my]) { wait_comp<NW>(sp.st_i1, sp.f_i1, (size_t)my, mine); st = 2; break; }
-                if (sp.f_a1[my]) {
-                    wait_comp<NW>(sp.st_a1, sp.f_a1, (size_t)my, mine);
+                if (try_comp<NW>(sp.st_i1, sp.f_i1, (size_t)my, mine)) { st = 2; break; }
+                if (try_comp<NW>(sp.st_a1, sp.f_a1, (size_t)my, mine)) {
                     st = 1;
                     if ((mine.kind & K_TYPE) == K_WAIT) { wait_comp<NW>(sp.st_i1, sp.f_i1, (size_t)my, mine); st = 2; }
                     break;
@@ -208,6 +173,12 @@ __device__ __forceinline__ void lookback_state(const ScanParams& sp, uint32_t ti
         }
     }
 }
+
+#ifdef RRX_PHASE_TIMING
+#define RRX_T(i) { const long long now_ = clock64(); if (lane == 0 && sp.phase_cycles) atomicAdd(sp.phase_cycles + (i), (unsigned long long)(now_ - tprev_)); tprev_ = now_; }
+#else
+#define RRX_T(i)
+#endif
 
 template <int NW, int NT, int NB>
 __global__ void __launch_bounds__(KCfg<NW, NT>::THREADS, 1) rrx_scan_kernel(const __grid_constant__ ScanParams sp) {
@@ -241,14 +212,34 @@ __global__ void __launch_bounds__(KCfg<NW, NT>::THREADS, 1) rrx_scan_kernel(cons
     TS ts;
     ts.carve(regions + (size_t)warp * K::REGION);
     const int64_t len = (int64_t)sp.len;
+#ifdef RRX_PHASE_TIMING
+    long long tprev_ = clock64();
+#endif
 
+    // De-phase the warps of the SM: if all of them load, scan, look back and emit at the same
+    // moments, nobody computes while everybody waits for memory.  Tickets are taken in arrival
+    // order afterwards, so the offsets persist.
+    if (sp.stagger_ns) {
+        const unsigned long long t0 = globaltimer_ns();
+        const unsigned long long wait = (unsigned long long)(warp & 7) * sp.stagger_ns;
+        while (globaltimer_ns() - t0 < wait) __nanosleep(200);
+    }
+
+    // While a warp works on tile i it asks L2 to fetch tile i + (warps in flight) — the tile some
+    // warp (whichever finishes first) will pick up about one round from now — one 128-byte line per
+    // lane, so the staging loads of the next round hit L2 instead of queueing on HBM.
+    const uint32_t warps_in_flight = gridDim.x * (uint32_t)K::WARPS;
     for (;;) {
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(sp.ticket, 1u);
         tile = __shfl_sync(FULL, tile, 0);
         if (tile >= sp.num_tiles) break;
+        {
+            const int64_t g = (((int64_t)tile + warps_in_flight) * TILE_ROWS + lane) << ROW_SHIFT;
+            if (g < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp.text + g));
+        }
         ts.row0 = (uint64_t)tile * TILE_ROWS;
-
+        RRX_T(0)
         // ---- stage the tile: 8 x 128-bit loads per lane, fully coalesced, XOR-swizzled store ----
         {
             const int64_t g0 = ts.lo();
@@ -266,7 +257,7 @@ __global__ void __launch_bounds__(KCfg<NW, NT>::THREADS, 1) rrx_scan_kernel(cons
             }
         }
         __syncwarp();
-
+        RRX_T(1)
         phase_a<NW>(sp, pv, fw, ts, lane);
         const uint32_t my_kind = ts.sum_kind[lane];
         const bool any_open = __any_sync(FULL, my_kind == K_RANK1 || my_kind == K_HARD) != 0;
@@ -275,7 +266,9 @@ __global__ void __launch_bounds__(KCfg<NW, NT>::THREADS, 1) rrx_scan_kernel(cons
         Comp<NW> agg, acc, inc;
         if (lane == 0) { phase_s1<NW>(sp, pv, fw, ts, any_open, L); agg = L.run; } else { comp_ident(agg); }
         bcast_comp(agg, 0);
+        RRX_T(2)
         lookback_state<NW>(sp, tile, agg, lane, acc);
+        RRX_T(3)
         if (lane == 0) {
             phase_s2<NW>(sp, pv, fw, ts, L, acc, inc);
             publish_comp<NW>(sp.st_i0, sp.f_i0, tile, inc);
@@ -284,6 +277,7 @@ __global__ void __launch_bounds__(KCfg<NW, NT>::THREADS, 1) rrx_scan_kernel(cons
             if (tile + 1 == sp.num_tiles) store_comp_global<NW>(sp.shard_comp, inc);
         }
         __syncwarp();
+        RRX_T(4)
         const uint32_t c = phase_b<NW>(sp, pv, fw, ts, lane, any_open);
         // exclusive offsets of the rows' matches inside the tile
         uint32_t inc_c = c;
@@ -294,7 +288,15 @@ __global__ void __launch_bounds__(KCfg<NW, NT>::THREADS, 1) rrx_scan_kernel(cons
         }
         const uint32_t total = __shfl_sync(FULL, inc_c, 31);
         const uint32_t offset = inc_c - c;
-        const unsigned long long base = lookback_count(sp, tile, total, lane);
+        RRX_T(5)
+        unsigned long long base = 0;
+        if (lane == 0) {
+            if (total) base = atomicAdd(sp.total, (unsigned long long)total);
+            sp.tile_seg[tile] = base;
+            sp.tile_cnt[tile] = total;
+        }
+        base = __shfl_sync(FULL, base, 0);
+        RRX_T(6)
         if (total) {
             uint32_t hit[4];
 #pragma unroll
@@ -309,6 +311,7 @@ __global__ void __launch_bounds__(KCfg<NW, NT>::THREADS, 1) rrx_scan_kernel(cons
             }
         }
         __syncwarp();
+        RRX_T(7)
     }
 }
 

@@ -8,6 +8,9 @@
 namespace rrx {
 struct ScanParams;
 cudaError_t launch_scan(const ScanParams& sp, const ProgHeader& h, int sm_count, cudaStream_t st, int* grid_out);
+cudaError_t launch_order(const uint32_t* tile_cnt, const unsigned long long* tile_seg, uint32_t num_tiles,
+                         unsigned long long* chunk_scratch, const long long* staging, long long* out, uint64_t cap,
+                         cudaStream_t st);
 cudaError_t launch_corpus_iid(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, const uint8_t* alpha256, cudaStream_t st);
 cudaError_t launch_corpus_records(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, cudaStream_t st);
 }  // namespace rrx

@@ -290,6 +290,9 @@ struct ScanParams {
     const uint32_t* prog;       // program blob (global memory)
     uint32_t num_tiles;
     uint32_t static_closed;     // 1: every row is closed by construction (acyclic E', depth < ROW_BYTES)
+    uint32_t stagger_ns;        // warps of a CTA start (warp%8)*stagger_ns apart, so that they are not all in the same phase
+    uint32_t backoff_ns;
+    unsigned long long* phase_cycles;   // optional [8]: per-phase warp cycles (RRX_PHASE_TIMING builds)
     uint32_t* ticket;
     // Two-level decoupled look-back (tiles, blocks of 32 tiles), see rrx_scan.cu.
     // state composites: payload arrays of 1+3*NW words per entry, ready flags apart (zeroed per scan)
@@ -302,14 +305,14 @@ struct ScanParams {
     volatile uint32_t* f_a1;    // [blocks]
     volatile uint32_t* f_i1;    // [blocks]
     uint32_t* st_arrive;        // [blocks] tiles of the block that have published their aggregate
-    // match counts: 64-bit words, bit 63 = ready
-    volatile unsigned long long* ct_a0;   // [tiles]  matches of the tile
-    volatile unsigned long long* ct_a1;   // [blocks] matches of the block
-    volatile unsigned long long* ct_i1;   // [blocks] matches up to and including the block
-    uint32_t* ct_arrive;        // [blocks]
-    long long* out;             // (start,end) pairs
+    // Output placement: a tile reserves a segment of the staging list with one atomicAdd (tiles land
+    // in completion order, matches inside a tile in text order) and records it; the ordering pass
+    // (rrx_order.cu) then moves the segments into tile order.  Nothing waits for match counts.
+    unsigned long long* tile_seg;   // [tiles] first staging slot of the tile's matches
+    uint32_t* tile_cnt;             // [tiles] matches of the tile
+    long long* out;             // staging list of (start,end) pairs
     uint64_t out_cap;
-    unsigned long long* total;  // [0] match count, [1] pending count
+    unsigned long long* total;  // [0] matches so far (staging allocator), [1] pending count
     uint32_t* err;
     uint32_t* shard_comp;       // [1+3*NW] composite of the whole shard (relative to an unknown entry)
     PendingStart* pending;
@@ -537,7 +540,7 @@ RRX_DEV void rrx_fence() {
 }
 RRX_DEV void rrx_backoff() {
 #if defined(__CUDA_ARCH__) && !defined(RRX_HOST_EMU)
-    __nanosleep(32);
+    __nanosleep(100);
 #endif
 }
 

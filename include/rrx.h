@@ -91,12 +91,27 @@ typedef struct rrx_scan_result {
 } rrx_scan_result;
 
 int rrx_scanner_create(const rrx_program* p, uint64_t max_len, uint64_t match_capacity, rrx_scanner** out);
+/* flags: RRX_SCANNER_JIT / RRX_SCANNER_NO_JIT force / forbid the run-time specialised kernel (NVRTC);
+ * default: specialise when max_len >= 32 MiB and the automaton fits one 32-bit word.
+ * The environment variable RRX_JIT=0/1 overrides the default. */
+enum { RRX_SCANNER_DEFAULT = 0, RRX_SCANNER_JIT = 1, RRX_SCANNER_NO_JIT = 2 };
+int rrx_scanner_create_ex(const rrx_program* p, uint64_t max_len, uint64_t match_capacity, uint32_t flags, rrx_scanner** out);
+/* 1 if the scanner runs a run-time specialised kernel, 0 if a pre-compiled one. */
+int rrx_scanner_is_jit(const rrx_scanner* s);
+/* CUDA source of the specialised follow functions for this program (for inspection); returns the
+ * length needed (including the NUL), copies at most cap bytes. */
+uint64_t rrx_program_jit_source(const rrx_program* p, char* buf, uint64_t cap);
+/* Compile the specialised kernel to an sm_100a cubin with NVRTC (no GPU needed) and write it to `path`
+ * (NULL: discard).  Returns RRX_OK, or RRX_ERR_UNSUPPORTED / RRX_ERR_CUDA with rrx_last_error(). */
+int rrx_program_jit_compile(const rrx_program* p, const char* path);
 void rrx_scanner_free(rrx_scanner* s);
 /* Enqueue one scan on `stream` (asynchronous). */
 int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64_t base_offset,
                      const rrx_scan_opts* opts, void* stream);
 /* Wait for the last scan and fetch its counters. */
 int rrx_scanner_result(rrx_scanner* s, rrx_scan_result* out, void* stream);
+/* Copy the first n matches of the last scan to host memory (n*2 int64). */
+int rrx_scanner_copy_matches(rrx_scanner* s, int64_t* host_out, uint64_t n, void* stream);
 /* Composite transfer function of the last scanned shard: 1+3*words uint32 (kind, b, U, P); host copy. */
 int rrx_scanner_shard_summary(rrx_scanner* s, uint32_t* out, uint64_t cap_words, void* stream);
 

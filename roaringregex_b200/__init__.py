@@ -86,10 +86,15 @@ def lib() -> C.CDLL:
         "rrx_matches_device_data": (vp, [vp]),
         "rrx_matches_free": (None, [vp]),
         "rrx_scanner_create": (C.c_int, [vp, u64, u64, C.POINTER(vp)]),
+        "rrx_scanner_create_ex": (C.c_int, [vp, u64, u64, u32, C.POINTER(vp)]),
+        "rrx_scanner_is_jit": (C.c_int, [vp]),
+        "rrx_program_jit_source": (u64, [vp, vp, u64]),
+        "rrx_program_jit_compile": (C.c_int, [vp, C.c_char_p]),
         "rrx_scanner_free": (None, [vp]),
         "rrx_scanner_scan": (C.c_int, [vp, vp, u64, u64, C.POINTER(_Opts), vp]),
         "rrx_scanner_result": (C.c_int, [vp, C.POINTER(_Result), vp]),
         "rrx_scanner_shard_summary": (C.c_int, [vp, vp, u64, vp]),
+        "rrx_scanner_copy_matches": (C.c_int, [vp, vp, u64, vp]),
         "rrx_corpus_iid_device": (C.c_int, [vp, u64, u64, u64, vp, vp]),
         "rrx_corpus_records_device": (C.c_int, [vp, u64, u64, u64, vp]),
         "rrx_last_error": (C.c_char_p, []),
@@ -153,6 +158,16 @@ class RRegex:
         n = C.c_uint64(0)
         p = lib().rrx_program_blob(self._h, C.byref(n))
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(int(n.value),)).copy()
+
+    def jit_source(self) -> str:
+        n = int(lib().rrx_program_jit_source(self._h, None, 0))
+        buf = C.create_string_buffer(n)
+        lib().rrx_program_jit_source(self._h, buf, n)
+        return buf.value.decode("latin-1")
+
+    def jit_compile(self, path: str | None = None) -> None:
+        """NVRTC-compile the specialised kernel for sm_100a (works without a GPU)."""
+        _check(lib().rrx_program_jit_compile(self._h, path.encode() if path else None))
 
     def raw_row(self, state: int, byte: int) -> list[int]:
         w = (self.info["n_raw"] + 31) // 32
@@ -283,10 +298,12 @@ class AcceptanceIterator:
 class Scanner:
     """Reusable device-side scan context (rrx_scanner): no allocation inside a scan call."""
 
-    def __init__(self, regex: RRegex, max_len: int, capacity: int):
+    def __init__(self, regex: RRegex, max_len: int, capacity: int, jit=None):
+        """jit: None = default policy (specialise for long inputs), True / False = force / forbid."""
         self.regex = regex
         h = C.c_void_p()
-        _check(lib().rrx_scanner_create(regex._h, max_len, capacity, C.byref(h)))
+        flags = 0 if jit is None else (1 if jit else 2)
+        _check(lib().rrx_scanner_create_ex(regex._h, max_len, capacity, flags, C.byref(h)))
         self._h = h
         self.capacity = capacity
         self._entry_keep = None
@@ -295,6 +312,10 @@ class Scanner:
         h, self._h = getattr(self, "_h", None), None
         if h and _LIB is not None:
             _LIB.rrx_scanner_free(h)
+
+    @property
+    def is_jit(self) -> bool:
+        return bool(lib().rrx_scanner_is_jit(self._h))
 
     def scan(self, d_ptr: int, length: int, base_offset: int = 0, left_context: int = 0, entry=None, stream: int = 0):
         o = _Opts(left_context, None, MODE_LAZY_V1, 0)
@@ -308,6 +329,14 @@ class Scanner:
         _check(lib().rrx_scanner_result(self._h, C.byref(r), stream))
         return dict(n_matches=int(r.n_matches), capacity=int(r.capacity), n_pending=int(r.n_pending),
                     error_bits=int(r.error_bits), launches=int(r.launches), d_matches=int(r.d_matches or 0))
+
+    def matches(self, stream: int = 0) -> np.ndarray:
+        """Match list of the last scan as an (M,2) int64 host array."""
+        r = self.result(stream)
+        n = min(r["n_matches"], r["capacity"])
+        out = np.empty((n, 2), dtype=np.int64)
+        _check(lib().rrx_scanner_copy_matches(self._h, out.ctypes.data, n, stream))
+        return out
 
     def shard_summary(self, stream: int = 0) -> np.ndarray:
         w = self.regex.info["words"]

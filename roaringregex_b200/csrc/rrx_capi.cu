@@ -11,6 +11,7 @@
 
 #include "../../include/rrx.h"
 #include "rrx_compile.h"
+#include "rrx_jit.h"
 #include "rrx_scan.h"
 #include "rrx_tile.cuh"
 
@@ -64,6 +65,7 @@ struct rrx_scanner {
     uint32_t pending_cap = 4096;
     uint32_t launches = 0;
     bool owns_out = true;
+    JitKernel* jit = nullptr;        // run-time specialised kernel (owned by the process-wide cache)
     // pinned host mirror of [ticket, err, total0, total1]
     uint64_t* h_ctr = nullptr;
 };
@@ -161,6 +163,31 @@ void rrx_scanner_free(rrx_scanner* s) {
 }
 
 int rrx_scanner_create(const rrx_program* p, uint64_t max_len, uint64_t capacity, rrx_scanner** out) {
+    return rrx_scanner_create_ex(p, max_len, capacity, RRX_SCANNER_DEFAULT, out);
+}
+int rrx_scanner_is_jit(const rrx_scanner* s) { return s && s->jit ? 1 : 0; }
+uint64_t rrx_program_jit_source(const rrx_program* p, char* buf, uint64_t cap) {
+    const std::string src = jit_applicable(p->prog) ? jit_policy_source(p->prog) : std::string();
+    if (buf && cap) { const size_t n = src.size() + 1 < cap ? src.size() + 1 : cap; std::memcpy(buf, src.c_str(), n); buf[n - 1] = 0; }
+    return src.size() + 1;
+}
+
+int rrx_program_jit_compile(const rrx_program* p, const char* path) {
+    if (!p) return set_err(RRX_ERR_ARG, "null argument");
+    if (!jit_applicable(p->prog)) return set_err(RRX_ERR_UNSUPPORTED, "only one-word automata without row tables are specialised");
+    std::vector<char> cubin;
+    std::string err;
+    if (!jit_compile_cubin(p->prog, &cubin, &err)) return set_err(RRX_ERR_CUDA, err);
+    if (path) {
+        FILE* f = fopen(path, "wb");
+        if (!f) return set_err(RRX_ERR_ARG, "cannot open output file");
+        fwrite(cubin.data(), 1, cubin.size(), f);
+        fclose(f);
+    }
+    return RRX_OK;
+}
+
+int rrx_scanner_create_ex(const rrx_program* p, uint64_t max_len, uint64_t capacity, uint32_t flags, rrx_scanner** out) {
     if (!p || !out) return set_err(RRX_ERR_ARG, "null argument");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -190,6 +217,19 @@ int rrx_scanner_create(const rrx_program* p, uint64_t max_len, uint64_t capacity
     RRX_CUDA(cudaMalloc(&s->d_shard, (1 + 3 * (size_t)h.NW) * 4));
     RRX_CUDA(cudaMalloc(&s->d_pending, sizeof(PendingStart) * s->pending_cap));
     RRX_CUDA(cudaMallocHost(&s->h_ctr, 32));
+    {
+        // run-time specialisation: worth its ~1 s compile only for long inputs
+        bool want = (flags & RRX_SCANNER_JIT) || (!(flags & RRX_SCANNER_NO_JIT) && max_len >= (32ull << 20));
+        if (const char* e = getenv("RRX_JIT")) want = e[0] == '1' && !(flags & RRX_SCANNER_NO_JIT);
+        if (want && jit_applicable(p->prog)) {
+            std::string err;
+            s->jit = jit_get(p->prog, &err);
+            if (!s->jit) {
+                if (flags & RRX_SCANNER_JIT) return set_err(RRX_ERR_CUDA, "run-time specialisation failed: " + err);
+                if (getenv("RRX_JIT_VERBOSE")) fprintf(stderr, "rrx: run-time specialisation unavailable (%s); using the pre-compiled kernel\n", err.c_str());
+            }
+        }
+    }
     *out = s.release();
     return RRX_OK;
 }
@@ -265,7 +305,7 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
         return RRX_OK;
     }
     int grid = 0;
-    cudaError_t e = launch_scan(sp, h, s->sm_count, st, &grid);
+    cudaError_t e = s->jit ? jit_launch(s->jit, sp, s->sm_count, st, &grid) : launch_scan(sp, h, s->sm_count, st, &grid);
     if (e != cudaSuccess) return cuda_err(e, "rrx_scan_kernel launch");
     e = launch_order(s->d_tile_cnt, s->d_tile_seg, sp.num_tiles, s->d_chunk, s->d_stage, s->d_out, s->capacity, st);
     if (e != cudaSuccess) return cuda_err(e, "ordering pass launch");
@@ -285,6 +325,15 @@ int rrx_scanner_result(rrx_scanner* s, rrx_scan_result* out, void* stream) {
     out->capacity = s->capacity;
     out->launches = s->launches;
     out->d_matches = reinterpret_cast<const int64_t*>(s->d_out);
+    return RRX_OK;
+}
+
+int rrx_scanner_copy_matches(rrx_scanner* s, int64_t* host_out, uint64_t n, void* stream) {
+    if (!s || (!host_out && n)) return set_err(RRX_ERR_ARG, "null argument");
+    if (n > s->capacity) return set_err(RRX_ERR_ARG, "more matches requested than the scanner holds");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n) RRX_CUDA(cudaMemcpyAsync(host_out, s->d_out, n * 16, cudaMemcpyDeviceToHost, st));
+    RRX_CUDA(cudaStreamSynchronize(st));
     return RRX_OK;
 }
 

@@ -2,7 +2,9 @@
 // (rrx_compile.cc), the kernels (rrx_tile.cuh) and the runtime-compiled specialisations.
 // No STL here: this header is also fed to NVRTC.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <stdint.h>
+#endif
 
 namespace rrx {
 

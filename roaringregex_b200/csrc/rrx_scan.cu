@@ -1,332 +1,28 @@
-// rrx scan kernel (sm_100a) and its launcher.
-//
-// One persistent CTA per SM slot walks tiles in ticket order.  Per tile:
-//   load   128-bit coalesced loads -> shared memory, rows of 128 B, XOR-swizzled 16-byte chunks
-//   A      every thread scans its row from the empty set (register state word(s)), finds match ends
-//   S      row transfer functions composed; tile aggregate published; decoupled look-back over
-//          predecessor tiles yields the tile's exact entry set
-//   B      rows replay their prefix from the exact entry (dies within a few bytes unless the
-//          automaton has an absorbing loop)
-//   C      match counts -> second look-back (output base) -> lazy start scans -> (start,end) writes
-// The phase bodies live in rrx_tile.cuh (shared with the host-side test emulator).
+// Pre-compiled instantiations of the rrx scan kernel (sm_100a) and their launcher.
+// The kernel body is in rrx_kernel.cuh; the run-time specialised variant in rrx_jit.cc.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <cstdio>
 
+#include "rrx_kernel.cuh"
 #include "rrx_scan.h"
-#include "rrx_tile.cuh"
 
 namespace rrx {
 
 // warps per CTA by state width: registers per thread grow with NW
-template <int NW, int NT> struct KCfg {
-    static constexpr int WARPS = (NW == 1 && NT >= 0) ? 32 : NW <= 2 ? 16 : NW <= 8 ? 8 : 4;
-    static constexpr int THREADS = WARPS * 32;
-    static constexpr uint32_t BT_BYTES = (NW == 1 ? 256u * 128u : 256u * (uint32_t)NW * 4u);
-    static constexpr size_t REGION = (TileState<NW>::bytes() + 127) & ~(size_t)127;
-};
-
-// =====================================================================================================
-// Two-level decoupled look-back.
-//
-// Every warp owns one tile at a time; tiles are handed out in ticket order, so every tile with a
-// smaller index is finished or in flight on a resident warp.  With ~4700 tiles in flight and all of
-// them reaching the same phase at about the same time, a flat look-back would walk thousands of
-// aggregates one by one.  Here
-//   level 0: each tile publishes its aggregate; the LAST tile of a 32-tile block to arrive folds the
-//            32 aggregates into the block aggregate (level 1);
-//   a tile's exclusive prefix = fold(aggregates of the tiles before it in its block)   [1 round,
-//            32 lanes read 32 entries in parallel]  combined with  fold(previous blocks' aggregates
-//            back to the nearest published block-inclusive value)   [32 blocks = 1024 tiles per round];
-//   the warp holding the last tile of a block publishes the block-inclusive value.
-// Every wait is on a value that its producer publishes BEFORE the producer itself waits for anything,
-// so the scheme cannot deadlock (exception: K_WAIT aggregates, whose consumers wait for the producer's
-// inclusive value — the producer only ever waits on smaller tile indices).
-// =====================================================================================================
-constexpr unsigned FULL = 0xffffffffu;
-__device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-constexpr unsigned long long CT_READY = 1ull << 63;
-
-template <int NW> __device__ __forceinline__ void bcast_comp(Comp<NW>& c, int src) {
-    c.kind = __shfl_sync(FULL, c.kind, src);
-#pragma unroll
-    for (int w = 0; w < NW; w++) {
-        c.b[w] = __shfl_sync(FULL, c.b[w], src);
-        c.U[w] = __shfl_sync(FULL, c.U[w], src);
-        c.P[w] = __shfl_sync(FULL, c.P[w], src);
-    }
-}
-// Publishing / awaiting a composite.  NW == 1: the composite and its ready bit form ONE aligned
-// 16-byte word {kind|READY, b, U, P}, stored and loaded with single 128-bit accesses (not torn on
-// this hardware; the same assumption CUB's decoupled look-back makes for its 16-byte tile
-// descriptors), so no fence is needed.  NW > 1: payload, fence, then a separate flag word.
-constexpr uint32_t K_READY = 0x80000000u;
-template <int NW> __device__ __forceinline__ void publish_comp(uint32_t* pay, volatile uint32_t* flag, size_t idx, const Comp<NW>& c) {
-    if (NW == 1) {
-        const uint4 v = make_uint4(c.kind | K_READY, c.b[0], c.U[0], c.P[0]);
-        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(pay + idx * 4), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    } else {
-        store_comp_global<NW>(pay + idx * (1 + 3 * NW), c);
-        __threadfence();
-        flag[idx] = 1u;
-    }
-}
-template <int NW> __device__ __forceinline__ bool try_comp(const uint32_t* pay, volatile uint32_t* flag, size_t idx, Comp<NW>& c) {
-    if (NW == 1) {
-        uint4 v;
-        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(pay + idx * 4) : "memory");
-        if (!(v.x & K_READY)) return false;
-        c.kind = v.x & ~K_READY; c.b[0] = v.y; c.U[0] = v.z; c.P[0] = v.w;
-        return true;
-    } else {
-        if (flag[idx] == 0u) return false;
-        __threadfence();
-        load_comp_global<NW>(pay + idx * (1 + 3 * NW), c);
-        return true;
-    }
-}
-template <int NW> __device__ __forceinline__ void wait_comp(const uint32_t* pay, volatile uint32_t* flag, size_t idx, Comp<NW>& c) {
-    while (!try_comp<NW>(pay, flag, idx, c)) rrx_backoff();
-}
-
-// state composites (ordered): all lanes pass the same `agg`; `acc` = composite of everything before
-// the tile, relative to the shard entry (same value in all lanes).
-template <int NW>
-__device__ __forceinline__ void lookback_state(const ScanParams& sp, uint32_t tile, const Comp<NW>& agg, int lane, Comp<NW>& acc) {
-    const uint32_t b = tile >> 5, k = tile & 31;
-    const uint32_t rest = sp.num_tiles - (b << 5);
-    const uint32_t nblk = rest < 32u ? rest : 32u;
-    Comp<NW> mine, x, nxt;
-    uint32_t old = 0;
-    if (lane == 0) {
-        publish_comp<NW>(sp.st_a0, sp.f_a0, tile, agg);
-        if (NW > 1) __threadfence();
-        old = atomicAdd(sp.st_arrive + b, 1u);
-    }
-    old = __shfl_sync(FULL, old, 0);
-    if (old == nblk - 1) {                                  // fold the block aggregate, in tile order
-        comp_ident(mine);
-        if ((uint32_t)lane < nblk) wait_comp<NW>(sp.st_a0, sp.f_a0, (size_t)(b << 5) + lane, mine);
-        Comp<NW> fold;
-        comp_ident(fold);
-        bool has_wait = false;
-        for (uint32_t l = 0; l < nblk; l++) {
-            x = mine;
-            bcast_comp(x, (int)l);
-            if ((x.kind & K_TYPE) == K_WAIT) { has_wait = true; continue; }
-            comp_compose(fold, x, nxt);
-            fold = nxt;
-        }
-        if (has_wait) fold.kind = K_WAIT;
-        if (lane == 0) publish_comp<NW>(sp.st_a1, sp.f_a1, b, fold);
-    }
-    // (0) shortcut: if the tile right before this one is closed, nothing earlier matters
-    comp_ident(acc);
-    if (tile == 0) return;
-    wait_comp<NW>(sp.st_a0, sp.f_a0, (size_t)tile - 1, x);
-    if ((x.kind & K_TYPE) == K_CLOSED) { acc = x; return; }
-    // (a) the tiles before this one inside the block, nearest first
-    comp_ident(mine);
-    if ((uint32_t)lane < k) wait_comp<NW>(sp.st_a0, sp.f_a0, (size_t)(b << 5) + lane, mine);
-    comp_ident(acc);
-    bool done = false;
-    for (int l = (int)k - 1; l >= 0 && !done; l--) {
-        x = mine;
-        bcast_comp(x, l);
-        if ((x.kind & K_TYPE) == K_WAIT) {                   // opaque tile: take its inclusive state
-            wait_comp<NW>(sp.st_i0, sp.f_i0, (size_t)(b << 5) + l, x);
-            done = true;
-        }
-        comp_compose(x, acc, nxt);
-        acc = nxt;
-        if ((acc.kind & K_TYPE) == K_CLOSED) done = true;
-    }
-    // (b) previous blocks, 32 per round, nearest first
-    for (int64_t jb = (int64_t)b - 1; jb >= 0 && !done; jb -= 32) {
-        const int64_t my = jb - lane;
-        uint32_t st = 0;                                    // 1 aggregate, 2 inclusive
-        comp_ident(mine);
-        if (my >= 0) {
-            for (;;) {
-                if (try_comp<NW>(sp.st_i1, sp.f_i1, (size_t)my, mine)) { st = 2; break; }
-                if (try_comp<NW>(sp.st_a1, sp.f_a1, (size_t)my, mine)) {
-                    st = 1;
-                    if ((mine.kind & K_TYPE) == K_WAIT) { wait_comp<NW>(sp.st_i1, sp.f_i1, (size_t)my, mine); st = 2; }
-                    break;
-                }
-                rrx_backoff();
-            }
-        }
-        for (int l = 0; l < 32 && !done; l++) {
-            const uint32_t sl = __shfl_sync(FULL, st, l);
-            if (sl == 0) { done = true; break; }            // ran past the first block
-            x = mine;
-            bcast_comp(x, l);
-            comp_compose(x, acc, nxt);
-            acc = nxt;
-            if (sl == 2 || (acc.kind & K_TYPE) == K_CLOSED) done = true;
-        }
-    }
-}
-
-#ifdef RRX_PHASE_TIMING
-#define RRX_T(i) { const long long now_ = clock64(); if (lane == 0 && sp.phase_cycles) atomicAdd(sp.phase_cycles + (i), (unsigned long long)(now_ - tprev_)); tprev_ = now_; }
-#else
-#define RRX_T(i)
-#endif
+template <int NW, int NT> struct Warps { static constexpr int N = (NW == 1 && NT >= 0) ? 32 : NW <= 2 ? 16 : NW <= 8 ? 8 : 4; };
 
 template <int NW, int NT, int NB>
-__global__ void __launch_bounds__(KCfg<NW, NT>::THREADS, 1) rrx_scan_kernel(const __grid_constant__ ScanParams sp) {
-    using K = KCfg<NW, NT>;
-    using TS = TileState<NW>;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    // shared memory: [byte table | per-warp tile regions | small program part]
-    uint32_t* Btab = reinterpret_cast<uint32_t*>(smem_raw);
-    uint8_t* regions = smem_raw + K::BT_BYTES;
-    uint32_t* progsm = reinterpret_cast<uint32_t*>(regions + (size_t)K::WARPS * K::REGION);
-
-    const ProgHeader* gh = reinterpret_cast<const ProgHeader*>(sp.prog);
-    const uint32_t n_small = gh->off_B, off_B = gh->off_B;
-    for (uint32_t i = tid; i < n_small; i += K::THREADS) progsm[i] = sp.prog[i];
-    if (NW == 1) {
-        // one private copy of the table per lane: entry (c, lane) lives in bank `lane`
-        for (uint32_t i = tid; i < K::BT_BYTES / 4; i += K::THREADS) Btab[i] = sp.prog[off_B + (i >> 5)];
-    } else {
-        for (uint32_t i = tid; i < K::BT_BYTES / 4; i += K::THREADS) Btab[i] = sp.prog[off_B + i];
-    }
-    __syncthreads();                      // the only block-level barrier of the kernel
-    ProgView pv;
-    pv.sm = progsm;
-    pv.glob = sp.prog;
-    pv.Btab = reinterpret_cast<const uint8_t*>(Btab);
-    pv.lane_off = (uint32_t)lane * 4u;
-    Prog<NW, NT, NB> fw;
-    fw.init(pv);
-    TS ts;
-    ts.carve(regions + (size_t)warp * K::REGION);
-    const int64_t len = (int64_t)sp.len;
-#ifdef RRX_PHASE_TIMING
-    long long tprev_ = clock64();
-#endif
-
-    // De-phase the warps of the SM: if all of them load, scan, look back and emit at the same
-    // moments, nobody computes while everybody waits for memory.  Tickets are taken in arrival
-    // order afterwards, so the offsets persist.
-    if (sp.stagger_ns) {
-        const unsigned long long t0 = globaltimer_ns();
-        const unsigned long long wait = (unsigned long long)(warp & 7) * sp.stagger_ns;
-        while (globaltimer_ns() - t0 < wait) __nanosleep(200);
-    }
-
-    // While a warp works on tile i it asks L2 to fetch tile i + (warps in flight) — the tile some
-    // warp (whichever finishes first) will pick up about one round from now — one 128-byte line per
-    // lane, so the staging loads of the next round hit L2 instead of queueing on HBM.
-    const uint32_t warps_in_flight = gridDim.x * (uint32_t)K::WARPS;
-    for (;;) {
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(sp.ticket, 1u);
-        tile = __shfl_sync(FULL, tile, 0);
-        if (tile >= sp.num_tiles) break;
-        {
-            const int64_t g = (((int64_t)tile + warps_in_flight) * TILE_ROWS + lane) << ROW_SHIFT;
-            if (g < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp.text + g));
-        }
-        ts.row0 = (uint64_t)tile * TILE_ROWS;
-        RRX_T(0)
-        // ---- stage the tile: 8 x 128-bit loads per lane, fully coalesced, XOR-swizzled store ----
-        {
-            const int64_t g0 = ts.lo();
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int q = k * 32 + lane;              // 16-byte chunk index inside the tile
-                const int s = q >> 3, j = q & 7;
-                const int64_t g = g0 + (int64_t)q * 16;
-                uint8_t* dst = ts.text + (s << ROW_SHIFT) + ((j ^ (s & 7)) << 4);
-                if (g + 16 <= len) {
-                    *reinterpret_cast<uint4*>(dst) = __ldcs(reinterpret_cast<const uint4*>(sp.text + g));
-                } else if (g < len) {
-                    for (int b = 0; b < 16 && g + b < len; b++) dst[b] = sp.text[g + b];
-                }
-            }
-        }
-        __syncwarp();
-        RRX_T(1)
-        phase_a<NW>(sp, pv, fw, ts, lane);
-        const uint32_t my_kind = ts.sum_kind[lane];
-        const bool any_open = __any_sync(FULL, my_kind == K_RANK1 || my_kind == K_HARD) != 0;
-        __syncwarp();
-        SLocal<NW> L;
-        Comp<NW> agg, acc, inc;
-        if (lane == 0) { phase_s1<NW>(sp, pv, fw, ts, any_open, L); agg = L.run; } else { comp_ident(agg); }
-        bcast_comp(agg, 0);
-        RRX_T(2)
-        lookback_state<NW>(sp, tile, agg, lane, acc);
-        RRX_T(3)
-        if (lane == 0) {
-            phase_s2<NW>(sp, pv, fw, ts, L, acc, inc);
-            publish_comp<NW>(sp.st_i0, sp.f_i0, tile, inc);
-            const uint32_t rest = sp.num_tiles - (tile & ~31u);
-            if ((tile & 31u) == (rest < 32u ? rest : 32u) - 1u) publish_comp<NW>(sp.st_i1, sp.f_i1, tile >> 5, inc);
-            if (tile + 1 == sp.num_tiles) store_comp_global<NW>(sp.shard_comp, inc);
-        }
-        __syncwarp();
-        RRX_T(4)
-        const uint32_t c = phase_b<NW>(sp, pv, fw, ts, lane, any_open);
-        // exclusive offsets of the rows' matches inside the tile
-        uint32_t inc_c = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(FULL, inc_c, d);
-            if (lane >= d) inc_c += v;
-        }
-        const uint32_t total = __shfl_sync(FULL, inc_c, 31);
-        const uint32_t offset = inc_c - c;
-        RRX_T(5)
-        unsigned long long base = 0;
-        if (lane == 0) {
-            if (total) base = atomicAdd(sp.total, (unsigned long long)total);
-            sp.tile_seg[tile] = base;
-            sp.tile_cnt[tile] = total;
-        }
-        base = __shfl_sync(FULL, base, 0);
-        RRX_T(6)
-        if (total) {
-            uint32_t hit[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) hit[q] = ts.hits[q * TILE_ROWS + lane];
-            __syncwarp();                 // every lane is done with the row summaries: reuse as hit list
-            if (total <= (uint32_t)TS::LIST_CAP) {
-                phase_c1_list<NW>(ts, lane, offset, hit);
-                __syncwarp();
-                phase_c2_balanced<NW>(sp, pv, fw, ts, lane, total, base);
-            } else {
-                phase_c2_rows<NW>(sp, pv, fw, ts, lane, offset, hit, base);
-            }
-        }
-        __syncwarp();
-        RRX_T(7)
-    }
-}
-
-template <int NW, int NT> static size_t smem_bytes_for() {
-    using K = KCfg<NW, NT>;
-    // small program part: header + 3 sets + 2 decompositions
-    const size_t small = sizeof(ProgHeader) + 4u * (3 * NW + 2 * (RRX_MAX_TERMS * (1 + NW) + RRX_MAX_BICL * 2 * NW + NW));
-    return K::BT_BYTES + (size_t)K::WARPS * K::REGION + small + 64;
+__global__ void __launch_bounds__(Warps<NW, NT>::N * 32, 1) rrx_scan_kernel(const __grid_constant__ ScanParams sp) {
+    rrx_scan_body<NW, Prog<NW, NT, NB>, Warps<NW, NT>::N>(sp);
 }
 
 template <int NW, int NT, int NB>
 static cudaError_t launch_one(const ScanParams& sp, int sm_count, cudaStream_t st, int* grid_out) {
-    using K = KCfg<NW, NT>;
+    using K = KCfg<NW, Warps<NW, NT>::N>;
     auto kern = rrx_scan_kernel<NW, NT, NB>;
-    const size_t smem = smem_bytes_for<NW, NT>();
+    const size_t smem = K::SMEM;
     static bool configured = false;     // per instantiation
     static int occ = 1;
     if (!configured) {

@@ -39,6 +39,10 @@ constexpr int ROW_BYTES = 128;
 constexpr int ROW_SHIFT = 7;
 constexpr int TILE_ROWS = 32;                         // one row per lane
 constexpr int TILE_BYTES = TILE_ROWS * ROW_BYTES;     // 4 KiB
+// Rows are staged in shared memory 132 bytes apart: lane t reading byte p of ITS row touches bank
+// (33t + p/4) mod 32 = (t + p/4) mod 32, so the 32 lanes of a warp stepping through their rows in
+// lock-step never collide, for byte, word or any other same-offset access.
+constexpr int ROW_PITCH = 132;
 
 // error bits reported by the kernel
 enum : uint32_t { ERR_PENDING_OVERFLOW = 2u };
@@ -100,27 +104,46 @@ template <int NW> RRX_DEV int popc_w(const uint32_t* a) {
 struct ProgView {
     const uint32_t* sm;        // shared copy of blob[0 .. off_B)
     const uint32_t* glob;      // the blob in global memory
-    const uint8_t* Btab;       // shared byte table
-    uint32_t lane_off;         // NW == 1: lane*4
+    const uint8_t* Blane;      // shared byte table; NW == 1: already offset by lane*4
     RRX_DEV const ProgHeader& h() const { return *reinterpret_cast<const ProgHeader*>(sm); }
 };
 
+// Shared-memory accesses of the scan loop, pinned to the instructions we want: a byte load
+// (LSU pipe) instead of word load + PRMT (ALU pipe), and one IMAD (FMA pipe) for the table address.
+// The ALU pipe is the bottleneck of the scan loop, the other two have room.
+#if defined(__CUDA_ARCH__) && !defined(RRX_HOST_EMU)
+template <int K> RRX_DEV uint32_t lds_u8(const uint8_t* p) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)), "n"(K));
+    return v;
+}
+RRX_DEV uint32_t lds_tab1(const uint8_t* blane, uint32_t c) {
+    uint32_t a, v;
+    asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(a) : "r"(c), "r"((uint32_t)__cvta_generic_to_shared(blane)));
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+// (a | b) & c in one LOP3
+RRX_DEV uint32_t or_and(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xA8;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+#else
+template <int K> RRX_DEV uint32_t lds_u8(const uint8_t* p) { return p[K]; }
+RRX_DEV uint32_t lds_tab1(const uint8_t* blane, uint32_t c) { return *reinterpret_cast<const uint32_t*>(blane + c * 128u); }
+RRX_DEV uint32_t or_and(uint32_t a, uint32_t b, uint32_t c) { return (a | b) & c; }
+#endif
+
 template <int NW> RRX_DEV void load_B(const ProgView& pv, uint32_t c, uint32_t* out) {
     if (NW == 1) {
-        out[0] = *reinterpret_cast<const uint32_t*>(pv.Btab + ((c << 7) | pv.lane_off));
+        out[0] = lds_tab1(pv.Blane, c);
     } else {
-        const uint32_t* e = reinterpret_cast<const uint32_t*>(pv.Btab) + c * NW;
+        const uint32_t* e = reinterpret_cast<const uint32_t*>(pv.Blane) + c * NW;
 #pragma unroll
         for (int w = 0; w < NW; w++) out[w] = e[w];
     }
 }
-// NW == 1 only: table entry for byte I (0..3) of the little-endian text word `w`, with the byte
-// moved straight to its place in the table offset (shift + and/or, no multiply).
-template <int I> RRX_DEV uint32_t load_B1(const ProgView& pv, uint32_t w) {
-    const uint32_t sh = I == 0 ? (w << 7) : (w >> (I == 0 ? 0 : 8 * I - 7));
-    return *reinterpret_cast<const uint32_t*>(pv.Btab + ((sh & 0x7F80u) | pv.lane_off));
-}
-
 // f = follow'(S) through a decomposition (shift terms, bicliques, rows) read from shared memory.
 template <int NW>
 RRX_DEV void follow_terms(const uint32_t* terms, uint32_t n_terms, const uint32_t* bicl, uint32_t n_bicl,
@@ -323,7 +346,7 @@ struct ScanParams {
 // ---- shared-memory state of one tile (= one warp) ----------------------------------------------------
 template <int NW> struct TileState {
     static constexpr int ROWS = TILE_ROWS;
-    uint8_t* text;        // 32 rows of 128 B; 16-byte chunk j of row s sits at chunk j^(s&7)
+    uint8_t* text;        // 32 rows of 128 B, ROW_PITCH bytes apart
     uint32_t* sum_b;      // [NW][32]   exit of the row scanned from the empty set
     uint32_t* sum_U;      // [NW][32]   (open rows) survivors at the row end / prefix composite U
     uint32_t* sum_P;      // [NW][32]   (open rows) entry states that feed the survivor
@@ -337,11 +360,11 @@ template <int NW> struct TileState {
     static constexpr int MISC_WORDS = 8 + NW;
     static constexpr int LIST_CAP = 3 * NW * ROWS * 2;
     static constexpr size_t bytes() {
-        return (size_t)ROWS * ROW_BYTES + sizeof(uint32_t) * ((size_t)3 * NW * ROWS + 6 * ROWS + MISC_WORDS);
+        return (size_t)ROWS * ROW_PITCH + sizeof(uint32_t) * ((size_t)3 * NW * ROWS + 6 * ROWS + MISC_WORDS);
     }
     RRX_DEV void carve(uint8_t* base) {
         text = base;
-        uint32_t* p = reinterpret_cast<uint32_t*>(base + (size_t)ROWS * ROW_BYTES);
+        uint32_t* p = reinterpret_cast<uint32_t*>(base + (size_t)ROWS * ROW_PITCH);
         sum_b = p; p += NW * ROWS;
         sum_U = p; p += NW * ROWS;
         sum_P = p; p += NW * ROWS;
@@ -353,9 +376,10 @@ template <int NW> struct TileState {
     }
     RRX_DEV int64_t lo() const { return (int64_t)(row0 << ROW_SHIFT); }
     // byte at tile-relative offset rel (0 .. TILE_BYTES)
-    RRX_DEV uint32_t rel_byte(uint32_t rel) const {
-        const uint32_t s = rel >> ROW_SHIFT, col = rel & (ROW_BYTES - 1);
-        return text[(s << ROW_SHIFT) + ((((col >> 4) ^ (s & 7)) << 4) | (col & 15))];
+    RRX_DEV uint32_t rel_byte(uint32_t rel) const { return text[rel + 4u * (rel >> ROW_SHIFT)]; }
+    // where the q-th 16-byte chunk of the tile goes (4-byte aligned)
+    RRX_DEV uint32_t* chunk_ptr(int q) const {
+        return reinterpret_cast<uint32_t*>(text + (q >> 3) * ROW_PITCH + ((q & 7) << 4));
     }
     RRX_DEV uint32_t row_byte(int t, int p) const { return rel_byte(((uint32_t)t << ROW_SHIFT) + (uint32_t)p); }
 };
@@ -429,54 +453,50 @@ RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
     for (int w = 0; w < NW; w++) S[w] = 0;
     uint32_t hit[4] = {0, 0, 0, 0};
     if (nb == ROW_BYTES) {
-        const uint32_t s = (uint32_t)t;
-        const uint4* rowv = reinterpret_cast<const uint4*>(ts.text + ((size_t)s << ROW_SHIFT));
+        const uint8_t* rp = ts.text + t * ROW_PITCH;
 #pragma unroll 1
         for (int g = 0; g < 8; g++) {
-            const uint4 v = rowv[g ^ (s & 7)];
-            const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+            const uint8_t* gp = rp + g * 16;
             uint32_t Sq[4][NW], acc[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-#pragma unroll
-                for (int w = 0; w < NW; w++) Sq[q][w] = S[w];
-                uint32_t a = 0;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (NW == 1) {
-                        Bc[0] = i == 0 ? load_B1<0>(pv, wd[q]) : i == 1 ? load_B1<1>(pv, wd[q])
-                              : i == 2 ? load_B1<2>(pv, wd[q]) : load_B1<3>(pv, wd[q]);
-                    } else {
-                        load_B<NW>(pv, (wd[q] >> (8 * i)) & 0xffu, Bc);
-                    }
-                    fw.follow(pv, S, f);
-#pragma unroll
-                    for (int w = 0; w < NW; w++) {
-                        S[w] = (f[w] | fw.first(pv, w)) & Bc[w];
-                        a |= S[w] & fw.accept(pv, w);
-                    }
-                }
-                acc[q] = a;
+#define RRX_STEP(K_)                                                              \
+            {                                                                          \
+                load_B<NW>(pv, lds_u8<K_>(gp), Bc);                                    \
+                fw.follow(pv, S, f);                                                   \
+                _Pragma("unroll") for (int w = 0; w < NW; w++) {                       \
+                    S[w] = or_and(f[w], fw.first(pv, w), Bc[w]);                       \
+                    a |= S[w] & fw.accept(pv, w);                                      \
+                }                                                                      \
             }
+#define RRX_QUAD(Q_)                                                              \
+            {                                                                          \
+                _Pragma("unroll") for (int w = 0; w < NW; w++) Sq[Q_][w] = S[w];       \
+                uint32_t a = 0;                                                        \
+                RRX_STEP(Q_ * 4 + 0) RRX_STEP(Q_ * 4 + 1) RRX_STEP(Q_ * 4 + 2) RRX_STEP(Q_ * 4 + 3) \
+                acc[Q_] = a;                                                           \
+            }
+            RRX_QUAD(0) RRX_QUAD(1) RRX_QUAD(2) RRX_QUAD(3)
+#undef RRX_QUAD
+#undef RRX_STEP
             if (acc[0] | acc[1] | acc[2] | acc[3]) {
                 // rare: replay the 4-byte words that contain a match end to find the exact bytes
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    if (!acc[q]) continue;
-                    uint32_t T[NW];
+                    if (acc[q]) {
+                        uint32_t T[NW];
 #pragma unroll
-                    for (int w = 0; w < NW; w++) T[w] = Sq[q][w];
+                        for (int w = 0; w < NW; w++) T[w] = Sq[q][w];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        load_B<NW>(pv, (wd[q] >> (8 * i)) & 0xffu, Bc);
-                        fw.follow(pv, T, f);
-                        uint32_t a2 = 0;
+                        for (int i = 0; i < 4; i++) {
+                            load_B<NW>(pv, gp[q * 4 + i], Bc);
+                            fw.follow(pv, T, f);
+                            uint32_t a2 = 0;
 #pragma unroll
-                        for (int w = 0; w < NW; w++) {
-                            T[w] = (f[w] | fw.first(pv, w)) & Bc[w];
-                            a2 |= T[w] & fw.accept(pv, w);
+                            for (int w = 0; w < NW; w++) {
+                                T[w] = (f[w] | fw.first(pv, w)) & Bc[w];
+                                a2 |= T[w] & fw.accept(pv, w);
+                            }
+                            if (a2) hit[g >> 1] |= 1u << ((g & 1) * 16 + q * 4 + i);
                         }
-                        if (a2) hit[g >> 1] |= 1u << ((g & 1) * 16 + q * 4 + i);
                     }
                 }
             }

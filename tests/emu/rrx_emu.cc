@@ -62,8 +62,7 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
         ProgView pv;
         pv.sm = prog.blob.data();
         pv.glob = prog.blob.data();
-        pv.Btab = reinterpret_cast<const uint8_t*>(btab.data());
-        pv.lane_off = (uint32_t)lane * 4u;
+        pv.Blane = reinterpret_cast<const uint8_t*>(btab.data()) + (NW == 1 ? lane * 4 : 0);
         return pv;
     };
 
@@ -74,9 +73,8 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
         std::memset(smem.data(), 0xAA, smem.size());
         const int64_t g0 = ts.lo();
         for (int q = 0; q < ROWS * 8; q++) {
-            const int s = q >> 3, j = q & 7;
             const int64_t g = g0 + (int64_t)q * 16;
-            uint8_t* dst = ts.text + s * ROW_BYTES + ((j ^ (s & 7)) << 4);
+            uint8_t* dst = reinterpret_cast<uint8_t*>(ts.chunk_ptr(q));
             for (int k = 0; k < 16 && g + k < (int64_t)len; k++) dst[k] = text[g + k];
         }
         bool any_open = false;

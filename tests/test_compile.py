@@ -124,3 +124,18 @@ def test_scan_without_gpu_fails_loudly(rrx):
     assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
     with pytest.raises(rrx.RrxError):
         rrx.Scanner(r, 1 << 20, 1024)
+
+
+def test_specialised_kernel_compiles_without_gpu(rrx, tmp_path):
+    """NVRTC turns the generated policy + the embedded kernel headers into an sm_100a cubin."""
+    r = rrx.RRegex("[a-z]+@[a-z]+\\.(com|org|net)")
+    src = r.jit_source()
+    assert "struct ProgJit" in src and "rrx_mad" in src
+    out = tmp_path / "k.cubin"
+    try:
+        r.jit_compile(str(out))
+    except rrx.RrxError as e:
+        if "NVRTC could not be loaded" in str(e):
+            pytest.skip("no NVRTC on this machine")
+        raise
+    assert out.stat().st_size > 10000

@@ -158,3 +158,46 @@ def test_config2_full_size_properties(rrx, oracle_api, torch_cuda):
     host = d.cpu().numpy()
     for s_, e_ in got[idx]:
         assert rx.fullmatch(host[s_:e_].tobytes())
+
+
+@pytest.mark.parametrize("cfg_id,n", [(1, 1 << 20), (2, 8 << 20), (5, 8 << 20)])
+def test_runtime_specialised_kernel(rrx, oracle_api, torch_cuda, cfg_id, n):
+    """The NVRTC-specialised kernel (regex compiled to straight-line code) against the oracle and
+    against the pre-compiled generic kernel."""
+    torch = torch_cuda
+    cfg = CONFIGS[cfg_id]
+    text = cpu_corpus(cfg, 0, n)
+    d = torch.from_numpy(text).cuda()
+    want = oracle_api.Oracle(cfg.pattern).lazy_matches(text)
+    r = rrx.RRegex(cfg.pattern)
+    for jit in (True, False):
+        sc = rrx.Scanner(r, n, len(want) + 16, jit=jit)
+        assert sc.is_jit == jit
+        sc.scan(d.data_ptr(), n)
+        res = sc.result()
+        assert res["error_bits"] == 0 and res["n_matches"] == len(want)
+        assert np.array_equal(sc.matches(), want), (cfg_id, jit)
+
+
+def test_runtime_specialised_random_patterns(rrx, oracle_api, torch_cuda):
+    from test_emulator import _random_regex
+    torch = torch_cuda
+    rnd = random.Random(4242)
+    done = 0
+    while done < 12:
+        pat = _random_regex(rnd)
+        try:
+            o = oracle_api.Oracle(pat)
+            r = rrx.RRegex(pat)
+        except Exception:
+            continue
+        if r.info["words"] != 1 or r.info["uses_rows"]:
+            continue
+        done += 1
+        text = np.frombuffer(bytes(rnd.choices(b"abc\n", k=200000)), dtype=np.uint8)
+        d = torch.from_numpy(text.copy()).cuda()
+        want = o.lazy_matches(text)
+        sc = rrx.Scanner(r, len(text), len(want) + 16, jit=True)
+        sc.scan(d.data_ptr(), len(text))
+        assert sc.result()["n_matches"] == len(want), pat
+        assert np.array_equal(sc.matches(), want), pat

@@ -262,9 +262,12 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
                 dst[0] = v[k].x; dst[1] = v[k].y; dst[2] = v[k].z; dst[3] = v[k].w;
             }
         }
+        if (lane == 0) ts.misc[TS::M_RQCNT] = 0;
         __syncwarp();
         RRX_T(1)
         phase_a<NW>(sp, pv, fw, ts, lane);
+        __syncwarp();
+        phase_a2<NW>(pv, fw, ts, lane);
         const uint32_t my_kind = ts.sum_kind[lane];
         const bool any_open = __any_sync(FULL, my_kind == K_RANK1 || my_kind == K_HARD) != 0;
         __syncwarp();

@@ -31,6 +31,7 @@
 struct uint4 { uint32_t x, y, z, w; };
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { uint32_t o = *p; *p |= v; return o; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
 #endif
 
 namespace rrx {
@@ -354,13 +355,15 @@ template <int NW> struct TileState {
     uint32_t* hits;       // [4][32]    one bit per byte of the row: a match ends after that byte
     uint32_t* cnt;        // [32]       matches per row -> exclusive offsets
     uint32_t* misc;       // see M_* below
+    uint32_t* rq;         // replay queue: RQ_CAP items of {row<<5 | quad, state[NW]}
     uint16_t* list;       // hit list for the balanced start scans; aliases sum_b/sum_U/sum_P
     uint64_t row0;        // first row of the tile
-    static constexpr int M_ENTRY = 8;
+    static constexpr int M_RQCNT = 0, M_ENTRY = 8;
     static constexpr int MISC_WORDS = 8 + NW;
+    static constexpr int RQ_CAP = NW <= 2 ? 64 : 16;
     static constexpr int LIST_CAP = 3 * NW * ROWS * 2;
     static constexpr size_t bytes() {
-        return (size_t)ROWS * ROW_PITCH + sizeof(uint32_t) * ((size_t)3 * NW * ROWS + 6 * ROWS + MISC_WORDS);
+        return (size_t)ROWS * ROW_PITCH + sizeof(uint32_t) * ((size_t)3 * NW * ROWS + 6 * ROWS + MISC_WORDS + RQ_CAP * (1 + NW));
     }
     RRX_DEV void carve(uint8_t* base) {
         text = base;
@@ -371,7 +374,8 @@ template <int NW> struct TileState {
         sum_kind = p; p += ROWS;
         hits = p; p += 4 * ROWS;
         cnt = p; p += ROWS;
-        misc = p;
+        misc = p; p += MISC_WORDS;
+        rq = p;
         list = reinterpret_cast<uint16_t*>(sum_b);
     }
     RRX_DEV int64_t lo() const { return (int64_t)(row0 << ROW_SHIFT); }
@@ -396,6 +400,7 @@ RRX_DEV int row_nbytes(const ScanParams& sp, uint64_t row0, int t) {
 template <int NW, class F>
 RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t) {
     constexpr int ROWS = TILE_ROWS;
+    using TS = TileState<NW>;
     const int nb = row_nbytes(sp, ts.row0, t);
     uint32_t kind = nb ? K_CLOSED : K_IDENT;
     uint32_t Bc[NW], f[NW];
@@ -478,24 +483,40 @@ RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
 #undef RRX_QUAD
 #undef RRX_STEP
             if (acc[0] | acc[1] | acc[2] | acc[3]) {
-                // rare: replay the 4-byte words that contain a match end to find the exact bytes
+                // A match ends somewhere in these 16 bytes.  Finding the exact byte means replaying
+                // a 4-byte word from its saved start state; doing that here would make the whole
+                // warp wait for the one or two lanes concerned (and that happens in most groups as
+                // soon as matches are a few hundred bytes apart).  Queue the word instead: after the
+                // row loop the warp replays all queued words of the tile together, one per lane.
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     if (acc[q]) {
-                        uint32_t T[NW];
+                        const uint32_t slot = atomicAdd(ts.misc + TS::M_RQCNT, 1u);
+                        if (slot < (uint32_t)TS::RQ_CAP) {
+                            uint32_t* it = ts.rq + slot * (1 + NW);
+                            it[0] = ((uint32_t)t << 5) | (uint32_t)(g * 4 + q);
 #pragma unroll
-                        for (int w = 0; w < NW; w++) T[w] = Sq[q][w];
+                            for (int w = 0; w < NW; w++) it[1 + w] = Sq[q][w];
+                        } else {            // queue full: replay on the spot
+                            uint32_t T[NW];
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            load_B<NW>(pv, gp[q * 4 + i], Bc);
-                            fw.follow(pv, T, f);
-                            uint32_t a2 = 0;
+                            for (int w = 0; w < NW; w++) T[w] = Sq[q][w];
+#pragma unroll 1
+                            for (int i = 0; i < 4; i++) {
+                                load_B<NW>(pv, gp[q * 4 + i], Bc);
+                                fw.follow(pv, T, f);
+                                uint32_t a2 = 0;
 #pragma unroll
-                            for (int w = 0; w < NW; w++) {
-                                T[w] = (f[w] | fw.first(pv, w)) & Bc[w];
-                                a2 |= T[w] & fw.accept(pv, w);
+                                for (int w = 0; w < NW; w++) {
+                                    T[w] = (f[w] | fw.first(pv, w)) & Bc[w];
+                                    a2 |= T[w] & fw.accept(pv, w);
+                                }
+                                if (a2) {
+                                    const int p = g * 16 + q * 4 + i;
+                                    if (p < 32) hit[0] |= 1u << p; else if (p < 64) hit[1] |= 1u << (p - 32);
+                                    else if (p < 96) hit[2] |= 1u << (p - 64); else hit[3] |= 1u << (p - 96);
+                                }
                             }
-                            if (a2) hit[g >> 1] |= 1u << ((g & 1) * 16 + q * 4 + i);
                         }
                     }
                 }
@@ -519,6 +540,37 @@ RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
     ts.sum_kind[t] = kind;
 #pragma unroll
     for (int q = 0; q < 4; q++) ts.hits[q * ROWS + t] = hit[q];
+}
+
+// ===== phase A2: the warp replays the queued 4-byte words, one per lane ==============================
+// (after all lanes have finished phase A and stored their hit words)
+template <int NW, class F>
+RRX_DEV void phase_a2(const ProgView& pv, const F& fw, TileState<NW>& ts, int lane) {
+    constexpr int ROWS = TILE_ROWS;
+    using TS = TileState<NW>;
+    uint32_t n = ts.misc[TS::M_RQCNT];
+    if (n > (uint32_t)TS::RQ_CAP) n = TS::RQ_CAP;
+    for (uint32_t i = (uint32_t)lane; i < n; i += ROWS) {
+        const uint32_t* it = ts.rq + i * (1 + NW);
+        const uint32_t row = it[0] >> 5, quad = it[0] & 31u;
+        uint32_t T[NW], Bc[NW], f[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) T[w] = it[1 + w];
+        uint32_t bits = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            load_B<NW>(pv, ts.row_byte((int)row, (int)(quad * 4 + k)), Bc);
+            fw.follow(pv, T, f);
+            uint32_t a2 = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+                T[w] = (f[w] | fw.first(pv, w)) & Bc[w];
+                a2 |= T[w] & fw.accept(pv, w);
+            }
+            if (a2) bits |= 1u << k;
+        }
+        atomicOr(ts.hits + (quad >> 3) * ROWS + row, bits << ((quad & 7u) * 4u));
+    }
 }
 
 template <int NW> RRX_DEV void load_row_comp(const TileState<NW>& ts, int t, Comp<NW>& c) {
@@ -735,19 +787,32 @@ RRX_DEV void resolve_and_write(const ScanParams& sp, const ProgView& pv, const F
 #pragma unroll
     for (int w = 0; w < NW; w++) R[w] = fw.accept(pv, w);
     const int64_t tile_lo = ts.lo(), left_edge = -(int64_t)sp.left_ctx;
-    int64_t j = e - 1;
-    bool pend = false, found = false;
-    for (;;) {
-        const uint32_t c = j >= tile_lo ? ts.rel_byte((uint32_t)(j - tile_lo)) : (uint32_t)sp.text[j];
-        load_B<NW>(pv, c, Bc);
+    bool pend = false, found = false, dead = false;
+    // fast path: while the walk stays inside the tile (32-bit tile-relative offsets, shared memory)
+    int rel = (int)(e - 1 - tile_lo);
+    for (; rel >= 0; rel--) {
+        load_B<NW>(pv, ts.rel_byte((uint32_t)rel), Bc);
         uint32_t m = 0;
 #pragma unroll
         for (int w = 0; w < NW; w++) { x[w] = R[w] & Bc[w]; m |= x[w] & fw.first(pv, w); }
         if (m) { found = true; break; }
         fw.rfollow(pv, x, R);
-        j--;
-        if (!any_w<NW>(R)) break;               // only possible when the match began in the entry set
-        if (j < left_edge) { pend = true; break; }
+        if (!any_w<NW>(R)) { dead = true; break; }     // only possible when the match began in the entry set
+    }
+    int64_t j = tile_lo + rel;
+    if (!found && !dead) {
+        // slow path: the walk left the tile; continue in global memory
+        for (;;) {
+            if (j < left_edge) { pend = true; break; }
+            load_B<NW>(pv, (uint32_t)sp.text[j], Bc);
+            uint32_t m = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) { x[w] = R[w] & Bc[w]; m |= x[w] & fw.first(pv, w); }
+            if (m) { found = true; break; }
+            fw.rfollow(pv, x, R);
+            j--;
+            if (!any_w<NW>(R)) break;
+        }
     }
     if (slot < sp.out_cap) {
         long long* o = sp.out + 2 * slot;

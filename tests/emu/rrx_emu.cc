@@ -78,12 +78,19 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
             for (int k = 0; k < 16 && g + k < (int64_t)len; k++) dst[k] = text[g + k];
         }
         bool any_open = false;
+        ts.misc[TS::M_RQCNT] = 0;
         for (int t = 0; t < ROWS; t++) {
             ProgView pv = view(t);
             Prog<NW, NT, NB> fw;
             fw.init(pv);
             phase_a<NW>(sp, pv, fw, ts, t);
             any_open = any_open || ts.sum_kind[t] == K_RANK1 || ts.sum_kind[t] == K_HARD;
+        }
+        for (int t = 0; t < ROWS; t++) {
+            ProgView pv = view(t);
+            Prog<NW, NT, NB> fw;
+            fw.init(pv);
+            phase_a2<NW>(pv, fw, ts, t);
         }
         {
             ProgView pv = view(0);

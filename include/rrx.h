@@ -115,6 +115,26 @@ int rrx_scanner_copy_matches(rrx_scanner* s, int64_t* host_out, uint64_t n, void
 /* Composite transfer function of the last scanned shard: 1+3*words uint32 (kind, b, U, P); host copy. */
 int rrx_scanner_shard_summary(rrx_scanner* s, uint32_t* out, uint64_t cap_words, void* stream);
 
+/* ---- sharded scans (one shard per GPU): host-side helpers, no device work ---------------------
+ * A shard summary is the composite transfer function of the shard (rrx_scanner_shard_summary):
+ * words32 [kind, b[W], U[W], P[W]].  Given the summaries of ALL shards in rank order (as returned
+ * by an allgather), rrx_fold_entry computes the exact forward set entering shard `rank`.
+ * *exact is 0 when some summary left of `rank` is opaque (only valid for the entry it was computed
+ * with): the caller must then rescan that shard with its exact entry and fold again. */
+int rrx_fold_entry(const rrx_program* p, const uint32_t* summaries, uint32_t n_shards, uint32_t rank,
+                   uint32_t* entry_out, int* exact);
+/* exit = summary applied to entry (both words32 per rrx_info.words). */
+int rrx_apply_summary(const rrx_program* p, const uint32_t* summary, const uint32_t* entry, uint32_t* exit_out);
+/* Pending start scans of the last scan (those that ran off the left edge of the readable text):
+ * copies up to cap records {uint64 match_index; int64 next_offset; uint32 R[32]} to host. */
+int rrx_scanner_copy_pending(rrx_scanner* s, void* host_out, uint64_t cap, uint64_t* n_out, void* stream);
+/* Continue start scans handed over by the shard to the right: for each record walk backwards from
+ * the END of this shard's text (record.next_offset is rewritten relative to this shard: -1 = its
+ * last byte).  On return start_out[i] is the global start offset, or -1 if the walk ran off this
+ * shard's left edge too (then the record is updated for the next shard to the left). */
+int rrx_continue_starts(const rrx_program* p, const uint8_t* d_text, uint64_t len, uint64_t left_context,
+                        uint64_t base_offset, void* records_host, uint64_t n, int64_t* start_out, void* stream);
+
 /* ---- measurement harness: synthetic corpora of SURVEY.md §8d, generated in device memory ------ */
 int rrx_corpus_iid_device(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, const uint8_t alpha[256], void* stream);
 int rrx_corpus_records_device(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, void* stream);

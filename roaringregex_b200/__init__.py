@@ -95,6 +95,10 @@ def lib() -> C.CDLL:
         "rrx_scanner_result": (C.c_int, [vp, C.POINTER(_Result), vp]),
         "rrx_scanner_shard_summary": (C.c_int, [vp, vp, u64, vp]),
         "rrx_scanner_copy_matches": (C.c_int, [vp, vp, u64, vp]),
+        "rrx_scanner_copy_pending": (C.c_int, [vp, vp, u64, C.POINTER(u64), vp]),
+        "rrx_fold_entry": (C.c_int, [vp, vp, u32, u32, vp, C.POINTER(C.c_int)]),
+        "rrx_apply_summary": (C.c_int, [vp, vp, vp, vp]),
+        "rrx_continue_starts": (C.c_int, [vp, vp, u64, u64, u64, vp, u64, vp, vp]),
         "rrx_corpus_iid_device": (C.c_int, [vp, u64, u64, u64, vp, vp]),
         "rrx_corpus_records_device": (C.c_int, [vp, u64, u64, u64, vp]),
         "rrx_last_error": (C.c_char_p, []),

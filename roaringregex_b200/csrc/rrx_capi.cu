@@ -337,6 +337,50 @@ int rrx_scanner_copy_matches(rrx_scanner* s, int64_t* host_out, uint64_t n, void
     return RRX_OK;
 }
 
+int rrx_fold_entry(const rrx_program* p, const uint32_t* summaries, uint32_t n_shards, uint32_t rank, uint32_t* entry_out, int* exact) {
+    if (!p || !summaries || !entry_out || !exact) return set_err(RRX_ERR_ARG, "null argument");
+    fold_entry_host(p->prog.hdr().NW, summaries, n_shards, rank, entry_out, exact);
+    return RRX_OK;
+}
+int rrx_apply_summary(const rrx_program* p, const uint32_t* summary, const uint32_t* entry, uint32_t* exit_out) {
+    if (!p || !summary || !entry || !exit_out) return set_err(RRX_ERR_ARG, "null argument");
+    apply_summary_host(p->prog.hdr().NW, summary, entry, exit_out);
+    return RRX_OK;
+}
+int rrx_scanner_copy_pending(rrx_scanner* s, void* host_out, uint64_t cap, uint64_t* n_out, void* stream) {
+    if (!s || !n_out) return set_err(RRX_ERR_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    RRX_CUDA(cudaMemcpyAsync(s->h_ctr, s->d_ctrl, 32, cudaMemcpyDeviceToHost, st));
+    RRX_CUDA(cudaStreamSynchronize(st));
+    uint64_t n = s->h_ctr[2];
+    if (n > s->pending_cap) n = s->pending_cap;
+    *n_out = n;
+    if (n > cap) n = cap;
+    if (n && host_out) RRX_CUDA(cudaMemcpy(host_out, s->d_pending, n * sizeof(PendingStart), cudaMemcpyDeviceToHost));
+    return RRX_OK;
+}
+int rrx_continue_starts(const rrx_program* p, const uint8_t* d_text, uint64_t len, uint64_t left_context, uint64_t base_offset,
+                        void* records_host, uint64_t n, int64_t* start_out, void* stream) {
+    if (!p || (!records_host && n) || (!start_out && n)) return set_err(RRX_ERR_ARG, "null argument");
+    if (!n) return RRX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* d_prog = nullptr;
+    PendingStart* d_recs = nullptr;
+    long long* d_out = nullptr;
+    const size_t pb = p->prog.blob.size() * 4;
+    RRX_CUDA(cudaMalloc(&d_prog, pb));
+    RRX_CUDA(cudaMalloc(&d_recs, n * sizeof(PendingStart)));
+    RRX_CUDA(cudaMalloc(&d_out, n * 8));
+    cudaMemcpyAsync(d_prog, p->prog.blob.data(), pb, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_recs, records_host, n * sizeof(PendingStart), cudaMemcpyHostToDevice, st);
+    cudaError_t e = launch_continue_starts(p->prog.hdr().NW, d_prog, d_text, len, left_context, base_offset, d_recs, n, d_out, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(start_out, d_out, n * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(records_host, d_recs, n * sizeof(PendingStart), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_prog); cudaFree(d_recs); cudaFree(d_out);
+    return e == cudaSuccess ? RRX_OK : cuda_err(e, "rrx_continue_starts");
+}
+
 int rrx_scanner_shard_summary(rrx_scanner* s, uint32_t* out, uint64_t cap_words, void* stream) {
     const size_t n = 1 + 3 * (size_t)s->NW;
     if (!out || cap_words < n) return set_err(RRX_ERR_ARG, "summary buffer too small");

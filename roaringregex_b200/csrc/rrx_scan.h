@@ -11,6 +11,10 @@ cudaError_t launch_scan(const ScanParams& sp, const ProgHeader& h, int sm_count,
 cudaError_t launch_order(const uint32_t* tile_cnt, const unsigned long long* tile_seg, uint32_t num_tiles,
                          unsigned long long* chunk_scratch, const long long* staging, long long* out, uint64_t cap,
                          cudaStream_t st);
+cudaError_t launch_continue_starts(uint32_t NW, const uint32_t* d_prog, const uint8_t* d_text, uint64_t len, uint64_t left_ctx,
+                                   uint64_t base, void* d_recs, uint64_t n, long long* d_start_out, cudaStream_t st);
+void fold_entry_host(uint32_t NW, const uint32_t* summaries, uint32_t n, uint32_t rank, uint32_t* entry_out, int* exact);
+void apply_summary_host(uint32_t NW, const uint32_t* s, const uint32_t* entry, uint32_t* out);
 cudaError_t launch_corpus_iid(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, const uint8_t* alpha256, cudaStream_t st);
 cudaError_t launch_corpus_records(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, cudaStream_t st);
 }  // namespace rrx

@@ -23,8 +23,10 @@
 
 #if defined(__CUDACC__) && !defined(RRX_HOST_EMU)
 #define RRX_DEV __device__ __forceinline__
+#define RRX_HD __host__ __device__ __forceinline__
 #else
 #define RRX_DEV inline
+#define RRX_HD inline
 #endif
 
 #ifdef RRX_HOST_EMU
@@ -81,7 +83,7 @@ template <int NW> RRX_DEV bool any_w(const uint32_t* a) {
     for (int w = 0; w < NW; w++) o |= a[w];
     return o != 0;
 }
-template <int NW> RRX_DEV bool meets(const uint32_t* a, const uint32_t* b) {
+template <int NW> RRX_HD bool meets(const uint32_t* a, const uint32_t* b) {
     uint32_t o = 0;
 #pragma unroll
     for (int w = 0; w < NW; w++) o |= a[w] & b[w];
@@ -261,13 +263,13 @@ template <int NW> struct Comp {
     uint32_t kind;
     uint32_t b[NW], U[NW], P[NW];   // exit = b | (entry meets P ? U : 0)   [K_RANK1]
 };
-template <int NW> RRX_DEV void comp_ident(Comp<NW>& c) {
+template <int NW> RRX_HD void comp_ident(Comp<NW>& c) {
     c.kind = K_IDENT;
 #pragma unroll
     for (int w = 0; w < NW; w++) c.b[w] = c.U[w] = c.P[w] = 0;
 }
 // r = "x first, then y".  Neither is K_HARD/K_WAIT here.
-template <int NW> RRX_DEV void comp_compose(const Comp<NW>& x, const Comp<NW>& y, Comp<NW>& r) {
+template <int NW> RRX_HD void comp_compose(const Comp<NW>& x, const Comp<NW>& y, Comp<NW>& r) {
     const uint32_t xt = x.kind & K_TYPE, yt = y.kind & K_TYPE;
     if (yt == K_CLOSED || xt == K_IDENT) { r = y; return; }
     if (yt == K_IDENT) { r = x; return; }
@@ -282,7 +284,7 @@ template <int NW> RRX_DEV void comp_compose(const Comp<NW>& x, const Comp<NW>& y
     }
     r.kind = (hit_U ? K_RANK1 : K_CLOSED) | (x.kind & K_OPAQUE);
 }
-template <int NW> RRX_DEV void comp_apply(const Comp<NW>& c, const uint32_t* entry, uint32_t* out) {
+template <int NW> RRX_HD void comp_apply(const Comp<NW>& c, const uint32_t* entry, uint32_t* out) {
     const uint32_t ct = c.kind & K_TYPE;
     if (ct == K_IDENT) {
 #pragma unroll
@@ -293,7 +295,7 @@ template <int NW> RRX_DEV void comp_apply(const Comp<NW>& c, const uint32_t* ent
 #pragma unroll
     for (int w = 0; w < NW; w++) out[w] = c.b[w] | (hit ? c.U[w] : 0u);
 }
-template <int NW> RRX_DEV void comp_closed(Comp<NW>& c, const uint32_t* b, uint32_t flags) {
+template <int NW> RRX_HD void comp_closed(Comp<NW>& c, const uint32_t* b, uint32_t flags) {
     c.kind = K_CLOSED | flags;
 #pragma unroll
     for (int w = 0; w < NW; w++) { c.b[w] = b[w]; c.U[w] = 0; c.P[w] = 0; }

@@ -1,0 +1,232 @@
+"""Sharded scans: one contiguous byte range per GPU.
+
+Every rank scans its shard speculatively with an EMPTY entry set, then the ranks exchange one tiny
+message each — the shard's composite transfer function (1+3*W words) — with ONE allgather, fold
+the summaries of the ranks to their left into their exact entry set, and repair their result:
+
+  * entry set empty, or dead within the shard's first bytes  -> nothing or a few matches to add;
+  * otherwise                                                  -> the shard's PREFIX is rescanned
+    with the exact entry until the exact and the speculative scan agree on the automaton state
+    (from there on they agree forever); the exact prefix matches replace the speculative ones;
+  * if they never agree inside the prefix window               -> the whole shard is rescanned.
+
+Lazy start scans that run off a shard's left edge use `halo` bytes of left context resident on the
+rank; scans that exhaust even that are handed to the rank on the left (second, rare exchange).
+
+The collective is whatever `comm` provides (torch.distributed: NCCL on GPUs, gloo in the CPU
+tests); the per-shard work is done by a `backend` — DeviceBackend (librrx, the product) or, in the
+CPU test-suite only, an emulator-backed stand-in.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import Scanner, RRegex, lib, _check
+
+PREFIX_WINDOW = 1 << 20          # bytes of a shard rescanned with the exact entry before giving up
+PENDING_RECORD = 8 + 8 + 4 * 32  # sizeof(PendingStart)
+
+
+@dataclass
+class ShardScan:
+    """Outcome of one scan of (part of) a shard."""
+    n: int                      # matches found
+    matches: np.ndarray | None  # (n,2) int64 on the host, or None if left on the device
+    summary: np.ndarray         # composite of the scanned range [kind, b, U, P]
+    pending: list = field(default_factory=list)   # [(match_index, global_next_offset, R words)]
+    handle: object = None       # backend-specific (device list)
+
+
+class DeviceBackend:
+    """Scans a shard resident in HBM through librrx (the product path)."""
+
+    def __init__(self, regex: RRegex, d_text_ptr: int, shard_len: int, base: int, halo: int, capacity: int, stream: int = 0):
+        self.regex, self.ptr, self.len, self.base, self.halo, self.stream = regex, d_text_ptr, shard_len, base, halo, stream
+        self.capacity = capacity
+        self.scanner = Scanner(regex, shard_len, capacity)
+        self.prefix_scanner = None
+        self.words = regex.info["words"]
+
+    def scan(self, length: int, entry, fetch: bool, prefix: bool = False) -> ShardScan:
+        sc = self.scanner
+        if prefix:
+            if self.prefix_scanner is None:
+                self.prefix_scanner = Scanner(self.regex, min(self.len, PREFIX_WINDOW), min(self.len, PREFIX_WINDOW) + 16, jit=False)
+            sc = self.prefix_scanner
+        sc.scan(self.ptr, length, self.base, self.halo, entry, self.stream)
+        r = sc.result(self.stream)
+        if r["error_bits"]:
+            raise RuntimeError(f"scan kernel error bits {r['error_bits']}")
+        if r["n_matches"] > r["capacity"]:
+            raise RuntimeError("match buffer too small for this shard")
+        pend = []
+        if r["n_pending"]:
+            buf = np.zeros(r["n_pending"] * PENDING_RECORD, dtype=np.uint8)
+            n = C.c_uint64(0)
+            _check(lib().rrx_scanner_copy_pending(sc._h, buf.ctypes.data, r["n_pending"], C.byref(n), self.stream))
+            if int(n.value) < r["n_pending"]:
+                raise RuntimeError("too many start scans cross the shard's left edge (pending list overflow)")
+            for i in range(int(n.value)):
+                rec = buf[i * PENDING_RECORD:(i + 1) * PENDING_RECORD]
+                mi, nxt = np.frombuffer(rec[:16].tobytes(), dtype=np.int64)
+                pend.append((int(mi), self.base + int(nxt), np.frombuffer(rec[16:].tobytes(), dtype=np.uint32).copy()))
+        return ShardScan(n=r["n_matches"], matches=sc.matches(self.stream) if fetch else None,
+                         summary=sc.shard_summary(self.stream), pending=pend, handle=sc)
+
+    def head(self, scan: ShardScan, k: int) -> np.ndarray:
+        """First k matches of a scan left on the device."""
+        k = min(k, scan.n)
+        out = np.empty((k, 2), dtype=np.int64)
+        _check(lib().rrx_scanner_copy_matches(scan.handle._h, out.ctypes.data, k, self.stream))
+        return out
+
+    def continue_starts(self, records):
+        """records: [(global_next_offset, R words)] -> (starts list, updated records)."""
+        n = len(records)
+        buf = np.zeros(n * PENDING_RECORD, dtype=np.uint8)
+        for i, (nxt, R) in enumerate(records):
+            buf[i * PENDING_RECORD + 8:i * PENDING_RECORD + 16] = np.frombuffer(np.int64(nxt).tobytes(), dtype=np.uint8)
+            buf[i * PENDING_RECORD + 16:(i + 1) * PENDING_RECORD] = np.frombuffer(np.asarray(R, dtype=np.uint32).tobytes(), dtype=np.uint8)
+        starts = np.zeros(n, dtype=np.int64)
+        _check(lib().rrx_continue_starts(self.regex._h, self.ptr, self.len, self.halo, self.base, buf.ctypes.data, n,
+                                         starts.ctypes.data, self.stream))
+        out = []
+        for i in range(n):
+            rec = buf[i * PENDING_RECORD:(i + 1) * PENDING_RECORD]
+            out.append((int(np.frombuffer(rec[8:16].tobytes(), dtype=np.int64)[0]), np.frombuffer(rec[16:].tobytes(), dtype=np.uint32).copy()))
+        return starts.tolist(), out
+
+
+def fold_entry(regex: RRegex, summaries: np.ndarray, rank: int):
+    """Exact entry set of `rank` from all ranks' summaries ((world, 1+3W) uint32).  -> (entry, exact)"""
+    w = regex.info["words"]
+    s = np.ascontiguousarray(summaries, dtype=np.uint32)
+    entry = np.zeros(w, dtype=np.uint32)
+    exact = C.c_int(0)
+    _check(lib().rrx_fold_entry(regex._h, s.ctypes.data, s.shape[0], rank, entry.ctypes.data, C.byref(exact)))
+    return entry, bool(exact.value)
+
+
+def apply_summary(regex: RRegex, summary: np.ndarray, entry: np.ndarray) -> np.ndarray:
+    w = regex.info["words"]
+    out = np.zeros(w, dtype=np.uint32)
+    s = np.ascontiguousarray(summary, dtype=np.uint32)
+    e = np.ascontiguousarray(entry, dtype=np.uint32)
+    _check(lib().rrx_apply_summary(regex._h, s.ctypes.data, e.ctypes.data, out.ctypes.data))
+    return out
+
+
+@dataclass
+class ShardResult:
+    """Exact matches of one shard: `head` (host, repaired prefix) followed by the speculative scan's
+    matches from index `skip` on (device list `tail`, or host array when fetched)."""
+    count: int
+    head: np.ndarray
+    skip: int
+    tail: ShardScan
+    rescans: int = 0             # 0 none, 1 prefix only, 2 whole shard
+    pending: list = field(default_factory=list)   # [(where, index, global_next_offset, R)], where in {"head","tail"}
+    patches: list = field(default_factory=list)   # [(where, index, start)] starts found by ranks to the left
+
+    def to_host(self, backend) -> np.ndarray:
+        t = self.tail.matches if self.tail.matches is not None else backend.head(self.tail, self.tail.n)
+        out = np.concatenate([self.head, t[self.skip:]]) if (len(self.head) or self.skip) else t.copy()
+        for where, idx, s in self.patches:
+            out[idx if where == "head" else len(self.head) + idx - self.skip, 0] = s
+        return out
+
+
+def scan_sharded(regex: RRegex, backend, comm, rank: int, world: int, fetch: bool = False) -> ShardResult:
+    """The per-rank procedure.  `comm.allgather(np.ndarray) -> (world, ...) ndarray` is the only
+    collective on the data path (one summary of 1+3W words per rank and round; one round unless a
+    summary is opaque); `comm.allgather_obj(obj)` (pickled, tiny) serves the rare hand-over of
+    unfinished start scans."""
+    spec = backend.scan(backend.len, None, fetch)                 # speculative: empty entry
+    advertised, result, last_entry = spec, None, None
+    for _round in range(max(world, 1)):
+        summaries = comm.allgather(advertised.summary.astype(np.uint32))
+        entry, exact = fold_entry(regex, summaries, rank)
+        if result is None or not np.array_equal(entry, last_entry):
+            last_entry = entry
+            if entry.any():
+                result = _repair(regex, backend, spec, entry, fetch)
+                if result.rescans == 2:
+                    advertised = result.tail                      # now computed with the exact entry
+            else:
+                result = ShardResult(spec.n, np.zeros((0, 2), np.int64), 0, spec, 0,
+                                     [("tail", i, nxt, R) for i, nxt, R in spec.pending])
+        if comm.allgather(np.array([1 if exact else 0], dtype=np.uint32)).all():
+            break                                                 # nobody folded through an opaque summary
+    _resolve_pending(backend, comm, rank, world, result)
+    return result
+
+
+def _repair(regex, backend, spec: ShardScan, entry: np.ndarray, fetch: bool) -> ShardResult:
+    window = min(backend.len, PREFIX_WINDOW)
+    if window < backend.len:
+        window -= window % 4096
+    a = backend.scan(window, None, True, prefix=True)             # speculative state after the window
+    b = backend.scan(window, entry, True, prefix=True)            # exact state after the window
+    sa = apply_summary(regex, a.summary, np.zeros_like(entry))
+    sb = apply_summary(regex, b.summary, entry)
+    if np.array_equal(sa, sb) or window == backend.len:
+        skip = a.n                                                # speculative matches ending inside the window
+        pend = [("tail", i, nxt, R) for i, nxt, R in spec.pending if i >= skip] + [("head", i, nxt, R) for i, nxt, R in b.pending]
+        return ShardResult(len(b.matches) + spec.n - skip, b.matches, skip, spec, 1, pend)
+    full = backend.scan(backend.len, entry, fetch)                # the entry's influence never died: rescan
+    return ShardResult(full.n, np.zeros((0, 2), np.int64), 0, full, 2, [("tail", i, nxt, R) for i, nxt, R in full.pending])
+
+
+def _resolve_pending(backend, comm, rank, world, result: ShardResult):
+    """Start scans that ran off the left edge of the rank's readable text travel left, one rank
+    per hop, until some rank finds the start.  Usually there are none."""
+    counts = comm.allgather(np.array([len(result.pending)], dtype=np.uint32))
+    if not counts.any():
+        return
+    flight = [(rank, where, idx, nxt, R) for where, idx, nxt, R in result.pending]   # records I must hand left
+    found = []
+    for hop in range(1, world):
+        everyone = comm.allgather_obj(flight)
+        todo = [rec for recs in everyone for rec in recs if rec[0] - hop == rank]      # owner - hop == me
+        flight = []
+        if todo:
+            starts, upd = backend.continue_starts([(nxt, R) for _o, _w, _i, nxt, R in todo])
+            for (owner, where, idx, _n, _r), s, (nxt2, R2) in zip(todo, starts, upd):
+                if s >= 0:
+                    found.append((owner, where, idx, s))
+                elif s == -1:
+                    flight.append((owner, where, idx, nxt2, R2))
+    fixes = comm.allgather_obj(found)
+    result.patches = [(where, idx, s) for recs in fixes for (owner, where, idx, s) in recs if owner == rank]
+
+
+class TorchComm:
+    """torch.distributed as the collective provider (NCCL with device tensors, gloo with CPU ones)."""
+
+    def __init__(self, dist, device):
+        self.dist, self.device = dist, device
+
+    def allgather(self, arr: np.ndarray) -> np.ndarray:
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.int32)).to(self.device)
+        out = [torch.empty_like(t) for _ in range(self.dist.get_world_size())]
+        self.dist.all_gather(out, t)
+        return np.stack([o.cpu().numpy().view(np.uint32) for o in out])
+
+    def allgather_obj(self, obj):
+        out = [None] * self.dist.get_world_size()
+        self.dist.all_gather_object(out, obj)
+        return out
+
+
+class LocalComm:
+    """Single-rank stand-in."""
+
+    def allgather(self, arr):
+        return np.asarray(arr)[None]
+
+    def allgather_obj(self, obj):
+        return [obj]

@@ -164,30 +164,52 @@ def main():
     stream = torch.cuda.current_stream()
     sh = stream.cuda_stream
 
-    # corpus of this rank, generated in place: [rank*size, (rank+1)*size) of the global text
+    # corpus of this rank, generated in place: [rank*size, (rank+1)*size) of the global text, plus
+    # `halo` bytes of left context for lazy start scans that cross the shard's left edge
     off = rank * size
-    d_text = torch.empty(size + 256, dtype=torch.uint8, device="cuda")
-    gen = (lambda: rrx.corpus_iid(d_text.data_ptr(), off, size, cfg.seed, cfg.alpha, sh)) if cfg.mode == "iid" else \
-          (lambda: rrx.corpus_records(d_text.data_ptr(), off, size, cfg.seed, sh))
-    gen()
+    halo = min(off, 1 << 20)
+    d_buf = torch.empty(halo + size + 256, dtype=torch.uint8, device="cuda")
+    d_text = d_buf[halo:]
+    assert d_text.data_ptr() % 16 == 0
+    if cfg.mode == "iid":
+        rrx.corpus_iid(d_buf.data_ptr(), off - halo, halo + size, cfg.seed, cfg.alpha, sh)
+    else:
+        rrx.corpus_records(d_buf.data_ptr(), off - halo, halo + size, cfg.seed, sh)
     torch.cuda.synchronize()
 
     cap = max(1 << 20, size // 48)
-    sc = rrx.Scanner(regex, size, cap)
-
-    def step():
-        sc.scan(d_text.data_ptr(), size, off, 0, None, sh)
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    res = sc.result(sh)
-    assert res["error_bits"] == 0, res
-    if res["n_matches"] > cap:
-        cap = res["n_matches"] + 1024
+    if world == 1:
         sc = rrx.Scanner(regex, size, cap)
-        step()
+        step = lambda: sc.scan(d_text.data_ptr(), size, off, 0, None, sh)
+        for _ in range(max(args.warmup, 3)):
+            step()
         res = sc.result(sh)
-    n_matches = res["n_matches"]
+        assert res["error_bits"] == 0, res
+        if res["n_matches"] > cap:
+            cap = res["n_matches"] + 1024
+            sc = rrx.Scanner(regex, size, cap)
+            step()
+            res = sc.result(sh)
+        n_matches = res["n_matches"]
+        launches_per_step = res["launches"]
+        is_jit = sc.is_jit
+    else:
+        from roaringregex_b200 import sharded
+        comm = sharded.TorchComm(dist, torch.device("cuda", local))
+        probe = rrx.Scanner(regex, size, cap)
+        probe.scan(d_text.data_ptr(), size, off, halo, None, sh)
+        cap = max(cap, probe.result(sh)["n_matches"] + (1 << 16))
+        del probe
+        be = sharded.DeviceBackend(regex, d_text.data_ptr(), size, off, halo, cap, sh)
+        last = {}
+
+        def step():
+            last["res"] = sharded.scan_sharded(regex, be, comm, rank, world, fetch=False)
+        for _ in range(max(args.warmup, 3)):
+            step()
+        n_matches = last["res"].count
+        launches_per_step = 4 * (1 + (2 if last["res"].rescans == 1 else last["res"].rescans))
+        is_jit = be.scanner.is_jit
 
     def barrier():
         torch.cuda.synchronize()
@@ -200,6 +222,7 @@ def main():
         sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    w0 = time.perf_counter()
     t_all0 = torch.cuda.Event(enable_timing=True); t_all1 = torch.cuda.Event(enable_timing=True)
     t_all0.record(stream)
     for a, b in evs:
@@ -208,11 +231,15 @@ def main():
         b.record(stream)
     t_all1.record(stream)
     barrier()
-    total_ms = t_all0.elapsed_time(t_all1)
+    wall_ms = (time.perf_counter() - w0) * 1e3
+    # N=1: device time between the first launch and the last kernel's end (CUDA events on the launching
+    # stream); N>1: a step contains host-side collectives, so the barrier-to-barrier wall clock counts.
+    total_ms = t_all0.elapsed_time(t_all1) if world == 1 else wall_ms
     kern_ms = [a.elapsed_time(b) for a, b in evs]
     clocks = sampler.stop() if sampler else None
-    res = sc.result(sh)
-    assert res["n_matches"] == n_matches and res["error_bits"] == 0
+    if world == 1:
+        res = sc.result(sh)
+        assert res["n_matches"] == n_matches and res["error_bits"] == 0
 
     if dist is not None:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
@@ -268,7 +295,8 @@ def main():
                    "states_raw": info["n_raw"], "states_flat": info["n_flat"], "states_device": info["n_device"], "words": info["words"]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "kernel": "rrx_scan_kernel", "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "peak_source": peak_src},
-        "e2e": e2e, "gpu_launches": args.steps * res["launches"], "clocks": clocks,
+        "e2e": e2e, "gpu_launches": args.steps * launches_per_step, "clocks": clocks,
+        "kernel_variant": "run-time specialised (NVRTC)" if is_jit else "pre-compiled generic",
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(cfg, 32 << 20)

@@ -201,3 +201,55 @@ def test_runtime_specialised_random_patterns(rrx, oracle_api, torch_cuda):
         sc.scan(d.data_ptr(), len(text))
         assert sc.result()["n_matches"] == len(want), pat
         assert np.array_equal(sc.matches(), want), pat
+
+
+def _run_world_gpu(rrx, torch, pattern, text, world, halo):
+    """`world` shards of one device buffer, scanned by `world` threads through the product's
+    DeviceBackend (librrx), exchanging summaries through an in-process allgather."""
+    import threading
+    from roaringregex_b200 import sharded
+    from test_sharded import ThreadComm
+    n = len(text)
+    cuts = [((n * r // world) // 128) * 128 for r in range(world)] + [n]
+    d = torch.from_numpy(np.ascontiguousarray(text)).cuda()
+    comm = ThreadComm(world)
+    out, errs = [None] * world, []
+    regex = rrx.RRegex(pattern)
+
+    def work(rank):
+        try:
+            torch.cuda.set_device(0)
+            lo, hi = cuts[rank], cuts[rank + 1]
+            be = sharded.DeviceBackend(regex, d.data_ptr() + lo, hi - lo, lo, min(halo, lo), (hi - lo) // 2 + 4096)
+            res = sharded.scan_sharded(regex, be, comm.view(rank), rank, world, fetch=True)
+            out[rank] = res.to_host(be)
+        except Exception as e:      # pragma: no cover
+            errs.append(e)
+            comm.bar.abort()
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    if errs:
+        raise errs[0]
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("cfg_id", [2, 5])
+def test_sharded_on_device(rrx, oracle_api, torch_cuda, cfg_id):
+    cfg = CONFIGS[cfg_id]
+    text = cpu_corpus(cfg, 0, (8 << 20) + 4096 * 3)
+    want = oracle_api.Oracle(cfg.pattern).lazy_matches(text)
+    for world in (2, 4):
+        got = _run_world_gpu(rrx, torch_cuda, cfg.pattern, text, world, halo=1 << 16)
+        assert np.array_equal(got, want), (cfg_id, world)
+
+
+def test_sharded_start_scan_travels_through_all_shards(rrx, oracle_api, torch_cuda, monkeypatch):
+    from roaringregex_b200 import sharded
+    monkeypatch.setattr(sharded, "PREFIX_WINDOW", 8192)
+    n = 4 * 65536
+    text = np.full(n, ord("a"), dtype=np.uint8)
+    text[0] = ord("z")
+    text[-5] = ord("q")
+    got = _run_world_gpu(rrx, torch_cuda, "(x|y)*z.*q", text, 4, halo=256)
+    assert got.tolist() == [[0, n - 4]]

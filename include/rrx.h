@@ -68,6 +68,11 @@ int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, u
 int rrx_scan_host(const rrx_program* p, const uint8_t* text, uint64_t len, uint64_t base_offset,
                   int mode, rrx_matches** out);
 
+/* Whole-string acceptance, what the reference's AcceptanceIterator answers (regex.h:150-165):
+ * *accepted = 1 iff text[0:len) is in the language.  Sequential in len (one GPU thread), like the
+ * reference; provided for source compatibility, not for throughput. */
+int rrx_accepts_host(const rrx_program* p, const uint8_t* text, uint64_t len, int* accepted);
+
 uint64_t rrx_matches_count(const rrx_matches* m);
 const int64_t* rrx_matches_data(rrx_matches* m);                /* host pairs (start,end); copied D2H on first use */
 const int64_t* rrx_matches_device_data(const rrx_matches* m);   /* device pairs */

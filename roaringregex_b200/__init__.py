@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
         "rrx_program_raw_finals": (i64, [vp, vp, u64]),
         "rrx_scan_device": (C.c_int, [vp, vp, u64, u64, C.c_int, C.POINTER(vp), vp]),
         "rrx_scan_host": (C.c_int, [vp, vp, u64, u64, C.c_int, C.POINTER(vp)]),
+        "rrx_accepts_host": (C.c_int, [vp, vp, u64, C.POINTER(C.c_int)]),
         "rrx_matches_count": (u64, [vp]),
         "rrx_matches_data": (vp, [vp]),
         "rrx_matches_device_data": (vp, [vp]),
@@ -198,6 +199,13 @@ class RRegex:
         _check(lib().rrx_scan_device(self._h, d_ptr, length, base_offset, mode, C.byref(h), stream))
         return _take_matches(h)
 
+    def accepts(self, text) -> bool:
+        """Whole-string acceptance (the reference's AcceptanceIterator); runs on the GPU."""
+        buf = _as_u8(text)
+        acc = C.c_int(0)
+        _check(lib().rrx_accepts_host(self._h, buf.ctypes.data if len(buf) else None, len(buf), C.byref(acc)))
+        return bool(acc.value)
+
     def get_lazy_iter(self, text) -> "LazyIterator":
         return LazyIterator(self, text)
 
@@ -279,24 +287,29 @@ class LazyIterator:
 
 
 class AcceptanceIterator:
-    """regex.h:150-165: consume the whole NUL-terminated text; `*` is Match(0,len) iff the whole
-    string is in the language.  Answered on the GPU: the whole string matches iff LAZY-v1 ... has a
-    match ending at len whose anchored variant starts at 0; computed with an anchored entry set."""
+    """regex.h:150-165: `++` consumes the whole NUL-terminated text; `*` is Match(0,len) iff the
+    whole string is in the language."""
 
     def __init__(self, regex: RRegex, text):
         raw = bytes(text) if not isinstance(text, str) else text.encode("latin-1")
         nul = raw.find(b"\0")
         self._text = raw if nul < 0 else raw[:nul]
         self._regex = regex
-        self._done = False
         self._accepted = None
 
     def advance(self):
-        self._done = True
+        self._accepted = self._regex.accepts(self._text)
         return self
 
     def value(self):
-        raise RrxError("whole-string acceptance is not on the accelerated path yet (see DESIGN.md, out of scope)")
+        if self._accepted is None:           # the reference's processor before any byte: initial state only
+            return Match(0, 0, self._text) if self._regex.info["nullable"] else None
+        return Match(0, len(self._text), self._text) if self._accepted else None
+
+    def create_copy(self):
+        c = AcceptanceIterator.__new__(AcceptanceIterator)
+        c.__dict__.update(self.__dict__)
+        return c
 
 
 class Scanner:

@@ -440,6 +440,26 @@ int rrx_scan_host(const rrx_program* p, const uint8_t* text, uint64_t len, uint6
     return rc;
 }
 
+int rrx_accepts_host(const rrx_program* p, const uint8_t* text, uint64_t len, int* accepted) {
+    if (!p || !accepted || (!text && len)) return set_err(RRX_ERR_ARG, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return set_err(RRX_ERR_CUDA, "no CUDA device: librrx has no CPU fallback");
+    uint8_t* d = nullptr;
+    uint32_t* d_prog = nullptr;
+    int* d_out = nullptr;
+    const size_t pb = p->prog.blob.size() * 4;
+    RRX_CUDA(cudaMalloc(&d, len + 16));
+    RRX_CUDA(cudaMalloc(&d_prog, pb));
+    RRX_CUDA(cudaMalloc(&d_out, 4));
+    cudaMemcpy(d, text, len, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_prog, p->prog.blob.data(), pb, cudaMemcpyHostToDevice);
+    cudaError_t e = launch_accepts(p->prog.hdr().NW, d_prog, d, len, d_out, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(accepted, d_out, 4, cudaMemcpyDeviceToHost);
+    cudaFree(d); cudaFree(d_prog); cudaFree(d_out);
+    return e == cudaSuccess ? RRX_OK : cuda_err(e, "rrx_accepts_host");
+}
+
 uint64_t rrx_matches_count(const rrx_matches* m) { return m ? m->count : 0; }
 const int64_t* rrx_matches_device_data(const rrx_matches* m) { return reinterpret_cast<const int64_t*>(m->d_pairs); }
 const int64_t* rrx_matches_data(rrx_matches* m) {

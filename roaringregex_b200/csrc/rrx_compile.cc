@@ -579,6 +579,7 @@ Program build_program(const Automaton& a, const std::string& pattern, bool reduc
     h.off_B = take(256 * NW);
     h.off_follow = take(P * NW); h.off_rfollow = take(P * NW);
     h.off_rows = take(P * NW); h.off_rrows = take(P * NW);
+    h.off_rfull = take(P * NW);
     h.total_words = off;
 
     Program pr;
@@ -607,9 +608,12 @@ Program build_program(const Automaton& a, const std::string& pattern, bool reduc
     for (uint32_t c = 0; c < 128; c++)
         for (uint32_t k = 0; k < P; k++)
             if ((pos[k].cls[c >> 6] >> (c & 63)) & 1ull) pr.blob[h.off_B + c * NW + (k >> 5)] |= 1u << (k & 31);
+    std::vector<Bits> rfull(P, Bits(P));
+    for (uint32_t k = 0; k < P; k++) for (uint32_t t : pos[k].follow.list()) rfull[t].add(k);
     for (uint32_t k = 0; k < P; k++) {
         put_bits(pr.blob, h.off_follow + k * NW, fol[k], NW);
         put_bits(pr.blob, h.off_rfollow + k * NW, rfol[k], NW);
+        put_bits(pr.blob, h.off_rfull + k * NW, rfull[k], NW);
     }
     return pr;
 }

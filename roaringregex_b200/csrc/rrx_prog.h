@@ -33,7 +33,8 @@ struct ProgHeader {
     uint32_t n_raw, ref_width_class, nullable;
     uint32_t static_depth;      // longest path (edges) in the pruned follow graph; 0xffffffff if cyclic
     uint32_t n_flat;            // atoms + START before reduction
-    uint32_t reserved[2];
+    uint32_t off_rfull;         // P*NW: transpose of the UNPRUNED follow relation (whole-string acceptance)
+    uint32_t reserved[1];
 };
 
 }  // namespace rrx

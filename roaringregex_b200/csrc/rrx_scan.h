@@ -13,6 +13,7 @@ cudaError_t launch_order(const uint32_t* tile_cnt, const unsigned long long* til
                          cudaStream_t st);
 cudaError_t launch_continue_starts(uint32_t NW, const uint32_t* d_prog, const uint8_t* d_text, uint64_t len, uint64_t left_ctx,
                                    uint64_t base, void* d_recs, uint64_t n, long long* d_start_out, cudaStream_t st);
+cudaError_t launch_accepts(uint32_t NW, const uint32_t* d_prog, const uint8_t* d_text, uint64_t len, int* d_out, cudaStream_t st);
 void fold_entry_host(uint32_t NW, const uint32_t* summaries, uint32_t n, uint32_t rank, uint32_t* entry_out, int* exact);
 void apply_summary_host(uint32_t NW, const uint32_t* s, const uint32_t* entry, uint32_t* out);
 cudaError_t launch_corpus_iid(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, const uint8_t* alpha256, cudaStream_t st);

@@ -42,7 +42,59 @@ __global__ void continue_starts_kernel(const uint32_t* prog, const uint8_t* text
     }
 }
 
+// Whole-string acceptance (the reference's AcceptanceIterator, regex.h:150-165): text[0:len) is in
+// the language iff, walking BACKWARDS from the accepting positions over the unpruned automaton, a
+// first-position is alive after consuming byte 0.  One thread, sequential in len like the reference;
+// kept for source compatibility of the drop-in API, not a throughput path.
+template <int NW>
+__global__ void accepts_kernel(const uint32_t* prog, const uint8_t* text, long long len, int* out) {
+    const ProgHeader& h = *reinterpret_cast<const ProgHeader*>(prog);
+    if (len == 0) { *out = (int)h.nullable; return; }
+    uint32_t R[NW], x[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) R[w] = prog[h.off_accept + w];
+    for (long long j = len - 1; j >= 0; j--) {
+        const uint32_t c = text[j];
+        uint32_t any = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) { x[w] = R[w] & prog[h.off_B + c * NW + w]; any |= x[w]; }
+        if (!any) { *out = 0; return; }
+        if (j == 0) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) m |= x[w] & prog[h.off_first + w];
+            *out = m != 0;
+            return;
+        }
+#pragma unroll
+        for (int w = 0; w < NW; w++) R[w] = 0;
+        for (int w = 0; w < NW; w++) {
+            uint32_t v = x[w];
+            while (v) {
+                const uint32_t k = (uint32_t)w * 32u + (uint32_t)(__ffs((int)v) - 1);
+                v &= v - 1;
+                for (int y = 0; y < NW; y++) R[y] |= prog[h.off_rfull + k * NW + y];
+            }
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_accepts(uint32_t NW, const uint32_t* d_prog, const uint8_t* d_text, uint64_t len, int* d_out, cudaStream_t st) {
+#define RRX_GO(NW_) accepts_kernel<NW_><<<1, 1, 0, st>>>(d_prog, d_text, (long long)len, d_out)
+    switch (NW) {
+        case 1: RRX_GO(1); break;
+        case 2: RRX_GO(2); break;
+        case 4: RRX_GO(4); break;
+        case 8: RRX_GO(8); break;
+        case 16: RRX_GO(16); break;
+        case 32: RRX_GO(32); break;
+        default: return cudaErrorInvalidValue;
+    }
+#undef RRX_GO
+    return cudaGetLastError();
+}
 
 cudaError_t launch_continue_starts(uint32_t NW, const uint32_t* d_prog, const uint8_t* d_text, uint64_t len, uint64_t left_ctx,
                                    uint64_t base, void* d_recs, uint64_t n, long long* d_start_out, cudaStream_t st) {

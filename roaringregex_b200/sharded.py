@@ -141,14 +141,19 @@ class ShardResult:
 
 def scan_sharded(regex: RRegex, backend, comm, rank: int, world: int, fetch: bool = False) -> ShardResult:
     """The per-rank procedure.  `comm.allgather(np.ndarray) -> (world, ...) ndarray` is the only
-    collective on the data path (one summary of 1+3W words per rank and round; one round unless a
-    summary is opaque); `comm.allgather_obj(obj)` (pickled, tiny) serves the rare hand-over of
-    unfinished start scans."""
+    collective on the data path: ONE message of 1+3W+1 words per rank (the shard summary and the
+    number of unfinished start scans).  Everything else each rank derives locally from the gathered
+    summaries (every rank can fold every other rank's entry), so in the common case — no entry set
+    survives into any shard, no start scan crosses a halo — a step has exactly one collective.
+    `comm.allgather_obj(obj)` (pickled, tiny) serves the rare hand-over of unfinished start scans."""
     spec = backend.scan(backend.len, None, fetch)                 # speculative: empty entry
     advertised, result, last_entry = spec, None, None
     for _round in range(max(world, 1)):
-        summaries = comm.allgather(advertised.summary.astype(np.uint32))
-        entry, exact = fold_entry(regex, summaries, rank)
+        msg = np.concatenate([advertised.summary.astype(np.uint32), np.array([len(spec.pending)], dtype=np.uint32)])
+        gathered = comm.allgather(msg)
+        summaries, spec_pending = gathered[:, :-1], gathered[:, -1]
+        folds = [fold_entry(regex, summaries, r) for r in range(world)]
+        entry, _ = folds[rank]
         if result is None or not np.array_equal(entry, last_entry):
             last_entry = entry
             if entry.any():
@@ -158,9 +163,11 @@ def scan_sharded(regex: RRegex, backend, comm, rank: int, world: int, fetch: boo
             else:
                 result = ShardResult(spec.n, np.zeros((0, 2), np.int64), 0, spec, 0,
                                      [("tail", i, nxt, R) for i, nxt, R in spec.pending])
-        if comm.allgather(np.array([1 if exact else 0], dtype=np.uint32)).all():
+        if all(ex for _e, ex in folds):
             break                                                 # nobody folded through an opaque summary
-    _resolve_pending(backend, comm, rank, world, result)
+    any_repair = any(e.any() for e, _ex in folds)
+    if any_repair or spec_pending.any():
+        _resolve_pending(backend, comm, rank, world, result)
     return result
 
 

@@ -3,7 +3,7 @@ import numpy as np
 
 FIELDS = ("magic P NW flags n_terms n_bicl use_rows pad0 n_rterms n_rbicl use_rrows pad1 off_first off_accept off_all "
           "off_terms off_bicl off_rowsrc off_rterms off_rbicl off_rrowsrc off_B off_follow off_rfollow off_rows off_rrows "
-          "total n_raw rwc nullable static_depth n_flat").split()
+          "total n_raw rwc nullable static_depth n_flat off_rfull").split()
 
 
 def _int(words):

@@ -41,6 +41,8 @@ typedef struct rrx_info {
     uint32_t nullable;       /* the empty string is in the language */
     uint32_t n_terms, n_bicliques, uses_rows;   /* forward follow decomposition */
     uint32_t static_closed;  /* no chunk's exit can depend on its entry (acyclic pruned follow, depth < 128) */
+    uint32_t sparse_ok;      /* a single-byte cut exists: rows are scanned candidate-driven (DESIGN.md "Sparse row scan") */
+    uint32_t cand_byte;      /* that byte */
 } rrx_info;
 
 /* ---- compile: replaces RRegex::RRegex(const char*) (regex.h:224, Parser.cpp:161-170) ---------- */
@@ -64,7 +66,10 @@ int64_t rrx_program_raw_finals(const rrx_program* p, uint32_t* out, uint64_t cap
 /* d_text: device pointer, 16-byte aligned.  stream: cudaStream_t (NULL = default stream). */
 int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, uint64_t base_offset,
                     int mode, rrx_matches** out, void* stream);
-/* text: host pointer; the copy to the device is part of the call. */
+/* text: host pointer; the copy to the device is part of the call (asynchronous when the buffer is
+ * page-locked).  The program keeps the device text buffer, a scanner and pinned match buffers between
+ * calls, so repeated host scans do not allocate.  The match list of a host scan lives in pinned host
+ * memory: rrx_matches_data() returns it without a further copy; rrx_matches_device_data() is NULL. */
 int rrx_scan_host(const rrx_program* p, const uint8_t* text, uint64_t len, uint64_t base_offset,
                   int mode, rrx_matches** out);
 

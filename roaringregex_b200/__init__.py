@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 from dataclasses import dataclass
 
 import numpy as np
@@ -42,7 +43,7 @@ class InvalidExpression(RrxError):
 
 class _Info(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("n_raw", "ref_width_class", "n_flat", "n_device", "words", "nullable",
-                                          "n_terms", "n_bicliques", "uses_rows", "static_closed")]
+                                          "n_terms", "n_bicliques", "uses_rows", "static_closed", "sparse_ok", "cand_byte")]
 
 
 class _Opts(C.Structure):
@@ -214,17 +215,21 @@ class RRegex:
 
 
 def _take_matches(h) -> np.ndarray:
+    """(M,2) int64 view of the match list owned by the rrx_matches handle (for host scans: pinned
+    memory the D2H copy landed in — no second copy); the handle is released with the array."""
     L = lib()
     n = int(L.rrx_matches_count(h))
-    try:
-        if n == 0:
-            return np.zeros((0, 2), dtype=np.int64)
-        p = L.rrx_matches_data(h)
-        if not p:
-            _check(RRX_ERR_CUDA)
-        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int64)), shape=(n, 2)).copy()
-    finally:
+    if n == 0:
         L.rrx_matches_free(h)
+        return np.zeros((0, 2), dtype=np.int64)
+    p = L.rrx_matches_data(h)
+    if not p:
+        L.rrx_matches_free(h)
+        _check(RRX_ERR_CUDA)
+    arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int64)), shape=(n, 2))
+    fin = weakref.finalize(arr, L.rrx_matches_free, h)
+    fin.atexit = False
+    return arr
 
 
 def _bits_of(words: np.ndarray) -> list[int]:

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -41,9 +42,30 @@ size_t ctrl_layout(size_t T, size_t* off) {
 }
 }  // namespace
 
+// Device-side state kept between rrx_scan_host calls on one program: the text buffer, a scanner
+// sized for it, a private stream and a pool of pinned match buffers.  A host scan is then
+// H2D copy -> kernels -> D2H copy with no allocation on the way (after the first call).
+struct HostCtx {
+    std::mutex mu;
+    int device = -1;
+    cudaStream_t st = nullptr;
+    uint8_t* d_text = nullptr;
+    uint64_t text_cap = 0;
+    rrx_scanner* sc = nullptr;          // freed by rrx_program_free (it refers to the program)
+    uint64_t sc_len = 0, sc_cap = 0;
+    struct Pinned { int64_t* p; uint64_t pairs; };
+    std::vector<Pinned> pool;           // free pinned buffers
+    ~HostCtx() {
+        cudaFree(d_text);
+        for (auto& b : pool) cudaFreeHost(b.p);
+        if (st) cudaStreamDestroy(st);
+    }
+};
+
 struct rrx_program {
     Automaton automaton;   // reference-equivalent view (atoms, flattened positions)
     Program prog;          // device program
+    std::shared_ptr<HostCtx> host = std::make_shared<HostCtx>();
 };
 
 struct rrx_scanner {
@@ -72,9 +94,12 @@ struct rrx_scanner {
 
 struct rrx_matches {
     uint64_t count = 0;
-    long long* d_pairs = nullptr;   // owned
+    long long* d_pairs = nullptr;   // owned (device scans)
     std::vector<int64_t> host;
     bool host_valid = false;
+    // host scans: the list lives in a pinned buffer borrowed from the program's pool
+    std::shared_ptr<HostCtx> owner;
+    HostCtx::Pinned pinned = {nullptr, 0};
 };
 
 extern "C" {
@@ -97,7 +122,11 @@ int rrx_compile_ex(const char* ere, uint32_t flags, rrx_program** out) {
     }
 }
 int rrx_compile(const char* ere, rrx_program** out) { return rrx_compile_ex(ere, RRX_COMPILE_DEFAULT, out); }
-void rrx_program_free(rrx_program* p) { delete p; }
+void rrx_program_free(rrx_program* p) {
+    if (!p) return;
+    if (p->host && p->host->sc) { rrx_scanner_free(p->host->sc); p->host->sc = nullptr; }
+    delete p;
+}
 
 void rrx_program_info(const rrx_program* p, rrx_info* o) {
     const ProgHeader& h = p->prog.hdr();
@@ -111,6 +140,8 @@ void rrx_program_info(const rrx_program* p, rrx_info* o) {
     o->n_bicliques = h.n_bicl;
     o->uses_rows = h.use_rows;
     o->static_closed = (h.static_depth != 0xffffffffu && h.static_depth + 1 <= (uint32_t)ROW_BYTES) ? 1u : 0u;
+    o->sparse_ok = h.sparse_ok;
+    o->cand_byte = h.cand_byte;
 }
 
 int64_t rrx_program_flat_table(const rrx_program* p, int which, uint32_t* out, uint64_t cap) {
@@ -255,6 +286,8 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     {
         const char* e = getenv("RRX_STAGGER_NS");
         sp.stagger_ns = e ? (uint32_t)atoi(e) : 1500u;
+        const char* sv = getenv("RRX_SPARSE");     // 0 forces the dense row scan (A/B measurements)
+        sp.sparse = (h.sparse_ok && !(sv && sv[0] == '0')) ? 1u : 0u;
     }
 #ifdef RRX_PHASE_TIMING
     {
@@ -428,16 +461,71 @@ int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, u
 int rrx_scan_host(const rrx_program* p, const uint8_t* text, uint64_t len, uint64_t base_offset,
                   int mode, rrx_matches** out) {
     if (!p || !out || (!text && len)) return set_err(RRX_ERR_ARG, "null argument");
+    if (mode != RRX_MODE_LAZY_V1) return set_err(RRX_ERR_UNSUPPORTED, "only RRX_MODE_LAZY_V1 is implemented on the device");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return set_err(RRX_ERR_CUDA, "no CUDA device: librrx has no CPU fallback");
-    uint8_t* d = nullptr;
-    RRX_CUDA(cudaMalloc(&d, len + 16));
-    cudaError_t e = cudaMemcpy(d, text, len, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(d); return cuda_err(e, "cudaMemcpy H2D"); }
-    int rc = rrx_scan_device(p, d, len, base_offset, mode, out, nullptr);
-    cudaFree(d);
-    return rc;
+    std::shared_ptr<HostCtx> hc = p->host;
+    std::lock_guard<std::mutex> lk(hc->mu);
+    int dev = 0;
+    RRX_CUDA(cudaGetDevice(&dev));
+    if (hc->device != dev) {            // first use, or the caller switched devices: start over
+        if (hc->sc) { rrx_scanner_free(hc->sc); hc->sc = nullptr; }
+        cudaFree(hc->d_text); hc->d_text = nullptr; hc->text_cap = 0;
+        if (hc->st) { cudaStreamDestroy(hc->st); hc->st = nullptr; }
+        RRX_CUDA(cudaStreamCreateWithFlags(&hc->st, cudaStreamNonBlocking));
+        hc->device = dev;
+    }
+    if (len + 16 > hc->text_cap) {
+        if (hc->sc) { rrx_scanner_free(hc->sc); hc->sc = nullptr; }
+        cudaFree(hc->d_text); hc->d_text = nullptr; hc->text_cap = 0;
+        const uint64_t cap = ((len + 16 + (1ull << 20) - 1) >> 20) << 20;
+        RRX_CUDA(cudaMalloc(&hc->d_text, cap));
+        hc->text_cap = cap;
+    }
+    // the copy is enqueued first, so that whatever set-up follows overlaps it
+    if (len) RRX_CUDA(cudaMemcpyAsync(hc->d_text, text, len, cudaMemcpyHostToDevice, hc->st));
+    uint64_t want_cap = len / 64 + 1024;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (!hc->sc || hc->sc_len < len || hc->sc_cap < want_cap) {
+            if (hc->sc) { rrx_scanner_free(hc->sc); hc->sc = nullptr; }
+            const uint64_t sl = hc->text_cap - 16;
+            int rc = rrx_scanner_create(p, sl, want_cap, &hc->sc);
+            if (rc) return rc;
+            hc->sc_len = sl; hc->sc_cap = want_cap;
+        }
+        rrx_scan_opts o;
+        std::memset(&o, 0, sizeof(o));
+        int rc = rrx_scanner_scan(hc->sc, hc->d_text, len, base_offset, &o, hc->st);
+        rrx_scan_result r;
+        if (!rc) rc = rrx_scanner_result(hc->sc, &r, hc->st);
+        if (rc) return rc;
+        if (r.error_bits) return set_err(RRX_ERR_CUDA, "scan kernel reported error bits " + std::to_string(r.error_bits));
+        if (r.n_matches > r.capacity) { want_cap = r.n_matches + 1024; continue; }    // exact size known now: scan again
+        std::unique_ptr<rrx_matches> m(new rrx_matches);
+        m->count = r.n_matches;
+        m->owner = hc;
+        if (m->count) {
+            size_t best = hc->pool.size();
+            for (size_t i = 0; i < hc->pool.size(); i++)
+                if (hc->pool[i].pairs >= m->count && (best == hc->pool.size() || hc->pool[i].pairs < hc->pool[best].pairs)) best = i;
+            if (best != hc->pool.size()) {
+                m->pinned = hc->pool[best];
+                hc->pool.erase(hc->pool.begin() + (long)best);
+            } else {
+                const uint64_t pairs = m->count + m->count / 8 + 1024;
+                RRX_CUDA(cudaMallocHost(&m->pinned.p, pairs * 16));
+                m->pinned.pairs = pairs;
+            }
+            cudaError_t e = cudaMemcpyAsync(m->pinned.p, r.d_matches, m->count * 16, cudaMemcpyDeviceToHost, hc->st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(hc->st);
+            if (e != cudaSuccess) { hc->pool.push_back(m->pinned); return cuda_err(e, "cudaMemcpy D2H"); }
+        }
+        m->host_valid = true;
+        *out = m.release();
+        return RRX_OK;
+    }
+    return set_err(RRX_ERR_CUDA, "match buffer overflow after resize");
 }
 
 int rrx_accepts_host(const rrx_program* p, const uint8_t* text, uint64_t len, int* accepted) {
@@ -464,6 +552,10 @@ uint64_t rrx_matches_count(const rrx_matches* m) { return m ? m->count : 0; }
 const int64_t* rrx_matches_device_data(const rrx_matches* m) { return reinterpret_cast<const int64_t*>(m->d_pairs); }
 const int64_t* rrx_matches_data(rrx_matches* m) {
     if (!m) return nullptr;
+    if (m->owner) {
+        static const int64_t none[2] = {0, 0};
+        return m->pinned.p ? m->pinned.p : none;
+    }
     if (!m->host_valid) {
         m->host.resize(2 * m->count + 2);
         if (m->count) {
@@ -476,6 +568,11 @@ const int64_t* rrx_matches_data(rrx_matches* m) {
 }
 void rrx_matches_free(rrx_matches* m) {
     if (!m) return;
+    if (m->owner && m->pinned.p) {
+        std::lock_guard<std::mutex> lk(m->owner->mu);
+        if (m->owner->pool.size() < 4) m->owner->pool.push_back(m->pinned);
+        else cudaFreeHost(m->pinned.p);
+    }
     cudaFree(m->d_pairs);
     delete m;
 }

@@ -506,6 +506,128 @@ void put_bits(std::vector<uint32_t>& blob, uint32_t off, const Bits& b, uint32_t
 
 }  // namespace
 
+namespace {
+// ---- cut analysis for the candidate-driven row scan (rrx_tile.cuh phase_a_sparse) -----------------
+// For a byte value v let K_v = positions whose class is exactly {v}.  K_v is a CUT when no activation
+// chain (start at a first-position, follow pruned edges) reaches an accept position without
+// visiting K_v.  Then D = positions every chain to which passes through K_v ("dominated"; accept is
+// inside D), and the scan only has to track D-states, which are empty except shortly after an
+// occurrence of v.  Among the cuts the cheapest by a static estimate (typical frequency of v x
+// expected length of the dominated run + of the backward verification) is chosen.
+struct Cut {
+    bool ok = false;
+    uint32_t byte = 0;
+    Bits D;
+    struct Group { Bits k, pred; uint32_t flags; };
+    std::vector<Group> groups;
+};
+
+uint32_t byte_freq_score(uint32_t v) {
+    if (v == ' ') return 10;
+    if (v >= 'a' && v <= 'z') return 8;
+    if (v >= '0' && v <= '9') return 4;
+    if (v >= 'A' && v <= 'Z') return 3;
+    if (v == '.' || v == ',' || v == '-' || v == '_' || v == '/' || v == ':' || v == '=' || v == '"' || v == '\'') return 3;
+    if (v == '\n' || v == '\t') return 2;
+    return 1;
+}
+
+// longest path (in nodes) inside `nodes` starting anywhere in `from`, following `edges`; capped at
+// `cap`, which is also returned when a cycle is reachable
+uint32_t longest_run(const std::vector<Bits>& edges, const Bits& nodes, const Bits& from, uint32_t cap) {
+    const uint32_t P = (uint32_t)edges.size();
+    std::vector<int> colour(P, 0);
+    std::vector<uint32_t> depth(P, 0);
+    uint32_t best = 0;
+    bool cyclic = false;
+    for (uint32_t root : from.list()) {
+        if (!nodes.has(root) || colour[root]) continue;
+        std::vector<std::pair<uint32_t, size_t>> st;
+        st.push_back({root, 0});
+        colour[root] = 1;
+        while (!st.empty() && !cyclic) {
+            const uint32_t k = st.back().first;
+            std::vector<uint32_t> succ;
+            for (uint32_t t : edges[k].list()) if (nodes.has(t)) succ.push_back(t);
+            if (st.back().second < succ.size()) {
+                const uint32_t t = succ[st.back().second++];
+                if (colour[t] == 1) cyclic = true;
+                else if (colour[t] == 0) { colour[t] = 1; st.push_back({t, 0}); }
+            } else {
+                uint32_t d = 1;
+                for (uint32_t t : succ) d = std::max(d, depth[t] + 1);
+                depth[k] = d;
+                colour[k] = 2;
+                st.pop_back();
+            }
+        }
+        if (cyclic) return cap;
+        best = std::max(best, depth[root]);
+    }
+    return std::min(best, cap);
+}
+
+Cut find_cut(const std::vector<Pos>& pos, const std::vector<Bits>& fol, const std::vector<Bits>& rfol,
+             const Bits& first, const Bits& accept) {
+    const uint32_t P = (uint32_t)pos.size();
+    Cut best;
+    uint64_t best_cost = ~0ull;
+    Bits all(P);
+    for (uint32_t k = 0; k < P; k++) all.add(k);
+    for (uint32_t v = 1; v < 128; v++) {
+        Bits K(P);
+        for (uint32_t k = 0; k < P; k++) {
+            const uint64_t lo = v < 64 ? 1ull << v : 0ull, hi = v < 64 ? 0ull : 1ull << (v - 64);
+            if (pos[k].cls[0] == lo && pos[k].cls[1] == hi) K.add(k);
+        }
+        if (!K.any()) continue;
+        // positions reachable from first while avoiding K
+        Bits nd(P);
+        std::vector<uint32_t> work;
+        for (uint32_t k : first.list()) if (!K.has(k)) { nd.add(k); work.push_back(k); }
+        while (!work.empty()) {
+            const uint32_t k = work.back();
+            work.pop_back();
+            for (uint32_t t : fol[k].list()) if (!K.has(t) && !nd.has(t)) { nd.add(t); work.push_back(t); }
+        }
+        if (nd.intersects(accept)) continue;                 // some match avoids v: not a cut
+        Cut c;
+        c.ok = true;
+        c.byte = v;
+        c.D = Bits(P);
+        for (uint32_t k = 0; k < P; k++) if (!nd.has(k)) c.D.add(k);
+        // the K positions that can be entered at all: first-positions, or with a predecessor
+        bool too_many = false;
+        for (uint32_t k : K.list()) {
+            const bool is_first = first.has(k);
+            if (!is_first && !rfol[k].any()) continue;       // unreachable
+            Bits pred = is_first ? Bits(P) : rfol[k];
+            bool placed = false;
+            for (auto& g : c.groups)
+                if (g.flags == (is_first ? 1u : 0u) && g.pred.equals(pred)) { g.k.add(k); placed = true; break; }
+            if (!placed) {
+                if (c.groups.size() == RRX_MAX_GROUPS) { too_many = true; break; }
+                Cut::Group g;
+                g.k = Bits(P); g.k.add(k); g.pred = pred; g.flags = is_first ? 1u : 0u;
+                c.groups.push_back(g);
+            }
+        }
+        if (too_many || c.groups.empty()) continue;
+        // static cost estimate
+        const uint32_t run = longest_run(fol, c.D, K, 16);
+        uint32_t ver = 0;
+        for (auto& g : c.groups) if (!(g.flags & 1u)) ver = std::max(ver, longest_run(rfol, all, g.pred, 16));
+        // ties: the smaller dominated set (more of the automaton is skipped between candidates)
+        const uint64_t cost = (uint64_t)byte_freq_score(v) * (run + ver) * 1024 + c.D.count();
+        if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    // not worth it when candidates are expected every few bytes and each starts a long run
+    if (best.ok && best_cost >= 8ull * 24ull * 1024ull) best.ok = false;
+    return best;
+}
+
+}  // namespace
+
 Program build_program(const Automaton& a, const std::string& pattern, bool reduce) {
     std::vector<Pos> pos(a.P);
     for (uint32_t k = 0; k < a.P; k++) {
@@ -576,6 +698,11 @@ Program build_program(const Automaton& a, const std::string& pattern, bool reduc
     h.off_first = take(NW); h.off_accept = take(NW); h.off_all = take(NW);
     h.off_terms = take(RRX_MAX_TERMS * (1 + NW)); h.off_bicl = take(RRX_MAX_BICL * 2 * NW); h.off_rowsrc = take(NW);
     h.off_rterms = take(RRX_MAX_TERMS * (1 + NW)); h.off_rbicl = take(RRX_MAX_BICL * 2 * NW); h.off_rrowsrc = take(NW);
+    const Cut cut = find_cut(pos, fol, rfol, first, accept);
+    h.off_sparse = take(NW + RRX_MAX_GROUPS * (2 * NW + 1));
+    h.sparse_ok = cut.ok ? 1u : 0u;
+    h.cand_byte = cut.byte;
+    h.n_groups = cut.ok ? (uint32_t)cut.groups.size() : 0u;
     h.off_B = take(256 * NW);
     h.off_follow = take(P * NW); h.off_rfollow = take(P * NW);
     h.off_rows = take(P * NW); h.off_rrows = take(P * NW);
@@ -589,6 +716,15 @@ Program build_program(const Automaton& a, const std::string& pattern, bool reduc
     put_bits(pr.blob, h.off_first, first, NW);
     put_bits(pr.blob, h.off_accept, accept, NW);
     put_bits(pr.blob, h.off_all, all, NW);
+    if (cut.ok) {
+        put_bits(pr.blob, h.off_sparse, cut.D, NW);
+        for (size_t g = 0; g < cut.groups.size(); g++) {
+            const uint32_t o = h.off_sparse + NW + (uint32_t)g * (2 * NW + 1);
+            put_bits(pr.blob, o, cut.groups[g].k, NW);
+            put_bits(pr.blob, o + NW, cut.groups[g].pred, NW);
+            pr.blob[o + 2 * NW] = cut.groups[g].flags;
+        }
+    }
     auto put_decomp = [&](const Decomp& d, uint32_t o_terms, uint32_t o_bicl, uint32_t o_rowsrc, uint32_t o_rows) {
         for (size_t i = 0; i < d.terms.size(); i++) {
             uint32_t o = o_terms + (uint32_t)i * (1 + NW);

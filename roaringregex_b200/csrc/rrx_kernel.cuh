@@ -24,7 +24,7 @@ template <int NW, int WARPS_> struct KCfg {
     static constexpr uint32_t BT_BYTES = (NW == 1 ? 256u * 128u : 256u * (uint32_t)NW * 4u);
     static constexpr size_t REGION = (TileState<NW>::bytes() + 15) & ~(size_t)15;
     // small program part: header + 3 sets + 2 decompositions
-    static constexpr size_t SMALL = sizeof(ProgHeader) + 4u * (3 * NW + 2 * (RRX_MAX_TERMS * (1 + NW) + RRX_MAX_BICL * 2 * NW + NW));
+    static constexpr size_t SMALL = sizeof(ProgHeader) + 4u * (3 * NW + 2 * (RRX_MAX_TERMS * (1 + NW) + RRX_MAX_BICL * 2 * NW + NW) + NW + RRX_MAX_GROUPS * (2 * NW + 1));
     static constexpr size_t SMEM = BT_BYTES + (size_t)WARPS * REGION + SMALL + 64;
 };
 
@@ -229,6 +229,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
     // warp (whichever finishes first) will pick up about one round from now — one 128-byte line per
     // lane, so the staging loads of the next round hit L2 instead of queueing on HBM.
     const uint32_t warps_in_flight = gridDim.x * (uint32_t)K::WARPS;
+    int dense_left = 0;
     for (;;) {
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(sp.ticket, 1u);
@@ -265,9 +266,25 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         if (lane == 0) ts.misc[TS::M_RQCNT] = 0;
         __syncwarp();
         RRX_T(1)
-        phase_a<NW>(sp, pv, fw, ts, lane);
-        __syncwarp();
-        phase_a2<NW>(pv, fw, ts, lane);
+        // Candidate-driven row scan where the automaton has a cut; if any row of the tile needs the
+        // dense scan the whole tile takes it (the lanes run in lock-step anyway), and the next few
+        // tiles of this warp do not try again.
+        bool dense = true;
+        if (sp.sparse) {
+            if (dense_left == 0) {
+                const bool ok = phase_a_sparse<NW>(sp, pv, fw, ts, lane);
+                dense = __any_sync(FULL, !ok) != 0;
+                if (dense) dense_left = 4;
+            } else {
+                dense_left--;
+            }
+        }
+        if (dense) {
+            __syncwarp();
+            phase_a<NW>(sp, pv, fw, ts, lane);
+            __syncwarp();
+            phase_a2<NW>(pv, fw, ts, lane);
+        }
         const uint32_t my_kind = ts.sum_kind[lane];
         const bool any_open = __any_sync(FULL, my_kind == K_RANK1 || my_kind == K_HARD) != 0;
         __syncwarp();

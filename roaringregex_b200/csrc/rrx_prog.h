@@ -34,7 +34,15 @@ struct ProgHeader {
     uint32_t static_depth;      // longest path (edges) in the pruned follow graph; 0xffffffff if cyclic
     uint32_t n_flat;            // atoms + START before reduction
     uint32_t off_rfull;         // P*NW: transpose of the UNPRUNED follow relation (whole-string acceptance)
-    uint32_t reserved[1];
+    // Candidate-driven ("sparse") row scan, see rrx_tile.cuh phase_a_sparse.  A CUT is a set K of
+    // positions that every activation chain first -> accept passes through and whose class is the
+    // single byte `cand_byte`: a match can only end after a run of dominated states that starts at an
+    // occurrence of that byte.  off_sparse: D[NW] (positions dominated by K), then n_groups records
+    // {kmask[NW], pred[NW], flags} — the K positions grouped by predecessor set; flags bit 0: the
+    // group's positions are first-positions (injected without looking back).
+    uint32_t sparse_ok, cand_byte, n_groups, off_sparse;
+    uint32_t reserved[3];
 };
+constexpr uint32_t RRX_MAX_GROUPS = 4;
 
 }  // namespace rrx

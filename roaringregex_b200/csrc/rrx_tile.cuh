@@ -318,6 +318,8 @@ struct ScanParams {
     uint32_t static_closed;     // 1: every row is closed by construction (acyclic E', depth < ROW_BYTES)
     uint32_t stagger_ns;        // warps of a CTA start (warp%8)*stagger_ns apart, so that they are not all in the same phase
     uint32_t backoff_ns;
+    uint32_t sparse;            // 1: try the candidate-driven row scan first (program has a cut; see phase_a_sparse)
+    uint32_t pad_;
     unsigned long long* phase_cycles;   // optional [8]: per-phase warp cycles (RRX_PHASE_TIMING builds)
     uint32_t* ticket;
     // Two-level decoupled look-back (tiles, blocks of 32 tiles), see rrx_scan.cu.
@@ -542,6 +544,157 @@ RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
     ts.sum_kind[t] = kind;
 #pragma unroll
     for (int q = 0; q < 4; q++) ts.hits[q * ROWS + t] = hit[q];
+}
+
+// ===== phase A, candidate-driven ("sparse") variant =================================================
+// Same outputs as phase_a + phase_a2 for a CLOSED full row — hits[], sum_b (exit of the row scanned
+// from the empty set with re-injection), sum_kind = K_CLOSED — computed without stepping the
+// automaton over every byte.  Needs a cut (rrx_prog.h: cand_byte, D, groups):
+//   (1) SWAR pass over the row's 32 words: bit mask of the positions holding cand_byte;
+//   (2) only the dominated states H = S & D are tracked.  H is empty except after a candidate byte:
+//       there a cut position k is injected iff it is a first-position or some predecessor of k was
+//       active before the byte, which a backward walk over the reversed automaton decides (exactly the
+//       lazy start scan of phase C, bounded by the row start since phase A assumes an empty entry).
+//       While H is empty the lane jumps straight to its next candidate.  accept is inside D, so
+//       H & accept gives the match ends exactly.
+//   (3) the exit set: walk back from the row end with the set of positions that can still lie on a
+//       path reaching the row end; where it dies no earlier byte can influence the exit, and a dense
+//       forward scan of that suffix gives sum_b.  If it survives to the row start the row is open.
+// Returns false when the row has to go through the dense scan (open or partial row, too many
+// candidates, step budget exhausted); the caller then runs phase_a/phase_a2 for the whole tile.
+constexpr int SPARSE_MAX_CAND = 16;
+constexpr int SPARSE_BUDGET = 96;
+
+template <int NW, class F>
+RRX_DEV bool phase_a_sparse(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t) {
+    constexpr int ROWS = TILE_ROWS;
+    const ProgHeader& h = pv.h();
+    if (row_nbytes(sp, ts.row0, t) != ROW_BYTES) return false;
+    const uint32_t* D = pv.sm + h.off_sparse;
+    const uint32_t* grp = D + NW;
+    const uint32_t ngr = h.n_groups, cand = h.cand_byte;
+    const uint8_t* rp = ts.text + t * ROW_PITCH;
+
+    // (1) candidate mask: bit p of cm[q] <=> byte 32q+p == cand
+    uint32_t cm[4];
+    {
+        const uint32_t C4 = cand * 0x01010101u;
+        const uint32_t* rw = reinterpret_cast<const uint32_t*>(rp);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int j = 7; j >= 0; j--) {
+                const uint32_t x = rw[q * 8 + j] ^ C4;
+                const uint32_t y = (x | 0x80808080u) - 0x01010101u;     // no borrow between bytes
+                const uint32_t f = ~(y | x) & 0x80808080u;              // 0x80 where the byte equals cand
+                acc = fshl(f * 0x00204081u, acc, 4);                    // the 4 flags land in the top nibble
+            }
+            cm[q] = acc;
+        }
+    }
+    int ncand = popc32(cm[0]) + popc32(cm[1]) + popc32(cm[2]) + popc32(cm[3]);
+    if (ncand > SPARSE_MAX_CAND) return false;
+
+    // (2) runs of dominated states
+    uint32_t hit[4] = {0, 0, 0, 0};
+    uint32_t H[NW], Bc[NW], f[NW], nx[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) H[w] = 0;
+    int budget = SPARSE_BUDGET, p = 0;
+    bool bail = false;
+    for (;;) {
+        if (!any_w<NW>(H)) {
+            if (ncand == 0) break;
+            int w = p >> 5;
+            uint32_t m = (w == 0 ? cm[0] : w == 1 ? cm[1] : w == 2 ? cm[2] : cm[3]) & (0xffffffffu << (p & 31));
+            while (!m) { w++; m = w == 1 ? cm[1] : w == 2 ? cm[2] : cm[3]; }
+            p = w * 32 + ctz32(m);
+        }
+        const uint32_t c = rp[p];
+        load_B<NW>(pv, c, Bc);
+        fw.follow(pv, H, f);
+#pragma unroll
+        for (int w = 0; w < NW; w++) nx[w] = f[w] & D[w];
+        if (c == cand) {
+            ncand--;
+            for (uint32_t g = 0; g < ngr && !bail; g++) {
+                const uint32_t* gk = grp + g * (2 * NW + 1);
+                uint32_t need = 0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) need |= gk[w] & ~f[w];
+                if (!need) continue;                       // already entered from H
+                bool inj = (gk[2 * NW] & 1u) != 0;
+                if (!inj) {
+                    uint32_t R[NW], Bq[NW], x[NW];
+#pragma unroll
+                    for (int w = 0; w < NW; w++) R[w] = gk[NW + w];
+                    for (int q = p - 1; q >= 0; q--) {
+                        load_B<NW>(pv, rp[q], Bq);
+                        uint32_t m = 0;
+#pragma unroll
+                        for (int w = 0; w < NW; w++) { x[w] = R[w] & Bq[w]; m |= x[w] & fw.first(pv, w); }
+                        if (m) { inj = true; break; }
+                        fw.rfollow(pv, x, R);
+                        if (!any_w<NW>(R)) break;
+                        if (--budget < 0) { bail = true; break; }
+                    }
+                }
+                if (inj) {
+#pragma unroll
+                    for (int w = 0; w < NW; w++) nx[w] |= gk[w];
+                }
+            }
+            if (bail) break;
+        }
+        uint32_t a = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            H[w] = nx[w] & Bc[w];
+            a |= H[w] & fw.accept(pv, w);
+        }
+        if (a) {
+            const uint32_t bit = 1u << (p & 31);
+            const int hw = p >> 5;
+            hit[0] |= hw == 0 ? bit : 0u; hit[1] |= hw == 1 ? bit : 0u;
+            hit[2] |= hw == 2 ? bit : 0u; hit[3] |= hw == 3 ? bit : 0u;
+        }
+        if (++p >= ROW_BYTES) break;
+        if (--budget < 0) { bail = true; break; }
+    }
+    if (bail) return false;
+
+    // (3) exit set
+    uint32_t S[NW];
+    {
+        uint32_t A[NW], x[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) A[w] = fw.all(pv, w);
+        int q = ROW_BYTES - 1;
+        for (;;) {
+            load_B<NW>(pv, rp[q], Bc);
+#pragma unroll
+            for (int w = 0; w < NW; w++) x[w] = A[w] & Bc[w];
+            if (!any_w<NW>(x)) break;          // nothing that consumes byte q reaches the row end
+            if (q == 0) return false;          // some path spans the whole row: open
+            fw.rfollow(pv, x, A);
+            q--;
+        }
+#pragma unroll
+        for (int w = 0; w < NW; w++) S[w] = 0;
+        for (int i = q + 1; i < ROW_BYTES; i++) {
+            load_B<NW>(pv, rp[i], Bc);
+            fw.follow(pv, S, f);
+#pragma unroll
+            for (int w = 0; w < NW; w++) S[w] = (f[w] | fw.first(pv, w)) & Bc[w];
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < NW; w++) ts.sum_b[w * ROWS + t] = S[w];
+    ts.sum_kind[t] = K_CLOSED;
+#pragma unroll
+    for (int q = 0; q < 4; q++) ts.hits[q * ROWS + t] = hit[q];
+    return true;
 }
 
 // ===== phase A2: the warp replays the queued 4-byte words, one per lane ==============================

@@ -19,6 +19,11 @@ using namespace rrx;
 
 namespace {
 
+// 0: dense row scans only; 1: candidate-driven row scan with dense fallback, as the kernel does;
+// 2: run both on every tile and report (err bit 0x80) any row where they disagree
+int g_sparse_mode = 1;
+unsigned long long g_sparse_rows = 0, g_dense_rows = 0;
+
 template <int NW, int NT, int NB>
 int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t len, int64_t base,
         const uint32_t* entry, int64_t* out, uint64_t cap, uint64_t* counts, uint32_t* err, uint32_t* shard_comp,
@@ -46,6 +51,7 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
     sp.prog = prog.blob.data();
     sp.num_tiles = num_tiles;
     sp.static_closed = (h.static_depth != 0xffffffffu && h.static_depth + 1 <= (uint32_t)ROW_BYTES) ? 1u : 0u;
+    sp.sparse = h.sparse_ok && g_sparse_mode ? 1u : 0u;
     sp.ticket = &ticket;
     sp.out = reinterpret_cast<long long*>(out);
     sp.out_cap = cap;
@@ -79,19 +85,49 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
         }
         bool any_open = false;
         ts.misc[TS::M_RQCNT] = 0;
-        for (int t = 0; t < ROWS; t++) {
-            ProgView pv = view(t);
-            Prog<NW, NT, NB> fw;
-            fw.init(pv);
-            phase_a<NW>(sp, pv, fw, ts, t);
-            any_open = any_open || ts.sum_kind[t] == K_RANK1 || ts.sum_kind[t] == K_HARD;
+        bool dense = true;
+        bool sp_ok[ROWS];
+        uint32_t sp_hits[ROWS][4], sp_b[ROWS][NW];
+        if (h.sparse_ok && g_sparse_mode) {
+            dense = false;
+            for (int t = 0; t < ROWS; t++) {
+                ProgView pv = view(t);
+                Prog<NW, NT, NB> fw;
+                fw.init(pv);
+                sp_ok[t] = phase_a_sparse<NW>(sp, pv, fw, ts, t);
+                if (!sp_ok[t]) dense = true;
+                else {
+                    if (ts.sum_kind[t] != K_CLOSED) *err |= 0x80u;
+                    for (int q = 0; q < 4; q++) sp_hits[t][q] = ts.hits[q * ROWS + t];
+                    for (int w = 0; w < NW; w++) sp_b[t][w] = ts.sum_b[w * ROWS + t];
+                }
+            }
+            if (g_sparse_mode == 2) dense = true;
+            (dense ? g_dense_rows : g_sparse_rows) += ROWS;
         }
-        for (int t = 0; t < ROWS; t++) {
-            ProgView pv = view(t);
-            Prog<NW, NT, NB> fw;
-            fw.init(pv);
-            phase_a2<NW>(pv, fw, ts, t);
+        if (dense) {
+            for (int t = 0; t < ROWS; t++) {
+                ProgView pv = view(t);
+                Prog<NW, NT, NB> fw;
+                fw.init(pv);
+                phase_a<NW>(sp, pv, fw, ts, t);
+            }
+            for (int t = 0; t < ROWS; t++) {
+                ProgView pv = view(t);
+                Prog<NW, NT, NB> fw;
+                fw.init(pv);
+                phase_a2<NW>(pv, fw, ts, t);
+            }
+            if (h.sparse_ok && g_sparse_mode == 2) {
+                for (int t = 0; t < ROWS; t++) {
+                    if (!sp_ok[t]) continue;
+                    if (ts.sum_kind[t] != K_CLOSED) *err |= 0x80u;
+                    for (int q = 0; q < 4; q++) if (sp_hits[t][q] != ts.hits[q * ROWS + t]) *err |= 0x80u;
+                    for (int w = 0; w < NW; w++) if (sp_b[t][w] != ts.sum_b[w * ROWS + t]) *err |= 0x80u;
+                }
+            }
         }
+        for (int t = 0; t < ROWS; t++) any_open = any_open || ts.sum_kind[t] == K_RANK1 || ts.sum_kind[t] == K_HARD;
         {
             ProgView pv = view(0);
             Prog<NW, NT, NB> fw;
@@ -163,7 +199,7 @@ int emu_scan(const char* pattern, int reduce, int fast, const uint8_t* text_with
         return -1;
     }
     const ProgHeader& h = prog.hdr();
-    if (info) { info[0] = h.NW; info[1] = h.P; info[2] = h.n_terms; info[3] = h.n_bicl; info[4] = h.use_rows; info[5] = h.static_depth; }
+    if (info) { info[0] = h.NW; info[1] = h.P; info[2] = h.n_terms; info[3] = h.n_bicl; info[4] = h.use_rows; info[5] = h.static_depth; info[6] = h.sparse_ok; info[7] = h.cand_byte; }
     const uint8_t* text = text_with_ctx + left_ctx;
     PendingStart* pend = reinterpret_cast<PendingStart*>(pending);
 #define GO(NW_, NT_, NB_) return run<NW_, NT_, NB_>(prog, text, left_ctx, len, base, entry, out, cap, counts, err, shard_comp, pend, pending_cap)
@@ -195,5 +231,11 @@ int emu_scan(const char* pattern, int reduce, int fast, const uint8_t* text_with
 }
 
 uint32_t emu_pending_size(void) { return (uint32_t)sizeof(PendingStart); }
+void emu_set_sparse(int mode) { g_sparse_mode = mode; }
+// rows handled by the candidate-driven scan / by the dense scan since the last call (sparse-capable programs only)
+void emu_sparse_stats(unsigned long long* out, int reset) {
+    out[0] = g_sparse_rows; out[1] = g_dense_rows;
+    if (reset) g_sparse_rows = g_dense_rows = 0;
+}
 
 }  // extern "C"

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "emu", "_build", "librrx_emu.so")
 SRCS = [os.path.join(HERE, "emu", "rrx_emu.cc"), os.path.join(ROOT, "roaringregex_b200", "csrc", "rrx_compile.cc")]
-DEPS = SRCS + [os.path.join(ROOT, "roaringregex_b200", "csrc", f) for f in ("rrx_tile.cuh", "rrx_compile.h")]
+DEPS = SRCS + [os.path.join(ROOT, "roaringregex_b200", "csrc", f) for f in ("rrx_tile.cuh", "rrx_compile.h", "rrx_prog.h")]
 
 
 def build():
@@ -31,7 +31,20 @@ def _lib():
                              C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_void_p, C.c_uint32]
     lib.emu_pending_size.restype = C.c_uint32
+    lib.emu_set_sparse.argtypes = [C.c_int]
+    lib.emu_sparse_stats.argtypes = [C.c_void_p, C.c_int]
     return lib
+
+
+def set_sparse(mode: int):
+    """0 dense only, 1 candidate-driven with dense fallback (default, = the kernel), 2 run both and compare."""
+    _lib().emu_set_sparse(mode)
+
+
+def sparse_stats(reset=True):
+    out = np.zeros(2, dtype=np.uint64)
+    _lib().emu_sparse_stats(out.ctypes.data, int(reset))
+    return int(out[0]), int(out[1])
 
 
 def scan(pattern: str, text, reduce=True, fast=True, left_ctx=0, base=0, entry=None, cap=None):
@@ -60,4 +73,4 @@ def scan(pattern: str, text, reduce=True, fast=True, left_ctx=0, base=0, entry=N
     m = int(counts[0])
     return dict(matches=out[:min(m, cap)].copy(), n=m, pending=int(counts[1]), err=int(err[0]), shard_comp=comp,
                 info=dict(NW=int(info[0]), P=int(info[1]), n_terms=int(info[2]), n_bicl=int(info[3]),
-                          use_rows=int(info[4]), static_depth=int(info[5])), pend_raw=pend, pend_size=psz)
+                          use_rows=int(info[4]), static_depth=int(info[5]), sparse_ok=int(info[6]), cand_byte=int(info[7])), pend_raw=pend, pend_size=psz)

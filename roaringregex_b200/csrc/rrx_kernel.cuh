@@ -97,9 +97,13 @@ template <int NW> __device__ __forceinline__ void wait_comp(const uint32_t* pay,
 
 // state composites (ordered): all lanes pass the same `agg`; `acc` = composite of everything before
 // the tile, relative to the shard entry (same value in all lanes).
+// lookback_publish: make the tile's aggregate visible (and fold the block aggregate if this is the
+// last tile of its block to arrive).  lookback_wait: composite of everything before the tile.
+// A tile whose aggregate is known early (all rows closed: the exit of its last row) publishes
+// before it looks for matches, so that its successors rarely wait.
 template <int NW>
-__device__ __forceinline__ void lookback_state(const ScanParams& sp, uint32_t tile, const Comp<NW>& agg, int lane, Comp<NW>& acc) {
-    const uint32_t b = tile >> 5, k = tile & 31;
+__device__ __forceinline__ void lookback_publish(const ScanParams& sp, uint32_t tile, const Comp<NW>& agg, int lane) {
+    const uint32_t b = tile >> 5;
     const uint32_t rest = sp.num_tiles - (b << 5);
     const uint32_t nblk = rest < 32u ? rest : 32u;
     Comp<NW> mine, x, nxt;
@@ -126,6 +130,11 @@ __device__ __forceinline__ void lookback_state(const ScanParams& sp, uint32_t ti
         if (has_wait) fold.kind = K_WAIT;
         if (lane == 0) publish_comp<NW>(sp.st_a1, sp.f_a1, b, fold);
     }
+}
+template <int NW>
+__device__ __forceinline__ void lookback_wait(const ScanParams& sp, uint32_t tile, int lane, Comp<NW>& acc) {
+    const uint32_t b = tile >> 5, k = tile & 31;
+    Comp<NW> mine, x, nxt;
     // (0) shortcut: if the tile right before this one is closed, nothing earlier matters
     comp_ident(acc);
     if (tile == 0) return;
@@ -225,17 +234,25 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         while (globaltimer_ns() - t0 < wait) __nanosleep(200);
     }
 
-    // While a warp works on tile i it asks L2 to fetch tile i + (warps in flight) — the tile some
-    // warp (whichever finishes first) will pick up about one round from now — one 128-byte line per
-    // lane, so the staging loads of the next round hit L2 instead of queueing on HBM.
+    // Tickets.  A tile that publishes its aggregate early (all rows closed) takes the ticket of the
+    // warp's NEXT tile right then: the atomic's latency hides behind the match search, and the next
+    // tile's 32 lines are prefetched into L2 as soon as the ticket arrives.  Taking tickets any
+    // earlier makes successors of a not-yet-started tile wait for its holder (head-of-line blocking
+    // whenever tile times vary), so all other tiles take theirs when they are done.
     const uint32_t warps_in_flight = gridDim.x * (uint32_t)K::WARPS;
     int dense_left = 0;
+    uint32_t tile = 0;
+    if (lane == 0) tile = atomicAdd(sp.ticket, 1u);
+    tile = __shfl_sync(FULL, tile, 0);
     for (;;) {
-        uint32_t tile = 0;
-        if (lane == 0) tile = atomicAdd(sp.ticket, 1u);
-        tile = __shfl_sync(FULL, tile, 0);
         if (tile >= sp.num_tiles) break;
-        {
+        uint32_t next_raw = 0;
+        bool have_next = false;
+        if (sp.ticket_ahead == 2) {
+            if (lane == 0) next_raw = atomicAdd(sp.ticket, 1u);
+            have_next = true;
+        } else {
+            // guess which tile some warp will pick up about one round from now, and ask L2 for it
             const int64_t g = (((int64_t)tile + warps_in_flight) * TILE_ROWS + lane) << ROW_SHIFT;
             if (g < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp.text + g));
         }
@@ -246,15 +263,21 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         {
             const int64_t g0 = ts.lo();
             uint4 v[8];
+            if (g0 + TILE_BYTES <= len) {                 // whole tile inside the text: no per-load checks
+                const uint4* src = reinterpret_cast<const uint4*>(sp.text + g0) + lane;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int64_t g = g0 + (int64_t)(k * 32 + lane) * 16;
-                if (g + 16 <= len) {
-                    v[k] = __ldcs(reinterpret_cast<const uint4*>(sp.text + g));
-                } else {
-                    uint32_t w[4] = {0, 0, 0, 0};
-                    for (int b = 0; b < 16 && g + b < len; b++) w[b >> 2] |= (uint32_t)sp.text[g + b] << (8 * (b & 3));
-                    v[k] = make_uint4(w[0], w[1], w[2], w[3]);
+                for (int k = 0; k < 8; k++) v[k] = __ldcs(src + k * 32);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int64_t g = g0 + (int64_t)(k * 32 + lane) * 16;
+                    if (g + 16 <= len) {
+                        v[k] = __ldcs(reinterpret_cast<const uint4*>(sp.text + g));
+                    } else {
+                        uint32_t w[4] = {0, 0, 0, 0};
+                        for (int b = 0; b < 16 && g + b < len; b++) w[b >> 2] |= (uint32_t)sp.text[g + b] << (8 * (b & 3));
+                        v[k] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
                 }
             }
 #pragma unroll
@@ -266,14 +289,30 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         if (lane == 0) ts.misc[TS::M_RQCNT] = 0;
         __syncwarp();
         RRX_T(1)
-        // Candidate-driven row scan where the automaton has a cut; if any row of the tile needs the
-        // dense scan the whole tile takes it (the lanes run in lock-step anyway), and the next few
-        // tiles of this warp do not try again.
-        bool dense = true;
+        // Candidate-driven row scan where the automaton has a cut.  Exit sets first: if every row is
+        // closed the tile aggregate is the last row's exit and is published at once.  If any row of the
+        // tile needs the dense scan the whole tile takes it (the lanes run in lock-step anyway), and
+        // the next few tiles of this warp do not try again.
+        bool dense = true, published = false;
+        Comp<NW> agg, acc, inc;
         if (sp.sparse) {
             if (dense_left == 0) {
-                const bool ok = phase_a_sparse<NW>(sp, pv, fw, ts, lane);
-                dense = __any_sync(FULL, !ok) != 0;
+                const bool closed = phase_a_exit<NW>(sp, pv, fw, ts, lane);
+                if (__all_sync(FULL, closed)) {
+                    __syncwarp();
+                    uint32_t bl[NW];
+#pragma unroll
+                    for (int w = 0; w < NW; w++) bl[w] = ts.sum_b[w * TILE_ROWS + (TILE_ROWS - 1)];
+                    comp_closed(agg, bl, 0);
+                    lookback_publish<NW>(sp, tile, agg, lane);
+                    published = true;
+                    if (sp.ticket_ahead == 1) {
+                        if (lane == 0) next_raw = atomicAdd(sp.ticket, 1u);
+                        have_next = true;
+                    }
+                    const bool ok = phase_a_cand<NW>(sp, pv, fw, ts, lane);
+                    dense = __any_sync(FULL, !ok) != 0;
+                }
                 if (dense) dense_left = 4;
             } else {
                 dense_left--;
@@ -285,15 +324,23 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             __syncwarp();
             phase_a2<NW>(pv, fw, ts, lane);
         }
+        uint32_t next_tile = 0;
+        if (have_next) {        // the next tile's ticket has arrived by now: ask L2 for its lines
+            next_tile = __shfl_sync(FULL, next_raw, 0);
+            const int64_t g = (((int64_t)next_tile) * TILE_ROWS + lane) << ROW_SHIFT;
+            if (g < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp.text + g));
+        }
         const uint32_t my_kind = ts.sum_kind[lane];
         const bool any_open = __any_sync(FULL, my_kind == K_RANK1 || my_kind == K_HARD) != 0;
         __syncwarp();
         SLocal<NW> L;
-        Comp<NW> agg, acc, inc;
         if (lane == 0) { phase_s1<NW>(sp, pv, fw, ts, any_open, L); agg = L.run; } else { comp_ident(agg); }
-        bcast_comp(agg, 0);
         RRX_T(2)
-        lookback_state<NW>(sp, tile, agg, lane, acc);
+        if (!published) {
+            bcast_comp(agg, 0);
+            lookback_publish<NW>(sp, tile, agg, lane);
+        }
+        lookback_wait<NW>(sp, tile, lane, acc);
         RRX_T(3)
         if (lane == 0) {
             phase_s2<NW>(sp, pv, fw, ts, L, acc, inc);
@@ -315,29 +362,39 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         const uint32_t total = __shfl_sync(FULL, inc_c, 31);
         const uint32_t offset = inc_c - c;
         RRX_T(5)
+        // reserve the tile's segment of the staging list; the hit list is built while the atomic is in flight
         unsigned long long base = 0;
-        if (lane == 0) {
-            if (total) base = atomicAdd(sp.total, (unsigned long long)total);
-            sp.tile_seg[tile] = base;
-            sp.tile_cnt[tile] = total;
-        }
-        base = __shfl_sync(FULL, base, 0);
+        if (lane == 0 && total) base = atomicAdd(sp.total, (unsigned long long)total);
         RRX_T(6)
         if (total) {
             uint32_t hit[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) hit[q] = ts.hits[q * TILE_ROWS + lane];
             __syncwarp();                 // every lane is done with the row summaries: reuse as hit list
-            if (total <= (uint32_t)TS::LIST_CAP) {
-                phase_c1_list<NW>(ts, lane, offset, hit);
-                __syncwarp();
+            const bool fits = total <= (uint32_t)TS::LIST_CAP;
+            if (fits) phase_c1_list<NW>(ts, lane, offset, hit);
+            __syncwarp();
+            if (lane == 0) {
+                sp.tile_seg[tile] = base;
+                sp.tile_cnt[tile] = total;
+            }
+            base = __shfl_sync(FULL, base, 0);
+            if (fits) {
                 phase_c2_balanced<NW>(sp, pv, fw, ts, lane, total, base);
             } else {
                 phase_c2_rows<NW>(sp, pv, fw, ts, lane, offset, hit, base);
             }
+        } else if (lane == 0) {
+            sp.tile_seg[tile] = 0;
+            sp.tile_cnt[tile] = 0;
         }
         __syncwarp();
         RRX_T(7)
+        if (!have_next) {
+            if (lane == 0) next_raw = atomicAdd(sp.ticket, 1u);
+            next_tile = __shfl_sync(FULL, next_raw, 0);
+        }
+        tile = next_tile;
     }
 }
 

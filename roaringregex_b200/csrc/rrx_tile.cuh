@@ -24,9 +24,12 @@
 #if defined(__CUDACC__) && !defined(RRX_HOST_EMU)
 #define RRX_DEV __device__ __forceinline__
 #define RRX_HD __host__ __device__ __forceinline__
+// warp-uniform loop control inside per-lane phase functions (all 32 lanes call them convergently)
+#define RRX_WARP_ANY(x) (__any_sync(0xffffffffu, (x)) != 0)
 #else
 #define RRX_DEV inline
 #define RRX_HD inline
+#define RRX_WARP_ANY(x) (x)          // the emulator steps one lane at a time
 #endif
 
 #ifdef RRX_HOST_EMU
@@ -137,6 +140,27 @@ template <int K> RRX_DEV uint32_t lds_u8(const uint8_t* p) { return p[K]; }
 RRX_DEV uint32_t lds_tab1(const uint8_t* blane, uint32_t c) { return *reinterpret_cast<const uint32_t*>(blane + c * 128u); }
 RRX_DEV uint32_t or_and(uint32_t a, uint32_t b, uint32_t c) { return (a | b) & c; }
 #endif
+
+// Byte reads at a run-time offset from a shared-memory row: the 32-bit shared address is formed once
+// (a generic pointer would have it re-derived at every access).
+struct SmemBytes {
+#if defined(__CUDA_ARCH__) && !defined(RRX_HOST_EMU)
+    uint32_t base;
+    RRX_DEV explicit SmemBytes(const uint8_t* p) {
+        // the volatile move keeps the compiler from re-deriving the address inside loops
+        asm volatile("mov.u32 %0, %1;" : "=r"(base) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    }
+    RRX_DEV uint32_t at(uint32_t i) const {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + i));
+        return v;
+    }
+#else
+    const uint8_t* base;
+    explicit SmemBytes(const uint8_t* p) : base(p) {}
+    uint32_t at(uint32_t i) const { return base[i]; }
+#endif
+};
 
 template <int NW> RRX_DEV void load_B(const ProgView& pv, uint32_t c, uint32_t* out) {
     if (NW == 1) {
@@ -318,8 +342,8 @@ struct ScanParams {
     uint32_t static_closed;     // 1: every row is closed by construction (acyclic E', depth < ROW_BYTES)
     uint32_t stagger_ns;        // warps of a CTA start (warp%8)*stagger_ns apart, so that they are not all in the same phase
     uint32_t backoff_ns;
-    uint32_t sparse;            // 1: try the candidate-driven row scan first (program has a cut; see phase_a_sparse)
-    uint32_t pad_;
+    uint32_t sparse;            // 1: try the candidate-driven row scan first (program has a cut; see phase_a_exit/phase_a_cand)
+    uint32_t ticket_ahead;      // when the next tile's ticket is taken: 0 after the tile, 1 once the tile has published early, 2 at its start
     unsigned long long* phase_cycles;   // optional [8]: per-phase warp cycles (RRX_PHASE_TIMING builds)
     uint32_t* ticket;
     // Two-level decoupled look-back (tiles, blocks of 32 tiles), see rrx_scan.cu.
@@ -361,13 +385,14 @@ template <int NW> struct TileState {
     uint32_t* misc;       // see M_* below
     uint32_t* rq;         // replay queue: RQ_CAP items of {row<<5 | quad, state[NW]}
     uint16_t* list;       // hit list for the balanced start scans; aliases sum_b/sum_U/sum_P
+    uint16_t* kst;        // [2][32]    known lazy starts of up to two matches per row: (end-1)<<8 | start, row-relative
     uint64_t row0;        // first row of the tile
     static constexpr int M_RQCNT = 0, M_ENTRY = 8;
     static constexpr int MISC_WORDS = 8 + NW;
     static constexpr int RQ_CAP = NW <= 2 ? 64 : 16;
     static constexpr int LIST_CAP = 3 * NW * ROWS * 2;
     static constexpr size_t bytes() {
-        return (size_t)ROWS * ROW_PITCH + sizeof(uint32_t) * ((size_t)3 * NW * ROWS + 6 * ROWS + MISC_WORDS + RQ_CAP * (1 + NW));
+        return (size_t)ROWS * ROW_PITCH + sizeof(uint32_t) * ((size_t)3 * NW * ROWS + 7 * ROWS + MISC_WORDS + RQ_CAP * (1 + NW));
     }
     RRX_DEV void carve(uint8_t* base) {
         text = base;
@@ -379,6 +404,7 @@ template <int NW> struct TileState {
         hits = p; p += 4 * ROWS;
         cnt = p; p += ROWS;
         misc = p; p += MISC_WORDS;
+        kst = reinterpret_cast<uint16_t*>(p); p += ROWS;
         rq = p;
         list = reinterpret_cast<uint16_t*>(sum_b);
     }
@@ -544,12 +570,21 @@ RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
     ts.sum_kind[t] = kind;
 #pragma unroll
     for (int q = 0; q < 4; q++) ts.hits[q * ROWS + t] = hit[q];
+    ts.kst[2 * t] = ts.kst[2 * t + 1] = (uint16_t)0xffffu;      // no lazy start known in advance
 }
 
 // ===== phase A, candidate-driven ("sparse") variant =================================================
 // Same outputs as phase_a + phase_a2 for a CLOSED full row — hits[], sum_b (exit of the row scanned
 // from the empty set with re-injection), sum_kind = K_CLOSED — computed without stepping the
-// automaton over every byte.  Needs a cut (rrx_prog.h: cand_byte, D, groups):
+// automaton over every byte.  Needs a cut (rrx_prog.h: cand_byte, D, groups).  Two functions:
+//
+// phase_a_exit — the exit set.  Walk back from the row end with the set of positions that can still
+//   lie on a path reaching the row end; where it dies no earlier byte can influence the exit, and a
+//   dense forward scan of that suffix gives sum_b.  If it survives to the row start the row is open
+//   (returns false).  Runs FIRST, so that a tile whose rows are all closed can publish its
+//   aggregate (= the last row's exit) before it looks for matches: successors then find it ready.
+//
+// phase_a_cand — the match ends.
 //   (1) SWAR pass over the row's 32 words: bit mask of the positions holding cand_byte;
 //   (2) only the dominated states H = S & D are tracked.  H is empty except after a candidate byte:
 //       there a cut position k is injected iff it is a first-position or some predecessor of k was
@@ -557,19 +592,52 @@ RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
 //       lazy start scan of phase C, bounded by the row start since phase A assumes an empty entry).
 //       While H is empty the lane jumps straight to its next candidate.  accept is inside D, so
 //       H & accept gives the match ends exactly.
-//   (3) the exit set: walk back from the row end with the set of positions that can still lie on a
-//       path reaching the row end; where it dies no earlier byte can influence the exit, and a dense
-//       forward scan of that suffix gives sum_b.  If it survives to the row start the row is open.
-// Returns false when the row has to go through the dense scan (open or partial row, too many
-// candidates, step budget exhausted); the caller then runs phase_a/phase_a2 for the whole tile.
+//   Known starts: a run of dominated states fed by ONE injection (no other candidate byte inside
+//   the run) can only contain matches that cross the cut at that byte, so their lazy start is the
+//   start the backward walk found (or the candidate itself for a first-position).  Up to two
+//   (end, start) pairs per row are handed to phase C in kst[], which then skips its own backward scan.
+//   Returns false when the row has to go through the dense scan (too many candidates, step budget
+//   exhausted); the caller then runs phase_a/phase_a2 for the whole tile.
 constexpr int SPARSE_MAX_CAND = 16;
 constexpr int SPARSE_BUDGET = 96;
+constexpr uint32_t KST_NONE = 0xffffu;
 
 template <int NW, class F>
-RRX_DEV bool phase_a_sparse(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t) {
+RRX_DEV bool phase_a_exit(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t) {
+    constexpr int ROWS = TILE_ROWS;
+    if (row_nbytes(sp, ts.row0, t) != ROW_BYTES) return false;
+    const uint8_t* rp = ts.text + t * ROW_PITCH;
+    uint32_t S[NW], A[NW], x[NW], Bc[NW], f[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) A[w] = fw.all(pv, w);
+    int q = ROW_BYTES - 1;
+    for (;;) {
+        load_B<NW>(pv, rp[q], Bc);
+#pragma unroll
+        for (int w = 0; w < NW; w++) x[w] = A[w] & Bc[w];
+        if (!any_w<NW>(x)) break;          // nothing that consumes byte q reaches the row end
+        if (q == 0) return false;          // some path spans the whole row: open
+        fw.rfollow(pv, x, A);
+        q--;
+    }
+#pragma unroll
+    for (int w = 0; w < NW; w++) S[w] = 0;
+    for (int i = q + 1; i < ROW_BYTES; i++) {
+        load_B<NW>(pv, rp[i], Bc);
+        fw.follow(pv, S, f);
+#pragma unroll
+        for (int w = 0; w < NW; w++) S[w] = (f[w] | fw.first(pv, w)) & Bc[w];
+    }
+#pragma unroll
+    for (int w = 0; w < NW; w++) ts.sum_b[w * ROWS + t] = S[w];
+    ts.sum_kind[t] = K_CLOSED;
+    return true;
+}
+
+template <int NW, class F>
+RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t) {
     constexpr int ROWS = TILE_ROWS;
     const ProgHeader& h = pv.h();
-    if (row_nbytes(sp, ts.row0, t) != ROW_BYTES) return false;
     const uint32_t* D = pv.sm + h.off_sparse;
     const uint32_t* grp = D + NW;
     const uint32_t ngr = h.n_groups, cand = h.cand_byte;
@@ -594,30 +662,45 @@ RRX_DEV bool phase_a_sparse(const ScanParams& sp, const ProgView& pv, const F& f
         }
     }
     int ncand = popc32(cm[0]) + popc32(cm[1]) + popc32(cm[2]) + popc32(cm[3]);
-    if (ncand > SPARSE_MAX_CAND) return false;
 
-    // (2) runs of dominated states
-    uint32_t hit[4] = {0, 0, 0, 0};
-    uint32_t H[NW], Bc[NW], f[NW], nx[NW];
+    // (2) runs of dominated states.  Two nested warp-uniform loops (every lane iterates until all
+    // are done, finished lanes idle, so the lanes reconverge after every step):
+    //   outer, once per run: a lane without live states jumps to its next candidate; a lane standing
+    //          on a candidate byte decides the injection (backward verification) and takes that step;
+    //   inner, once per byte: the plain step of a live lane — follow, mask, accept test — a dozen
+    //          instructions; a lane that meets a candidate byte inside a run parks until the outer
+    //          loop has handled it.
+    // Match ends are pushed into a 4-entry byte queue (kq: end+1, ks: known start+1 or 0) and
+    // unpacked after the loops.
+    uint32_t H[NW], Bc[NW], f[NW], DA[NW];
 #pragma unroll
-    for (int w = 0; w < NW; w++) H[w] = 0;
-    int budget = SPARSE_BUDGET, p = 0;
-    bool bail = false;
-    for (;;) {
-        if (!any_w<NW>(H)) {
-            if (ncand == 0) break;
-            int w = p >> 5;
-            uint32_t m = (w == 0 ? cm[0] : w == 1 ? cm[1] : w == 2 ? cm[2] : cm[3]) & (0xffffffffu << (p & 31));
-            while (!m) { w++; m = w == 1 ? cm[1] : w == 2 ? cm[2] : cm[3]; }
-            p = w * 32 + ctz32(m);
-        }
-        const uint32_t c = rp[p];
-        load_B<NW>(pv, c, Bc);
-        fw.follow(pv, H, f);
+    for (int w = 0; w < NW; w++) { H[w] = 0; DA[w] = D[w]; }
+    int budget = SPARSE_BUDGET;         // backward verification steps this row may spend
+    uint32_t p = 0;
+    uint32_t rs1 = 0;                   // 1 + lazy start of every match of the current run, or 0: not known
+    uint32_t kq = 0, ks = 0, nacc = 0;
+    uint32_t bail = ncand > SPARSE_MAX_CAND ? 1u : 0u;
+    uint32_t live = 0;                  // OR of the words of H
+    uint32_t work = bail ? 0u : (uint32_t)ncand;     // non-zero while the lane has something left to do
+    const SmemBytes rb(rp);
+    while (RRX_WARP_ANY(work != 0)) {
+        // ---- outer: the lane is at a candidate byte (or jumps to its next one) ----
+        if (work != 0) {
+            const uint32_t fresh = live == 0 ? 1u : 0u;
+            if (fresh) {
+                uint32_t w = p >> 5;
+                uint32_t m = (w == 0 ? cm[0] : w == 1 ? cm[1] : w == 2 ? cm[2] : cm[3]) & (0xffffffffu << (p & 31));
+                while (!m) { w++; m = w == 1 ? cm[1] : w == 2 ? cm[2] : cm[3]; }
+                p = w * 32 + (uint32_t)ctz32(m);
+            }
+            // byte p is a candidate here: either the lane just jumped to it, or the inner loop parked on it
+            load_B<NW>(pv, cand, Bc);
+            fw.follow(pv, H, f);
+            uint32_t nx[NW];
 #pragma unroll
-        for (int w = 0; w < NW; w++) nx[w] = f[w] & D[w];
-        if (c == cand) {
+            for (int w = 0; w < NW; w++) nx[w] = f[w] & DA[w];
             ncand--;
+            int n_inj = 0, s_inj = -1;
             for (uint32_t g = 0; g < ngr && !bail; g++) {
                 const uint32_t* gk = grp + g * (2 * NW + 1);
                 uint32_t need = 0;
@@ -625,75 +708,97 @@ RRX_DEV bool phase_a_sparse(const ScanParams& sp, const ProgView& pv, const F& f
                 for (int w = 0; w < NW; w++) need |= gk[w] & ~f[w];
                 if (!need) continue;                       // already entered from H
                 bool inj = (gk[2 * NW] & 1u) != 0;
+                int s = (int)p;
                 if (!inj) {
                     uint32_t R[NW], Bq[NW], x[NW];
 #pragma unroll
                     for (int w = 0; w < NW; w++) R[w] = gk[NW + w];
-                    for (int q = p - 1; q >= 0; q--) {
-                        load_B<NW>(pv, rp[q], Bq);
+                    for (int q = (int)p - 1; q >= 0; q--) {
+                        load_B<NW>(pv, rb.at((uint32_t)q), Bq);
                         uint32_t m = 0;
 #pragma unroll
                         for (int w = 0; w < NW; w++) { x[w] = R[w] & Bq[w]; m |= x[w] & fw.first(pv, w); }
-                        if (m) { inj = true; break; }
+                        if (m) { inj = true; s = q; break; }
                         fw.rfollow(pv, x, R);
                         if (!any_w<NW>(R)) break;
-                        if (--budget < 0) { bail = true; break; }
+                        if (--budget < 0) { bail = 1u; break; }
                     }
                 }
                 if (inj) {
+                    n_inj++;
+                    s_inj = s;
 #pragma unroll
                     for (int w = 0; w < NW; w++) nx[w] |= gk[w];
                 }
             }
-            if (bail) break;
-        }
-        uint32_t a = 0;
+            rs1 = (fresh && n_inj == 1) ? (uint32_t)(s_inj + 1) : 0u;       // a candidate inside a run: ambiguous from here on
+            uint32_t a = 0;
+            live = 0;
 #pragma unroll
-        for (int w = 0; w < NW; w++) {
-            H[w] = nx[w] & Bc[w];
-            a |= H[w] & fw.accept(pv, w);
+            for (int w = 0; w < NW; w++) {
+                H[w] = nx[w] & Bc[w];
+                live |= H[w];
+                a |= H[w] & fw.accept(pv, w);
+            }
+            p++;
+            if (a) { kq = (kq << 8) | p; ks = (ks << 8) | rs1; nacc++; }
+            if (p == (uint32_t)ROW_BYTES || bail) { live = 0; ncand = 0; }
+            work = live | (uint32_t)ncand;
         }
-        if (a) {
-            const uint32_t bit = 1u << (p & 31);
-            const int hw = p >> 5;
+        // ---- inner: plain steps while the run lives and no candidate byte comes up ----
+        // (branch-free: every lane computes the step, lanes that are not in a run or stand on a
+        // candidate byte just do not commit it)
+        // Two steps per vote: the second one is harmless for lanes that have stopped.
+        uint32_t go = live;
+#define RRX_SPARSE_STEP()                                                                       \
+        {                                                                                           \
+            const uint32_t c = rb.at(p & (uint32_t)(ROW_BYTES - 1));                                \
+            load_B<NW>(pv, c, Bc);                                                                  \
+            fw.follow(pv, H, f);                                                                    \
+            const bool step = go != 0 && c != cand;     /* c == cand: parked for the outer loop */  \
+            uint32_t a = 0, lv = 0;                                                                 \
+            _Pragma("unroll") for (int w = 0; w < NW; w++) {                                        \
+                const uint32_t hn = f[w] & DA[w] & Bc[w];                                           \
+                lv |= hn;                                                                           \
+                a |= hn & fw.accept(pv, w);                                                         \
+                H[w] = step ? hn : H[w];                                                            \
+            }                                                                                       \
+            p += step ? 1u : 0u;                                                                    \
+            const bool take = step && a != 0;                                                       \
+            kq = take ? ((kq << 8) | p) : kq;                                                       \
+            ks = take ? ((ks << 8) | rs1) : ks;                                                     \
+            nacc += take ? 1u : 0u;                                                                 \
+            const bool end = step && p == (uint32_t)ROW_BYTES;                                      \
+            ncand = end ? 0 : ncand;                                                                \
+            live = step ? (end ? 0u : lv) : live;                                                   \
+            go = step ? live : 0u;                                                                  \
+        }
+        while (RRX_WARP_ANY(go != 0)) {
+            RRX_SPARSE_STEP()
+            RRX_SPARSE_STEP()
+        }
+#undef RRX_SPARSE_STEP
+        work = live | (uint32_t)ncand;
+    }
+    if (bail || nacc > 4) return false;
+    uint32_t hit[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t e1 = (kq >> (8 * i)) & 0xffu;
+        if (e1) {
+            const uint32_t q = e1 - 1, bit = 1u << (q & 31), hw = q >> 5;
             hit[0] |= hw == 0 ? bit : 0u; hit[1] |= hw == 1 ? bit : 0u;
             hit[2] |= hw == 2 ? bit : 0u; hit[3] |= hw == 3 ? bit : 0u;
         }
-        if (++p >= ROW_BYTES) break;
-        if (--budget < 0) { bail = true; break; }
     }
-    if (bail) return false;
-
-    // (3) exit set
-    uint32_t S[NW];
-    {
-        uint32_t A[NW], x[NW];
-#pragma unroll
-        for (int w = 0; w < NW; w++) A[w] = fw.all(pv, w);
-        int q = ROW_BYTES - 1;
-        for (;;) {
-            load_B<NW>(pv, rp[q], Bc);
-#pragma unroll
-            for (int w = 0; w < NW; w++) x[w] = A[w] & Bc[w];
-            if (!any_w<NW>(x)) break;          // nothing that consumes byte q reaches the row end
-            if (q == 0) return false;          // some path spans the whole row: open
-            fw.rfollow(pv, x, A);
-            q--;
-        }
-#pragma unroll
-        for (int w = 0; w < NW; w++) S[w] = 0;
-        for (int i = q + 1; i < ROW_BYTES; i++) {
-            load_B<NW>(pv, rp[i], Bc);
-            fw.follow(pv, S, f);
-#pragma unroll
-            for (int w = 0; w < NW; w++) S[w] = (f[w] | fw.first(pv, w)) & Bc[w];
-        }
-    }
-#pragma unroll
-    for (int w = 0; w < NW; w++) ts.sum_b[w * ROWS + t] = S[w];
-    ts.sum_kind[t] = K_CLOSED;
+    // the two most recent match ends with a known start
+    uint32_t k0 = KST_NONE, k1 = KST_NONE;
+    if ((ks & 0xffu) != 0) k0 = (((kq & 0xffu) - 1) << 8) | ((ks & 0xffu) - 1);
+    if (((ks >> 8) & 0xffu) != 0) k1 = ((((kq >> 8) & 0xffu) - 1) << 8) | (((ks >> 8) & 0xffu) - 1);
 #pragma unroll
     for (int q = 0; q < 4; q++) ts.hits[q * ROWS + t] = hit[q];
+    ts.kst[2 * t] = (uint16_t)k0;
+    ts.kst[2 * t + 1] = (uint16_t)k1;
     return true;
 }
 
@@ -988,6 +1093,24 @@ RRX_DEV void resolve_and_write(const ScanParams& sp, const ProgView& pv, const F
     }
 }
 
+// The match ending after tile-relative byte `rel`: if phase A already knows its lazy start, write it.
+template <int NW>
+RRX_DEV bool write_known(const ScanParams& sp, const TileState<NW>& ts, uint32_t rel, unsigned long long slot) {
+    const uint32_t row = rel >> ROW_SHIFT, p = rel & (ROW_BYTES - 1);
+    const uint32_t k0 = ts.kst[2 * row], k1 = ts.kst[2 * row + 1];
+    uint32_t s;
+    if ((k0 >> 8) == p) s = k0 & 0xffu;
+    else if ((k1 >> 8) == p) s = k1 & 0xffu;
+    else return false;
+    if (slot < sp.out_cap) {
+        long long* o = sp.out + 2 * slot;
+        const long long row_lo = sp.base + ts.lo() + ((long long)row << ROW_SHIFT);
+        o[0] = row_lo + s;
+        o[1] = row_lo + p + 1;
+    }
+    return true;
+}
+
 // C1 (per lane): append the row's match ends to the tile's hit list (tile-relative end-1).
 // cnt[t] must hold the row's exclusive offset.  Only when the tile total fits the list.
 template <int NW> RRX_DEV void phase_c1_list(TileState<NW>& ts, int t, uint32_t offset, const uint32_t* hit) {
@@ -1006,8 +1129,9 @@ template <int NW, class F>
 RRX_DEV void phase_c2_balanced(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW>& ts, int lane,
                                uint32_t total, unsigned long long base) {
     for (uint32_t i = (uint32_t)lane; i < total; i += TILE_ROWS) {
-        const int64_t e = ts.lo() + (int64_t)ts.list[i] + 1;
-        resolve_and_write<NW>(sp, pv, fw, ts, e, base + i);
+        const uint32_t rel = ts.list[i];
+        const int64_t e = ts.lo() + (int64_t)rel + 1;
+        if (!write_known<NW>(sp, ts, rel, base + i)) resolve_and_write<NW>(sp, pv, fw, ts, e, base + i);
     }
 }
 // C2 fallback (per lane): every row resolves its own matches (tiles with more hits than the list holds).
@@ -1021,7 +1145,8 @@ RRX_DEV void phase_c2_rows(const ScanParams& sp, const ProgView& pv, const F& fw
         while (v) {
             const int p = q * 32 + ctz32(v);
             v &= v - 1;
-            resolve_and_write<NW>(sp, pv, fw, ts, row_lo + p + 1, slot++);
+            if (!write_known<NW>(sp, ts, ((uint32_t)t << ROW_SHIFT) + (uint32_t)p, slot)) resolve_and_write<NW>(sp, pv, fw, ts, row_lo + p + 1, slot);
+            slot++;
         }
     }
 }

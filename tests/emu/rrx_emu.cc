@@ -88,19 +88,34 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
         bool dense = true;
         bool sp_ok[ROWS];
         uint32_t sp_hits[ROWS][4], sp_b[ROWS][NW];
+        uint16_t sp_kst[ROWS][2];
         if (h.sparse_ok && g_sparse_mode) {
-            dense = false;
+            // as the kernel: exit sets first; candidates only if every row of the tile is closed
+            bool all_closed = true;
             for (int t = 0; t < ROWS; t++) {
                 ProgView pv = view(t);
                 Prog<NW, NT, NB> fw;
                 fw.init(pv);
-                sp_ok[t] = phase_a_sparse<NW>(sp, pv, fw, ts, t);
-                if (!sp_ok[t]) dense = true;
-                else {
-                    if (ts.sum_kind[t] != K_CLOSED) *err |= 0x80u;
-                    for (int q = 0; q < 4; q++) sp_hits[t][q] = ts.hits[q * ROWS + t];
-                    for (int w = 0; w < NW; w++) sp_b[t][w] = ts.sum_b[w * ROWS + t];
+                sp_ok[t] = phase_a_exit<NW>(sp, pv, fw, ts, t);
+                all_closed = all_closed && sp_ok[t];
+            }
+            dense = !all_closed;
+            if (all_closed) {
+                for (int t = 0; t < ROWS; t++) {
+                    ProgView pv = view(t);
+                    Prog<NW, NT, NB> fw;
+                    fw.init(pv);
+                    sp_ok[t] = phase_a_cand<NW>(sp, pv, fw, ts, t);
+                    if (!sp_ok[t]) dense = true;
+                    else {
+                        if (ts.sum_kind[t] != K_CLOSED) *err |= 0x80u;
+                        for (int q = 0; q < 4; q++) sp_hits[t][q] = ts.hits[q * ROWS + t];
+                        for (int w = 0; w < NW; w++) sp_b[t][w] = ts.sum_b[w * ROWS + t];
+                        sp_kst[t][0] = ts.kst[2 * t]; sp_kst[t][1] = ts.kst[2 * t + 1];
+                    }
                 }
+            } else {
+                for (int t = 0; t < ROWS; t++) sp_ok[t] = false;
             }
             if (g_sparse_mode == 2) dense = true;
             (dense ? g_dense_rows : g_sparse_rows) += ROWS;
@@ -124,6 +139,7 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
                     if (ts.sum_kind[t] != K_CLOSED) *err |= 0x80u;
                     for (int q = 0; q < 4; q++) if (sp_hits[t][q] != ts.hits[q * ROWS + t]) *err |= 0x80u;
                     for (int w = 0; w < NW; w++) if (sp_b[t][w] != ts.sum_b[w * ROWS + t]) *err |= 0x80u;
+                    ts.kst[2 * t] = sp_kst[t][0]; ts.kst[2 * t + 1] = sp_kst[t][1];   // let phase C use them
                 }
             }
         }

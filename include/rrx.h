@@ -25,6 +25,10 @@ enum {
     RRX_ERR_ARG = 4
 };
 
+/* RRX_MODE_NO_OVERLAP: the finditer-style view of the LAZY-v1 list:
+ *   p = base_offset; for (s,e) in LAZY-v1: if s >= p { emit; p = e }
+ * computed on the device (csrc/rrx_overlap.cu) by the one-shot calls rrx_scan_host / rrx_scan_device;
+ * the reusable scanner (rrx_scanner_scan) produces LAZY-v1 only. */
 enum { RRX_MODE_LAZY_V1 = 0, RRX_MODE_NO_OVERLAP = 1 };
 enum { RRX_COMPILE_DEFAULT = 0, RRX_COMPILE_NO_REDUCE = 1 };
 

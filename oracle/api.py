@@ -97,6 +97,15 @@ class Oracle:
                 return out[:m].copy()
             cap = int(m)
 
+    def no_overlap_matches(self, text, base: int = 0) -> np.ndarray:
+        """The non-overlapping view of the LAZY-v1 list."""
+        m = np.ascontiguousarray(self.lazy_matches(text, base))
+        L = _lib()
+        L.oracle_no_overlap.restype = C.c_uint64
+        L.oracle_no_overlap.argtypes = [C.c_void_p, C.c_uint64, C.c_int64]
+        k = int(L.oracle_no_overlap(m.ctypes.data, len(m), base))
+        return m[:k].copy()
+
     def time_parallel(self, text, piece: int, nthreads: int):
         buf = _as_u8(text)
         assert piece * nthreads <= len(buf)

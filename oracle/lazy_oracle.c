@@ -123,6 +123,22 @@ static void* job_run(void* p) {
 /* Scan `nthreads` independent contiguous pieces text[t*piece, (t+1)*piece) concurrently, one per
  * thread, each from an empty entry set (a throughput baseline, not a parity run).  Returns
  * seconds of wall time; *total_matches gets the sum. */
+/* Non-overlapping view of a LAZY-v1 list: p = base; for (s,e): if s >= p { emit; p = e }.
+ * Equivalent to resetting the forward set to the empty set after each reported match.  In place; returns the new length. */
+uint64_t oracle_no_overlap(int64_t* pairs, uint64_t n, int64_t base) {
+    uint64_t k = 0;
+    int64_t p = base;
+    for (uint64_t i = 0; i < n; i++) {
+        if (pairs[2 * i] >= p) {
+            pairs[2 * k] = pairs[2 * i];
+            pairs[2 * k + 1] = pairs[2 * i + 1];
+            p = pairs[2 * i + 1];
+            k++;
+        }
+    }
+    return k;
+}
+
 double oracle_time_parallel(const raw_nfa* a, const uint8_t* text, uint64_t piece, int nthreads,
                             uint64_t* total_matches) {
     pthread_t* th = malloc(sizeof(pthread_t) * (size_t)nthreads);

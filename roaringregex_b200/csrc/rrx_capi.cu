@@ -40,6 +40,30 @@ size_t ctrl_layout(size_t T, size_t* off) {
     f[4] = o; o += 4 * B;
     return (o + 15) & ~(size_t)15;
 }
+// Non-overlapping view (RRX_MODE_NO_OVERLAP): filter a device match list of n pairs into a newly
+// allocated device list.  *out_pairs is owned by the caller (cudaFree).
+int filter_no_overlap(const long long* d_in, uint64_t n, long long** out_pairs, uint64_t* out_n, cudaStream_t st) {
+    *out_pairs = nullptr;
+    *out_n = 0;
+    if (n == 0) return RRX_OK;
+    const size_t wsb = no_overlap_workspace_bytes(n);
+    void* ws = nullptr;
+    long long* d_out = nullptr;
+    unsigned long long* d_cnt = nullptr;
+    cudaError_t e = cudaMalloc(&ws, wsb);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, n * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&d_cnt, 8);
+    if (e == cudaSuccess) e = launch_no_overlap(reinterpret_cast<const longlong2*>(d_in), n, reinterpret_cast<longlong2*>(d_out), d_cnt, ws, wsb, st);
+    unsigned long long cnt = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(ws);
+    cudaFree(d_cnt);
+    if (e != cudaSuccess) { cudaFree(d_out); return cuda_err(e, "non-overlap filter"); }
+    *out_pairs = d_out;
+    *out_n = cnt;
+    return RRX_OK;
+}
 }  // namespace
 
 // Device-side state kept between rrx_scan_host calls on one program: the text buffer, a scanner
@@ -88,8 +112,9 @@ struct rrx_scanner {
     uint32_t launches = 0;
     bool owns_out = true;
     JitKernel* jit = nullptr;        // run-time specialised kernel (owned by the process-wide cache)
-    // pinned host mirror of [ticket, err, total0, total1]
+    // pinned host mirror of [ticket, err, total0, total1] followed by the shard composite (1+3*NW words)
     uint64_t* h_ctr = nullptr;
+    bool h_shard_valid = false;     // the composite in h_ctr belongs to the last scan
 };
 
 struct rrx_matches {
@@ -247,7 +272,7 @@ int rrx_scanner_create_ex(const rrx_program* p, uint64_t max_len, uint64_t capac
     RRX_CUDA(cudaMalloc(&s->d_chunk, ((s->max_tiles + 1023) / 1024 + 1) * 8));
     RRX_CUDA(cudaMalloc(&s->d_shard, (1 + 3 * (size_t)h.NW) * 4));
     RRX_CUDA(cudaMalloc(&s->d_pending, sizeof(PendingStart) * s->pending_cap));
-    RRX_CUDA(cudaMallocHost(&s->h_ctr, 32));
+    RRX_CUDA(cudaMallocHost(&s->h_ctr, 32 + 4 * (1 + 3 * (size_t)RRX_NW_MAX)));
     {
         // run-time specialisation: worth its ~1 s compile only for long inputs
         bool want = (flags & RRX_SCANNER_JIT) || (!(flags & RRX_SCANNER_NO_JIT) && max_len >= (32ull << 20));
@@ -330,6 +355,7 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     sp.pending_cap = s->pending_cap;
     if (opts && opts->entry) for (uint32_t w = 0; w < h.NW; w++) sp.entry[w] = opts->entry[w];
     s->launches = 0;
+    s->h_shard_valid = false;
     RRX_CUDA(cudaMemsetAsync(s->d_ctrl, 0, used, st));
     if (h.NW == 1)      // one-word automata keep the ready bit inside the 16-byte composite words
         RRX_CUDA(cudaMemsetAsync(s->d_tpay, 0, (2 * T + 2 * B) * PW * 4, st));
@@ -351,8 +377,11 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
 int rrx_scanner_result(rrx_scanner* s, rrx_scan_result* out, void* stream) {
     if (!s || !out) return set_err(RRX_ERR_ARG, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
+    // counters and the shard composite come back together: one synchronisation per scan
     RRX_CUDA(cudaMemcpyAsync(s->h_ctr, s->d_ctrl, 32, cudaMemcpyDeviceToHost, st));
+    RRX_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(s->h_ctr) + 32, s->d_shard, (1 + 3 * (size_t)s->NW) * 4, cudaMemcpyDeviceToHost, st));
     RRX_CUDA(cudaStreamSynchronize(st));
+    s->h_shard_valid = true;
     const uint32_t* w32 = reinterpret_cast<const uint32_t*>(s->h_ctr);
     out->error_bits = w32[1];
     out->n_matches = s->h_ctr[1];
@@ -419,6 +448,10 @@ int rrx_continue_starts(const rrx_program* p, const uint8_t* d_text, uint64_t le
 int rrx_scanner_shard_summary(rrx_scanner* s, uint32_t* out, uint64_t cap_words, void* stream) {
     const size_t n = 1 + 3 * (size_t)s->NW;
     if (!out || cap_words < n) return set_err(RRX_ERR_ARG, "summary buffer too small");
+    if (s->h_shard_valid) {          // already fetched with the counters (rrx_scanner_result)
+        std::memcpy(out, reinterpret_cast<const uint8_t*>(s->h_ctr) + 32, n * 4);
+        return RRX_OK;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     RRX_CUDA(cudaMemcpyAsync(out, s->d_shard, n * 4, cudaMemcpyDeviceToHost, st));
     RRX_CUDA(cudaStreamSynchronize(st));
@@ -429,7 +462,7 @@ int rrx_scanner_shard_summary(rrx_scanner* s, uint32_t* out, uint64_t cap_words,
 int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, uint64_t base_offset,
                     int mode, rrx_matches** out, void* stream) {
     if (!p || !out) return set_err(RRX_ERR_ARG, "null argument");
-    if (mode != RRX_MODE_LAZY_V1) return set_err(RRX_ERR_UNSUPPORTED, "only RRX_MODE_LAZY_V1 is implemented on the device");
+    if (mode != RRX_MODE_LAZY_V1 && mode != RRX_MODE_NO_OVERLAP) return set_err(RRX_ERR_ARG, "unknown mode");
     uint64_t cap = len / 64 + 1024;
     for (int attempt = 0; attempt < 2; attempt++) {
         rrx_scanner* s = nullptr;
@@ -451,6 +484,15 @@ int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, u
             m->d_pairs = s->d_out;
             s->owns_out = false;
             rrx_scanner_free(s);
+            if (mode == RRX_MODE_NO_OVERLAP) {
+                long long* filtered = nullptr;
+                uint64_t nf = 0;
+                rc = filter_no_overlap(m->d_pairs, m->count, &filtered, &nf, (cudaStream_t)stream);
+                if (rc) { rrx_matches_free(m); return rc; }
+                cudaFree(m->d_pairs);
+                m->d_pairs = filtered;
+                m->count = nf;
+            }
             *out = m;
             return RRX_OK;
         }
@@ -463,7 +505,7 @@ int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, u
 int rrx_scan_host(const rrx_program* p, const uint8_t* text, uint64_t len, uint64_t base_offset,
                   int mode, rrx_matches** out) {
     if (!p || !out || (!text && len)) return set_err(RRX_ERR_ARG, "null argument");
-    if (mode != RRX_MODE_LAZY_V1) return set_err(RRX_ERR_UNSUPPORTED, "only RRX_MODE_LAZY_V1 is implemented on the device");
+    if (mode != RRX_MODE_LAZY_V1 && mode != RRX_MODE_NO_OVERLAP) return set_err(RRX_ERR_ARG, "unknown mode");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return set_err(RRX_ERR_CUDA, "no CUDA device: librrx has no CPU fallback");
@@ -507,6 +549,15 @@ int rrx_scan_host(const rrx_program* p, const uint8_t* text, uint64_t len, uint6
         std::unique_ptr<rrx_matches> m(new rrx_matches);
         m->count = r.n_matches;
         m->owner = hc;
+        long long* filtered = nullptr;
+        if (mode == RRX_MODE_NO_OVERLAP) {
+            uint64_t nf = 0;
+            rc = filter_no_overlap(reinterpret_cast<const long long*>(r.d_matches), m->count, &filtered, &nf, hc->st);
+            if (rc) return rc;
+            m->count = nf;
+        }
+        std::unique_ptr<long long, void (*)(long long*)> filtered_guard(filtered, [](long long* q) { cudaFree(q); });
+        const long long* d_src = filtered ? filtered : reinterpret_cast<const long long*>(r.d_matches);
         if (m->count) {
             size_t best = hc->pool.size();
             for (size_t i = 0; i < hc->pool.size(); i++)
@@ -519,7 +570,7 @@ int rrx_scan_host(const rrx_program* p, const uint8_t* text, uint64_t len, uint6
                 RRX_CUDA(cudaMallocHost(&m->pinned.p, pairs * 16));
                 m->pinned.pairs = pairs;
             }
-            cudaError_t e = cudaMemcpyAsync(m->pinned.p, r.d_matches, m->count * 16, cudaMemcpyDeviceToHost, hc->st);
+            cudaError_t e = cudaMemcpyAsync(m->pinned.p, d_src, m->count * 16, cudaMemcpyDeviceToHost, hc->st);
             if (e == cudaSuccess) e = cudaStreamSynchronize(hc->st);
             if (e != cudaSuccess) { hc->pool.push_back(m->pinned); return cuda_err(e, "cudaMemcpy D2H"); }
         }

@@ -634,6 +634,25 @@ RRX_DEV bool phase_a_exit(const ScanParams& sp, const ProgView& pv, const F& fw,
     return true;
 }
 
+// Unpack the match-end queue of phase_a_cand into the row's hit mask (and its first two known starts).
+template <int NW>
+RRX_DEV void sparse_drain(TileState<NW>& ts, int t, uint32_t kq, uint32_t ks) {
+    constexpr int ROWS = TILE_ROWS;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t e1 = (kq >> (8 * i)) & 0xffu, s1 = (ks >> (8 * i)) & 0xffu;
+        if (e1) {
+            const uint32_t q = e1 - 1;
+            ts.hits[(q >> 5) * ROWS + t] |= 1u << (q & 31);
+            if (s1) {
+                const uint16_t rec = (uint16_t)((q << 8) | (s1 - 1));
+                if (ts.kst[2 * t] == (uint16_t)KST_NONE) ts.kst[2 * t] = rec;
+                else if (ts.kst[2 * t + 1] == (uint16_t)KST_NONE) ts.kst[2 * t + 1] = rec;
+            }
+        }
+    }
+}
+
 template <int NW, class F>
 RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t) {
     constexpr int ROWS = TILE_ROWS;
@@ -683,9 +702,15 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
     uint32_t live = 0;                  // OR of the words of H
     uint32_t work = bail ? 0u : (uint32_t)ncand;     // non-zero while the lane has something left to do
     const SmemBytes rb(rp);
+#pragma unroll
+    for (int q = 0; q < 4; q++) ts.hits[q * ROWS + t] = 0;
+    ts.kst[2 * t] = ts.kst[2 * t + 1] = (uint16_t)KST_NONE;
     while (RRX_WARP_ANY(work != 0)) {
-        // ---- outer: the lane is at a candidate byte (or jumps to its next one) ----
-        if (work != 0) {
+        // ---- outer: the queue is full, or the lane is at a candidate byte (or jumps to its next one) ----
+        if (work != 0 && nacc >= 4) {
+            sparse_drain<NW>(ts, t, kq, ks);
+            kq = ks = nacc = 0;
+        } else if (work != 0) {
             const uint32_t fresh = live == 0 ? 1u : 0u;
             if (fresh) {
                 uint32_t w = p >> 5;
@@ -749,7 +774,7 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
         // (branch-free: every lane computes the step, lanes that are not in a run or stand on a
         // candidate byte just do not commit it)
         // Two steps per vote: the second one is harmless for lanes that have stopped.
-        uint32_t go = live;
+        uint32_t go = nacc < 4 ? live : 0u;
 #define RRX_SPARSE_STEP()                                                                       \
         {                                                                                           \
             const uint32_t c = rb.at(p & (uint32_t)(ROW_BYTES - 1));                                \
@@ -771,7 +796,7 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
             const bool end = step && p == (uint32_t)ROW_BYTES;                                      \
             ncand = end ? 0 : ncand;                                                                \
             live = step ? (end ? 0u : lv) : live;                                                   \
-            go = step ? live : 0u;                                                                  \
+            go = (step && nacc < 4) ? live : 0u;        /* queue full: parked until drained */     \
         }
         while (RRX_WARP_ANY(go != 0)) {
             RRX_SPARSE_STEP()
@@ -780,25 +805,8 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
 #undef RRX_SPARSE_STEP
         work = live | (uint32_t)ncand;
     }
-    if (bail || nacc > 4) return false;
-    uint32_t hit[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint32_t e1 = (kq >> (8 * i)) & 0xffu;
-        if (e1) {
-            const uint32_t q = e1 - 1, bit = 1u << (q & 31), hw = q >> 5;
-            hit[0] |= hw == 0 ? bit : 0u; hit[1] |= hw == 1 ? bit : 0u;
-            hit[2] |= hw == 2 ? bit : 0u; hit[3] |= hw == 3 ? bit : 0u;
-        }
-    }
-    // the two most recent match ends with a known start
-    uint32_t k0 = KST_NONE, k1 = KST_NONE;
-    if ((ks & 0xffu) != 0) k0 = (((kq & 0xffu) - 1) << 8) | ((ks & 0xffu) - 1);
-    if (((ks >> 8) & 0xffu) != 0) k1 = ((((kq >> 8) & 0xffu) - 1) << 8) | (((ks >> 8) & 0xffu) - 1);
-#pragma unroll
-    for (int q = 0; q < 4; q++) ts.hits[q * ROWS + t] = hit[q];
-    ts.kst[2 * t] = (uint16_t)k0;
-    ts.kst[2 * t + 1] = (uint16_t)k1;
+    if (bail) return false;
+    sparse_drain<NW>(ts, t, kq, ks);
     return true;
 }
 

@@ -214,14 +214,30 @@ class TorchComm:
     """torch.distributed as the collective provider (NCCL with device tensors, gloo with CPU ones)."""
 
     def __init__(self, dist, device):
-        self.dist, self.device = dist, device
+        import torch
+        self.dist, self.device = dist, torch.device(device)
 
     def allgather(self, arr: np.ndarray) -> np.ndarray:
+        """One all_gather_into_tensor on preallocated buffers; pinned staging on both sides when the
+        collective runs on a GPU (one H2D, one collective, one D2H per call)."""
         import torch
-        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.int32)).to(self.device)
-        out = [torch.empty_like(t) for _ in range(self.dist.get_world_size())]
-        self.dist.all_gather(out, t)
-        return np.stack([o.cpu().numpy().view(np.uint32) for o in out])
+        a = np.ascontiguousarray(arr).view(np.int32)
+        n, world = a.size, self.dist.get_world_size()
+        key = (n, world)
+        if getattr(self, "_key", None) != key:
+            cuda = self.device.type == "cuda"
+            self._key = key
+            self._h_in = torch.empty(n, dtype=torch.int32, pin_memory=cuda)
+            self._h_out = torch.empty(world * n, dtype=torch.int32, pin_memory=cuda)
+            self._d_in = torch.empty(n, dtype=torch.int32, device=self.device)
+            self._d_out = torch.empty(world * n, dtype=torch.int32, device=self.device)
+        self._h_in.numpy()[:] = a
+        self._d_in.copy_(self._h_in, non_blocking=True)
+        self.dist.all_gather_into_tensor(self._d_out, self._d_in)
+        self._h_out.copy_(self._d_out, non_blocking=True)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+        return self._h_out.numpy().view(np.uint32).reshape(world, n).copy()
 
     def allgather_obj(self, obj):
         out = [None] * self.dist.get_world_size()

@@ -253,3 +253,45 @@ def test_sharded_start_scan_travels_through_all_shards(rrx, oracle_api, torch_cu
     text[-5] = ord("q")
     got = _run_world_gpu(rrx, torch_cuda, "(x|y)*z.*q", text, 4, halo=256)
     assert got.tolist() == [[0, n - 4]]
+
+
+def test_no_overlap_view(rrx, oracle_api, torch_cuda):
+    """RRX_MODE_NO_OVERLAP on the device against the oracle's filter: sparse and
+    heavy overlap (every match sharing one start), empty lists, and the config corpora."""
+    rnd = random.Random(3)
+    cases = [("(x|y)*z.*q", b"xyzaaqbbq q zq"), ("a+", b"aaa b aa"), ("ab|bc", b"abc abcbc"), ("(ab|cd)*e", b""), ("a+", b"bbbb")]
+    text = bytearray(b"a" * 200000)
+    text[0] = ord("z")
+    for i in range(50, len(text), 97):
+        text[i] = ord("q")
+    cases.append(("(x|y)*z.*q", bytes(text)))                       # all matches start at offset 0
+    cases.append(("(a|b)*a(a|b){3}c", bytes(rnd.choices(b"abc", k=100000))))
+    cases.append(("[ab]+c", bytes(rnd.choices(b"abc ", k=100000))))
+    for cid, n in ((1, 1 << 20), (2, 4 << 20), (3, 2 << 20), (5, 4 << 20)):
+        cases.append((CONFIGS[cid].pattern, cpu_corpus(CONFIGS[cid], 0, n)))
+    for pat, txt in cases:
+        want = oracle_api.Oracle(pat).no_overlap_matches(txt)
+        got = rrx.RRegex(pat).scan_host(txt, 0, rrx.MODE_NO_OVERLAP)
+        assert got.shape == want.shape and np.array_equal(got, want), (pat, got.shape, want.shape)
+        if len(txt):
+            t = torch_cuda.tensor(np.frombuffer(bytes(txt), dtype=np.uint8), device="cuda")
+            got_d = rrx.RRegex(pat).scan_device(t.data_ptr(), len(txt), 0, rrx.MODE_NO_OVERLAP)
+            assert np.array_equal(got_d, want), pat
+
+
+def test_host_scans_reuse_buffers_and_stay_exact(rrx, oracle_api, torch_cuda):
+    """rrx_scan_host keeps its device text buffer, scanner and pinned match buffers between calls:
+    growing, shrinking and overflowing (many matches) inputs on ONE program stay exact, and results of
+    earlier calls stay valid while later calls run."""
+    pat = "(ab|cd)*e"
+    r, o = rrx.RRegex(pat), oracle_api.Oracle(pat)
+    rnd = random.Random(8)
+    kept = []
+    for n in (1000, 3 << 20, 17, 1 << 20, 0, 5 << 20):
+        text = bytes(rnd.choices(b"abcdeee ", k=n))             # dense in matches: exercises the capacity retry
+        got = r.scan_host(text)
+        want = o.lazy_matches(text)
+        assert np.array_equal(got, want), n
+        kept.append((got, want))
+    for got, want in kept:
+        assert np.array_equal(got, want)

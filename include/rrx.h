@@ -129,6 +129,13 @@ int rrx_scanner_copy_matches(rrx_scanner* s, int64_t* host_out, uint64_t n, void
 /* Composite transfer function of the last scanned shard: 1+3*words uint32 (kind, b, U, P); host copy. */
 int rrx_scanner_shard_summary(rrx_scanner* s, uint32_t* out, uint64_t cap_words, void* stream);
 
+/* The same composite followed by the scan's counters, left in DEVICE memory (asynchronous): words32
+ * [kind, b[W], U[W], P[W], ticket, error_bits, n_matches lo, hi, n_pending lo, hi, 0, 0].  This is the
+ * message a rank contributes to the all-gather of a sharded scan: the collective can be enqueued on
+ * the same stream right behind the scan, and ONE device-to-host copy of the gathered messages gives
+ * every rank its own counters and everybody's composite (one synchronisation per step). */
+int rrx_scanner_message_device(rrx_scanner* s, uint32_t* d_out, uint64_t cap_words, void* stream);
+
 /* ---- sharded scans (one shard per GPU): host-side helpers, no device work ---------------------
  * A shard summary is the composite transfer function of the shard (rrx_scanner_shard_summary):
  * words32 [kind, b[W], U[W], P[W]].  Given the summaries of ALL shards in rank order (as returned

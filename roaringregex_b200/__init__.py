@@ -96,6 +96,7 @@ def lib() -> C.CDLL:
         "rrx_scanner_scan": (C.c_int, [vp, vp, u64, u64, C.POINTER(_Opts), vp]),
         "rrx_scanner_result": (C.c_int, [vp, C.POINTER(_Result), vp]),
         "rrx_scanner_shard_summary": (C.c_int, [vp, vp, u64, vp]),
+        "rrx_scanner_message_device": (C.c_int, [vp, vp, u64, vp]),
         "rrx_scanner_copy_matches": (C.c_int, [vp, vp, u64, vp]),
         "rrx_scanner_copy_pending": (C.c_int, [vp, vp, u64, C.POINTER(u64), vp]),
         "rrx_fold_entry": (C.c_int, [vp, vp, u32, u32, vp, C.POINTER(C.c_int)]),
@@ -359,6 +360,10 @@ class Scanner:
         out = np.empty((n, 2), dtype=np.int64)
         _check(lib().rrx_scanner_copy_matches(self._h, out.ctypes.data, n, stream))
         return out
+
+    def message_device(self, d_ptr: int, cap_words: int, stream: int = 0):
+        """Enqueue a device-to-device copy of [shard composite | counters] (rrx_scanner_message_device)."""
+        _check(lib().rrx_scanner_message_device(self._h, d_ptr, cap_words, stream))
 
     def shard_summary(self, stream: int = 0) -> np.ndarray:
         w = self.regex.info["words"]

@@ -458,6 +458,16 @@ int rrx_scanner_shard_summary(rrx_scanner* s, uint32_t* out, uint64_t cap_words,
     return RRX_OK;
 }
 
+int rrx_scanner_message_device(rrx_scanner* s, uint32_t* d_out, uint64_t cap_words, void* stream) {
+    if (!s || !d_out) return set_err(RRX_ERR_ARG, "null argument");
+    const size_t n = 1 + 3 * (size_t)s->NW;
+    if (cap_words < n + 8) return set_err(RRX_ERR_ARG, "message buffer too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    RRX_CUDA(cudaMemcpyAsync(d_out, s->d_shard, n * 4, cudaMemcpyDeviceToDevice, st));
+    RRX_CUDA(cudaMemcpyAsync(d_out + n, s->d_ctrl, 32, cudaMemcpyDeviceToDevice, st));
+    return RRX_OK;
+}
+
 // ---- one-shot convenience calls ----------------------------------------------------------------------
 int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, uint64_t base_offset,
                     int mode, rrx_matches** out, void* stream) {

@@ -62,19 +62,52 @@ class DeviceBackend:
             raise RuntimeError(f"scan kernel error bits {r['error_bits']}")
         if r["n_matches"] > r["capacity"]:
             raise RuntimeError("match buffer too small for this shard")
+        pend = self._fetch_pending(sc, r["n_pending"])
+        return ShardScan(n=r["n_matches"], matches=sc.matches(self.stream) if fetch else None,
+                         summary=sc.shard_summary(self.stream), pending=pend, handle=sc)
+
+    def _fetch_pending(self, sc, n_pending: int) -> list:
         pend = []
-        if r["n_pending"]:
-            buf = np.zeros(r["n_pending"] * PENDING_RECORD, dtype=np.uint8)
+        if n_pending:
+            buf = np.zeros(n_pending * PENDING_RECORD, dtype=np.uint8)
             n = C.c_uint64(0)
-            _check(lib().rrx_scanner_copy_pending(sc._h, buf.ctypes.data, r["n_pending"], C.byref(n), self.stream))
-            if int(n.value) < r["n_pending"]:
+            _check(lib().rrx_scanner_copy_pending(sc._h, buf.ctypes.data, n_pending, C.byref(n), self.stream))
+            if int(n.value) < n_pending:
                 raise RuntimeError("too many start scans cross the shard's left edge (pending list overflow)")
             for i in range(int(n.value)):
                 rec = buf[i * PENDING_RECORD:(i + 1) * PENDING_RECORD]
                 mi, nxt = np.frombuffer(rec[:16].tobytes(), dtype=np.int64)
                 pend.append((int(mi), self.base + int(nxt), np.frombuffer(rec[16:].tobytes(), dtype=np.uint32).copy()))
-        return ShardScan(n=r["n_matches"], matches=sc.matches(self.stream) if fetch else None,
-                         summary=sc.shard_summary(self.stream), pending=pend, handle=sc)
+        return pend
+
+    def scan_gather(self, comm, fetch: bool):
+        """Speculative scan of the whole shard fused with the exchange: scan kernels, a device-side copy of
+        [composite | counters] and the all-gather are enqueued back to back on one stream; a single
+        device-to-host copy of the gathered messages then gives this rank its own counters and every
+        rank's composite.  One synchronisation per step.  -> (ShardScan, (world, 1+3W+1) uint32 message
+        array in the format scan_sharded exchanges), or None if `comm` cannot gather device buffers."""
+        if not hasattr(comm, "allgather_device"):
+            return None
+        import torch
+        sc, W = self.scanner, self.words
+        nw = 1 + 3 * W + 8
+        if getattr(self, "_msg", None) is None:
+            self._msg = torch.zeros(nw, dtype=torch.int32, device="cuda")
+        sc.scan(self.ptr, self.len, self.base, self.halo, None, self.stream)
+        sc.message_device(self._msg.data_ptr(), nw, self.stream)
+        g = comm.allgather_device(self._msg)                    # (world, nw) uint32 on the host
+        mine = g[comm.dist.get_rank()]
+        ctr = mine[1 + 3 * W:]
+        err, n_matches, n_pending = int(ctr[1]), int(ctr[2]) | (int(ctr[3]) << 32), int(ctr[4]) | (int(ctr[5]) << 32)
+        if err:
+            raise RuntimeError(f"scan kernel error bits {err}")
+        if n_matches > self.capacity:
+            raise RuntimeError("match buffer too small for this shard")
+        pend = self._fetch_pending(sc, n_pending)               # rare; no collective involved
+        spec = ShardScan(n=n_matches, matches=sc.matches(self.stream) if fetch else None,
+                         summary=mine[:1 + 3 * W].copy(), pending=pend, handle=sc)
+        msgs = np.concatenate([g[:, :1 + 3 * W], np.minimum(g[:, 1 + 3 * W + 4:1 + 3 * W + 5], 0xffffffff)], axis=1).astype(np.uint32)
+        return spec, msgs
 
     def head(self, scan: ShardScan, k: int) -> np.ndarray:
         """First k matches of a scan left on the device."""
@@ -146,11 +179,18 @@ def scan_sharded(regex: RRegex, backend, comm, rank: int, world: int, fetch: boo
     summaries (every rank can fold every other rank's entry), so in the common case — no entry set
     survives into any shard, no start scan crosses a halo — a step has exactly one collective.
     `comm.allgather_obj(obj)` (pickled, tiny) serves the rare hand-over of unfinished start scans."""
-    spec = backend.scan(backend.len, None, fetch)                 # speculative: empty entry
+    fused = backend.scan_gather(comm, fetch) if hasattr(backend, "scan_gather") else None
+    if fused is not None:
+        spec, first_gather = fused                                # scan + exchange already done, one sync
+    else:
+        spec, first_gather = backend.scan(backend.len, None, fetch), None     # speculative: empty entry
     advertised, result, last_entry = spec, None, None
     for _round in range(max(world, 1)):
-        msg = np.concatenate([advertised.summary.astype(np.uint32), np.array([len(spec.pending)], dtype=np.uint32)])
-        gathered = comm.allgather(msg)
+        if _round == 0 and first_gather is not None:
+            gathered = first_gather
+        else:
+            msg = np.concatenate([advertised.summary.astype(np.uint32), np.array([len(spec.pending)], dtype=np.uint32)])
+            gathered = comm.allgather(msg)
         summaries, spec_pending = gathered[:, :-1], gathered[:, -1]
         folds = [fold_entry(regex, summaries, r) for r in range(world)]
         entry, _ = folds[rank]
@@ -238,6 +278,21 @@ class TorchComm:
         if self.device.type == "cuda":
             torch.cuda.current_stream(self.device).synchronize()
         return self._h_out.numpy().view(np.uint32).reshape(world, n).copy()
+
+    def allgather_device(self, d_msg) -> np.ndarray:
+        """All-gather of a device tensor enqueued on the current stream; -> (world, n) uint32 on the host."""
+        import torch
+        if self.device.type != "cuda":
+            raise RuntimeError("device all-gather needs a CUDA communicator")
+        n, world = d_msg.numel(), self.dist.get_world_size()
+        if getattr(self, "_dkey", None) != (n, world):
+            self._dkey = (n, world)
+            self._g_out = torch.empty(world * n, dtype=d_msg.dtype, device=self.device)
+            self._g_host = torch.empty(world * n, dtype=d_msg.dtype, pin_memory=True)
+        self.dist.all_gather_into_tensor(self._g_out, d_msg)
+        self._g_host.copy_(self._g_out, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._g_host.numpy().view(np.uint32).reshape(world, n).copy()
 
     def allgather_obj(self, obj):
         out = [None] * self.dist.get_world_size()

@@ -129,6 +129,12 @@ int rrx_scanner_copy_matches(rrx_scanner* s, int64_t* host_out, uint64_t n, void
 /* Composite transfer function of the last scanned shard: 1+3*words uint32 (kind, b, U, P); host copy. */
 int rrx_scanner_shard_summary(rrx_scanner* s, uint32_t* out, uint64_t cap_words, void* stream);
 
+/* Measurement: with timing enabled every rrx_scanner_scan records CUDA events on the launching stream
+ * right before and after the scan kernel's launch; rrx_scanner_kernel_ms returns the duration of the
+ * last one (the dominant kernel alone, without the memsets before and the ordering pass after it). */
+int rrx_scanner_enable_timing(rrx_scanner* s, int on);
+int rrx_scanner_kernel_ms(rrx_scanner* s, float* ms);
+
 /* The same composite followed by the scan's counters, left in DEVICE memory (asynchronous): words32
  * [kind, b[W], U[W], P[W], ticket, error_bits, n_matches lo, hi, n_pending lo, hi, 0, 0].  This is the
  * message a rank contributes to the all-gather of a sharded scan: the collective can be enqueued on

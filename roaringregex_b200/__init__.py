@@ -96,6 +96,8 @@ def lib() -> C.CDLL:
         "rrx_scanner_scan": (C.c_int, [vp, vp, u64, u64, C.POINTER(_Opts), vp]),
         "rrx_scanner_result": (C.c_int, [vp, C.POINTER(_Result), vp]),
         "rrx_scanner_shard_summary": (C.c_int, [vp, vp, u64, vp]),
+        "rrx_scanner_enable_timing": (C.c_int, [vp, C.c_int]),
+        "rrx_scanner_kernel_ms": (C.c_int, [vp, C.POINTER(C.c_float)]),
         "rrx_scanner_message_device": (C.c_int, [vp, vp, u64, vp]),
         "rrx_scanner_copy_matches": (C.c_int, [vp, vp, u64, vp]),
         "rrx_scanner_copy_pending": (C.c_int, [vp, vp, u64, C.POINTER(u64), vp]),
@@ -360,6 +362,15 @@ class Scanner:
         out = np.empty((n, 2), dtype=np.int64)
         _check(lib().rrx_scanner_copy_matches(self._h, out.ctypes.data, n, stream))
         return out
+
+    def enable_timing(self, on: bool = True):
+        _check(lib().rrx_scanner_enable_timing(self._h, int(on)))
+
+    def kernel_ms(self) -> float:
+        """Duration of the last scan kernel launch alone (CUDA events on the launching stream)."""
+        ms = C.c_float(0)
+        _check(lib().rrx_scanner_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
 
     def message_device(self, d_ptr: int, cap_words: int, stream: int = 0):
         """Enqueue a device-to-device copy of [shard composite | counters] (rrx_scanner_message_device)."""

@@ -115,6 +115,9 @@ struct rrx_scanner {
     // pinned host mirror of [ticket, err, total0, total1] followed by the shard composite (1+3*NW words)
     uint64_t* h_ctr = nullptr;
     bool h_shard_valid = false;     // the composite in h_ctr belongs to the last scan
+    // optional: CUDA events around the scan kernel launch alone (measurement)
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 struct rrx_matches {
@@ -215,6 +218,8 @@ void rrx_scanner_free(rrx_scanner* s) {
     cudaFree(s->d_stage); cudaFree(s->d_tile_seg); cudaFree(s->d_tile_cnt); cudaFree(s->d_chunk);
     cudaFree(s->d_shard); cudaFree(s->d_pending);
     if (s->h_ctr) cudaFreeHost(s->h_ctr);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
     delete s;
 }
 
@@ -230,7 +235,7 @@ uint64_t rrx_program_jit_source(const rrx_program* p, char* buf, uint64_t cap) {
 
 int rrx_program_jit_compile(const rrx_program* p, const char* path) {
     if (!p) return set_err(RRX_ERR_ARG, "null argument");
-    if (!jit_applicable(p->prog)) return set_err(RRX_ERR_UNSUPPORTED, "only one-word automata without row tables are specialised");
+    if (!jit_applicable(p->prog)) return set_err(RRX_ERR_UNSUPPORTED, "automata that need per-source row tables are not specialised");
     std::vector<char> cubin;
     std::string err;
     if (!jit_compile_cubin(p->prog, &cubin, &err)) return set_err(RRX_ERR_CUDA, err);
@@ -366,8 +371,10 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
         return RRX_OK;
     }
     int grid = 0;
+    if (s->timing) RRX_CUDA(cudaEventRecord(s->ev0, st));
     cudaError_t e = s->jit ? jit_launch(s->jit, sp, s->sm_count, st, &grid) : launch_scan(sp, h, s->sm_count, st, &grid);
     if (e != cudaSuccess) return cuda_err(e, "rrx_scan_kernel launch");
+    if (s->timing) RRX_CUDA(cudaEventRecord(s->ev1, st));
     e = launch_order(s->d_tile_cnt, s->d_tile_seg, sp.num_tiles, s->d_chunk, s->d_stage, s->d_out, s->capacity, st);
     if (e != cudaSuccess) return cuda_err(e, "ordering pass launch");
     s->launches = 4;
@@ -455,6 +462,22 @@ int rrx_scanner_shard_summary(rrx_scanner* s, uint32_t* out, uint64_t cap_words,
     cudaStream_t st = (cudaStream_t)stream;
     RRX_CUDA(cudaMemcpyAsync(out, s->d_shard, n * 4, cudaMemcpyDeviceToHost, st));
     RRX_CUDA(cudaStreamSynchronize(st));
+    return RRX_OK;
+}
+
+int rrx_scanner_enable_timing(rrx_scanner* s, int on) {
+    if (!s) return set_err(RRX_ERR_ARG, "null argument");
+    if (on && !s->ev0) {
+        RRX_CUDA(cudaEventCreate(&s->ev0));
+        RRX_CUDA(cudaEventCreate(&s->ev1));
+    }
+    s->timing = on != 0;
+    return RRX_OK;
+}
+int rrx_scanner_kernel_ms(rrx_scanner* s, float* ms) {
+    if (!s || !ms || !s->ev0) return set_err(RRX_ERR_ARG, "timing was not enabled");
+    RRX_CUDA(cudaEventSynchronize(s->ev1));
+    RRX_CUDA(cudaEventElapsedTime(ms, s->ev0, s->ev1));
     return RRX_OK;
 }
 

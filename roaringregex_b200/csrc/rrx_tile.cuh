@@ -167,8 +167,21 @@ template <int NW> RRX_DEV void load_B(const ProgView& pv, uint32_t c, uint32_t* 
         out[0] = lds_tab1(pv.Blane, c);
     } else {
         const uint32_t* e = reinterpret_cast<const uint32_t*>(pv.Blane) + c * NW;
+#if defined(__CUDA_ARCH__) && !defined(RRX_HOST_EMU)
+        if (NW == 2) {                       // entries are NW*4 bytes and the table is 16-byte aligned: vector loads
+            const uint2 v = *reinterpret_cast<const uint2*>(e);
+            out[0] = v.x; out[1] = v.y;
+        } else {
+#pragma unroll
+            for (int w = 0; w < NW; w += 4) {
+                const uint4 v = *reinterpret_cast<const uint4*>(e + w);
+                out[w] = v.x; out[w + 1] = v.y; out[w + 2] = v.z; out[w + 3] = v.w;
+            }
+        }
+#else
 #pragma unroll
         for (int w = 0; w < NW; w++) out[w] = e[w];
+#endif
     }
 }
 // f = follow'(S) through a decomposition (shift terms, bicliques, rows) read from shared memory.
@@ -216,9 +229,21 @@ RRX_DEV void follow_terms(const uint32_t* terms, uint32_t n_terms, const uint32_
     }
 }
 
+// Parameters of the candidate-driven row scan (rrx_prog.h: cand_byte, D, groups) read from the
+// shared copy of the program; the run-time specialised policy (rrx_jit.cu) overrides these with
+// immediates.
+template <int NW> struct SparseFromSmem {
+    RRX_DEV uint32_t sp_cand(const ProgView& pv) const { return pv.h().cand_byte; }
+    RRX_DEV uint32_t sp_ngroups(const ProgView& pv) const { return pv.h().n_groups; }
+    RRX_DEV uint32_t sp_D(const ProgView& pv, int w) const { return pv.sm[pv.h().off_sparse + w]; }
+    RRX_DEV uint32_t sp_gk(const ProgView& pv, uint32_t g, int w) const { return pv.sm[pv.h().off_sparse + NW + g * (2 * NW + 1) + w]; }
+    RRX_DEV uint32_t sp_gpred(const ProgView& pv, uint32_t g, int w) const { return pv.sm[pv.h().off_sparse + NW + g * (2 * NW + 1) + NW + w]; }
+    RRX_DEV uint32_t sp_gflags(const ProgView& pv, uint32_t g) const { return pv.sm[pv.h().off_sparse + NW + g * (2 * NW + 1) + 2 * NW]; }
+};
+
 // Follow policy.  NT >= 0: one-word automaton whose forward AND reverse decompositions (up to NT
 // rotations, NB bicliques each) live in registers; NT < 0: anything, read from shared memory.
-template <int NW, int NT, int NB> struct Prog {
+template <int NW, int NT, int NB> struct Prog : SparseFromSmem<NW> {
     static_assert(NW == 1, "register program is for one-word sets");
     uint32_t rot[NT > 0 ? NT : 1], msk[NT > 0 ? NT : 1], bsrc[NB > 0 ? NB : 1], bdst[NB > 0 ? NB : 1];
     uint32_t rrot[NT > 0 ? NT : 1], rmsk[NT > 0 ? NT : 1], rbsrc[NB > 0 ? NB : 1], rbdst[NB > 0 ? NB : 1];
@@ -265,7 +290,7 @@ template <int NW, int NT, int NB> struct Prog {
         f[0] = o;
     }
 };
-template <int NW, int NB> struct Prog<NW, -1, NB> {
+template <int NW, int NB> struct Prog<NW, -1, NB> : SparseFromSmem<NW> {
     RRX_DEV void init(const ProgView&) {}
     RRX_DEV uint32_t first(const ProgView& pv, int w) const { return pv.sm[pv.h().off_first + w]; }
     RRX_DEV uint32_t accept(const ProgView& pv, int w) const { return pv.sm[pv.h().off_accept + w]; }
@@ -657,9 +682,7 @@ template <int NW, class F>
 RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t) {
     constexpr int ROWS = TILE_ROWS;
     const ProgHeader& h = pv.h();
-    const uint32_t* D = pv.sm + h.off_sparse;
-    const uint32_t* grp = D + NW;
-    const uint32_t ngr = h.n_groups, cand = h.cand_byte;
+    const uint32_t ngr = fw.sp_ngroups(pv), cand = fw.sp_cand(pv);
     const uint8_t* rp = ts.text + t * ROW_PITCH;
 
     // (1) candidate mask: bit p of cm[q] <=> byte 32q+p == cand
@@ -693,7 +716,7 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
     // unpacked after the loops.
     uint32_t H[NW], Bc[NW], f[NW], DA[NW];
 #pragma unroll
-    for (int w = 0; w < NW; w++) { H[w] = 0; DA[w] = D[w]; }
+    for (int w = 0; w < NW; w++) { H[w] = 0; DA[w] = fw.sp_D(pv, w); }
     int budget = SPARSE_BUDGET;         // backward verification steps this row may spend
     uint32_t p = 0;
     uint32_t rs1 = 0;                   // 1 + lazy start of every match of the current run, or 0: not known
@@ -726,18 +749,19 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
             for (int w = 0; w < NW; w++) nx[w] = f[w] & DA[w];
             ncand--;
             int n_inj = 0, s_inj = -1;
-            for (uint32_t g = 0; g < ngr && !bail; g++) {
-                const uint32_t* gk = grp + g * (2 * NW + 1);
+#pragma unroll
+            for (uint32_t g = 0; g < RRX_MAX_GROUPS; g++) {
+                if (g >= ngr || bail) break;
                 uint32_t need = 0;
 #pragma unroll
-                for (int w = 0; w < NW; w++) need |= gk[w] & ~f[w];
+                for (int w = 0; w < NW; w++) need |= fw.sp_gk(pv, g, w) & ~f[w];
                 if (!need) continue;                       // already entered from H
-                bool inj = (gk[2 * NW] & 1u) != 0;
+                bool inj = (fw.sp_gflags(pv, g) & 1u) != 0;
                 int s = (int)p;
                 if (!inj) {
                     uint32_t R[NW], Bq[NW], x[NW];
 #pragma unroll
-                    for (int w = 0; w < NW; w++) R[w] = gk[NW + w];
+                    for (int w = 0; w < NW; w++) R[w] = fw.sp_gpred(pv, g, w);
                     for (int q = (int)p - 1; q >= 0; q--) {
                         load_B<NW>(pv, rb.at((uint32_t)q), Bq);
                         uint32_t m = 0;
@@ -753,7 +777,7 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
                     n_inj++;
                     s_inj = s;
 #pragma unroll
-                    for (int w = 0; w < NW; w++) nx[w] |= gk[w];
+                    for (int w = 0; w < NW; w++) nx[w] |= fw.sp_gk(pv, g, w);
                 }
             }
             rs1 = (fresh && n_inj == 1) ? (uint32_t)(s_inj + 1) : 0u;       // a candidate inside a run: ambiguous from here on

@@ -139,3 +139,9 @@ def test_specialised_kernel_compiles_without_gpu(rrx, tmp_path):
             pytest.skip("no NVRTC on this machine")
         raise
     assert out.stat().st_size > 10000
+    # multi-word automata are specialised too (word-by-word funnel shifts, zero words dropped)
+    for pat, words in (("a{1,100}b", 4), ("(a|b){1,300}c", 16)):
+        rw = rrx.RRegex(pat)
+        assert rw.info["words"] == words and "__funnelshift_l" in rw.jit_source()
+        rw.jit_compile(str(out))
+        assert out.stat().st_size > 10000

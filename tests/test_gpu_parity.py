@@ -160,7 +160,7 @@ def test_config2_full_size_properties(rrx, oracle_api, torch_cuda):
         assert rx.fullmatch(host[s_:e_].tobytes())
 
 
-@pytest.mark.parametrize("cfg_id,n", [(1, 1 << 20), (2, 8 << 20), (5, 8 << 20)])
+@pytest.mark.parametrize("cfg_id,n", [(1, 1 << 20), (2, 8 << 20), (3, 8 << 20), (4, 4 << 20), (5, 8 << 20)])
 def test_runtime_specialised_kernel(rrx, oracle_api, torch_cuda, cfg_id, n):
     """The NVRTC-specialised kernel (regex compiled to straight-line code) against the oracle and
     against the pre-compiled generic kernel."""
@@ -184,14 +184,14 @@ def test_runtime_specialised_random_patterns(rrx, oracle_api, torch_cuda):
     torch = torch_cuda
     rnd = random.Random(4242)
     done = 0
-    while done < 12:
+    while done < 16:
         pat = _random_regex(rnd)
         try:
             o = oracle_api.Oracle(pat)
             r = rrx.RRegex(pat)
         except Exception:
             continue
-        if r.info["words"] != 1 or r.info["uses_rows"]:
+        if r.info["uses_rows"]:
             continue
         done += 1
         text = np.frombuffer(bytes(rnd.choices(b"abc\n", k=200000)), dtype=np.uint8)

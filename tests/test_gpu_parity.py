@@ -295,3 +295,55 @@ def test_host_scans_reuse_buffers_and_stay_exact(rrx, oracle_api, torch_cuda):
         kept.append((got, want))
     for got, want in kept:
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("cfg_id,n", [(3, 1 << 30), (4, 1 << 30), (5, 2 << 30)])
+def test_large_corpora_properties(rrx, oracle_api, torch_cuda, cfg_id, n):
+    """Configs 3-5 at GiB scale, through size-independent properties: ends strictly ascending and one
+    match per end; every end is where the pattern's last byte sits and no such byte is missed
+    (closed forms of these regexes); each sampled span is in the language and no later start works
+    (laziness); scanning in two pieces with the carried state gives the same list as scanning whole;
+    a 32 MiB prefix is bit-exact against the oracle."""
+    torch = torch_cuda
+    cfg = CONFIGS[cfg_id]
+    d = torch.empty(n + 256, dtype=torch.uint8, device="cuda")
+    rrx.corpus_iid(d.data_ptr(), 0, n, cfg.seed, cfg.alpha)
+    torch.cuda.synchronize()
+    r = rrx.RRegex(cfg.pattern)
+    got = r.scan_device(d.data_ptr(), n)
+    assert np.all(np.diff(got[:, 1]) > 0) and np.all(got[:, 0] < got[:, 1]) and got[-1, 1] <= n
+    host = d[:n].cpu().numpy()
+    last = {3: ord("b"), 4: ord("c"), 5: ord("q")}[cfg_id]
+    prev_ok = {3: (ord("a"),), 4: (ord("a"), ord("b")), 5: None}[cfg_id]
+    # closed form of the end set: the last byte of the pattern preceded by a letter of the counted class
+    # (configs 3, 4) / preceded anywhere by a 'z' (config 5)
+    pos = np.nonzero(host == last)[0]
+    if prev_ok is not None:
+        pos = pos[pos > 0]
+        pos = pos[np.isin(host[pos - 1], prev_ok)]
+    else:
+        first_z = int(np.argmax(host == ord("z")))
+        pos = pos[pos > first_z]
+    assert np.array_equal(got[:, 1], pos + 1)
+    rx = re.compile(cfg.pattern.encode(), re.S)
+    for s_, e_ in got[np.linspace(0, len(got) - 1, 300).astype(int)]:
+        span = host[s_:e_].tobytes()
+        assert rx.fullmatch(span)
+        assert not any(rx.fullmatch(span[k:]) for k in range(1, min(len(span), 400)))     # lazy: no later start
+    # two pieces with the carried state == whole
+    cut = (n // 3) & ~4095
+    cap = len(got) + 1024
+    sc = rrx.Scanner(r, n, cap)
+    sc.scan(d.data_ptr(), cut)
+    left, summary = sc.matches(), sc.shard_summary()
+    entry = np.zeros(r.info["words"], dtype=np.uint32)
+    from roaringregex_b200 import sharded
+    entry = sharded.apply_summary(r, summary, entry)
+    sc.scan(d.data_ptr() + cut, n - cut, cut, cut, entry)
+    res = sc.result()
+    assert res["error_bits"] == 0 and res["n_pending"] == 0
+    both = np.concatenate([left, sc.matches()])
+    assert np.array_equal(both, got)
+    pre = 32 << 20
+    want = oracle_api.Oracle(cfg.pattern).lazy_matches(cpu_corpus(cfg, 0, pre))
+    assert np.array_equal(got[:len(want)], want)

@@ -295,6 +295,9 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         // the next few tiles of this warp do not try again.
         bool dense = true, published = false;
         Comp<NW> agg, acc, inc;
+        SparseTail tail;
+        tail.kq = tail.ks = tail.nacc = 0;
+        tail.drained = 1;
         if (sp.sparse) {
             if (dense_left == 0) {
                 const bool closed = phase_a_exit<NW>(sp, pv, fw, ts, lane);
@@ -310,7 +313,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
                         if (lane == 0) next_raw = atomicAdd(sp.ticket, 1u);
                         have_next = true;
                     }
-                    const bool ok = phase_a_cand<NW>(sp, pv, fw, ts, lane);
+                    const bool ok = phase_a_cand<NW>(sp, pv, fw, ts, lane, tail);
                     dense = __any_sync(FULL, !ok) != 0;
                 }
                 if (dense) dense_left = 4;
@@ -351,42 +354,72 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         }
         __syncwarp();
         RRX_T(4)
-        const uint32_t c = phase_b<NW>(sp, pv, fw, ts, lane, any_open);
-        // exclusive offsets of the rows' matches inside the tile
-        uint32_t inc_c = c;
+        // Fast tail: the sparse scan kept every match of every row in its register queue with a known
+        // start, and no row receives a carried state (its predecessor's exit / the tile entry is empty):
+        // nothing to replay, nothing to resolve — count, reserve, write.
+        bool fast = false;
+        if (!dense) {
+            uint32_t carried = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(FULL, inc_c, d);
-            if (lane >= d) inc_c += v;
-        }
-        const uint32_t total = __shfl_sync(FULL, inc_c, 31);
-        const uint32_t offset = inc_c - c;
-        RRX_T(5)
-        // reserve the tile's segment of the staging list; the hit list is built while the atomic is in flight
-        unsigned long long base = 0;
-        if (lane == 0 && total) base = atomicAdd(sp.total, (unsigned long long)total);
-        RRX_T(6)
-        if (total) {
-            uint32_t hit[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) hit[q] = ts.hits[q * TILE_ROWS + lane];
-            __syncwarp();                 // every lane is done with the row summaries: reuse as hit list
-            const bool fits = total <= (uint32_t)TS::LIST_CAP;
-            if (fits) phase_c1_list<NW>(ts, lane, offset, hit);
+            for (int w = 0; w < NW; w++) carried |= lane == 0 ? ts.misc[TS::M_ENTRY + w] : ts.sum_b[w * TILE_ROWS + lane - 1];
+            fast = __all_sync(FULL, tail.simple() && carried == 0) != 0;
+            if (!fast) sparse_drain<NW>(ts, lane, tail.kq, tail.ks);
             __syncwarp();
+        }
+        if (fast) {
+            uint32_t inc_c = tail.nacc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, inc_c, d);
+                if (lane >= d) inc_c += v;
+            }
+            const uint32_t total = __shfl_sync(FULL, inc_c, 31);
+            unsigned long long base = 0;
             if (lane == 0) {
+                if (total) base = atomicAdd(sp.total, (unsigned long long)total);
                 sp.tile_seg[tile] = base;
                 sp.tile_cnt[tile] = total;
             }
             base = __shfl_sync(FULL, base, 0);
-            if (fits) {
-                phase_c2_balanced<NW>(sp, pv, fw, ts, lane, total, base);
-            } else {
-                phase_c2_rows<NW>(sp, pv, fw, ts, lane, offset, hit, base);
+            phase_tail_fast<NW>(sp, ts, lane, tail, base + (inc_c - tail.nacc));
+        } else {
+            const uint32_t c = phase_b<NW>(sp, pv, fw, ts, lane, any_open);
+            // exclusive offsets of the rows' matches inside the tile
+            uint32_t inc_c = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, inc_c, d);
+                if (lane >= d) inc_c += v;
             }
-        } else if (lane == 0) {
-            sp.tile_seg[tile] = 0;
-            sp.tile_cnt[tile] = 0;
+            const uint32_t total = __shfl_sync(FULL, inc_c, 31);
+            const uint32_t offset = inc_c - c;
+            RRX_T(5)
+            // reserve the tile's segment of the staging list; the hit list is built while the atomic is in flight
+            unsigned long long base = 0;
+            if (lane == 0 && total) base = atomicAdd(sp.total, (unsigned long long)total);
+            RRX_T(6)
+            if (total) {
+                uint32_t hit[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) hit[q] = ts.hits[q * TILE_ROWS + lane];
+                __syncwarp();                 // every lane is done with the row summaries: reuse as hit list
+                const bool fits = total <= (uint32_t)TS::LIST_CAP;
+                if (fits) phase_c1_list<NW>(ts, lane, offset, hit);
+                __syncwarp();
+                if (lane == 0) {
+                    sp.tile_seg[tile] = base;
+                    sp.tile_cnt[tile] = total;
+                }
+                base = __shfl_sync(FULL, base, 0);
+                if (fits) {
+                    phase_c2_balanced<NW>(sp, pv, fw, ts, lane, total, base);
+                } else {
+                    phase_c2_rows<NW>(sp, pv, fw, ts, lane, offset, hit, base);
+                }
+            } else if (lane == 0) {
+                sp.tile_seg[tile] = 0;
+                sp.tile_cnt[tile] = 0;
+            }
         }
         __syncwarp();
         RRX_T(7)

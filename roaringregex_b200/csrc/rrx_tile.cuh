@@ -659,6 +659,36 @@ RRX_DEV bool phase_a_exit(const ScanParams& sp, const ProgView& pv, const F& fw,
     return true;
 }
 
+// What phase_a_cand leaves in registers: up to four match ends of the row (kq: end+1 per byte, most
+// recent in the low byte) with their lazy starts (ks: start+1, or 0 = not known).
+struct SparseTail {
+    uint32_t kq, ks, nacc, drained;
+    // every match of the row is in the queue and has a known start
+    RRX_DEV bool simple() const {
+        if (drained) return false;
+        const uint32_t m = nacc == 0 ? 0u : (0xffffffffu >> (32u - 8u * nacc));
+        const uint32_t v = ks | ~m;                              // bytes beyond the queue count as known
+        return (((v - 0x01010101u) & ~v) & 0x80808080u) == 0u;   // no zero byte
+    }
+};
+
+// Fast tail of a tile: the row's matches go from the queue straight to the output list, in text order
+// (oldest queue entry first), at slots slot0, slot0+1, ...
+template <int NW>
+RRX_DEV void phase_tail_fast(const ScanParams& sp, const TileState<NW>& ts, int t, const SparseTail& tail, unsigned long long slot0) {
+    const long long row_lo = sp.base + ts.lo() + ((long long)t << ROW_SHIFT);
+    for (uint32_t i = 0; i < tail.nacc; i++) {
+        const uint32_t sh = 8u * (tail.nacc - 1u - i);
+        const uint32_t e1 = (tail.kq >> sh) & 0xffu, s1 = (tail.ks >> sh) & 0xffu;
+        const unsigned long long slot = slot0 + i;
+        if (slot < sp.out_cap) {
+            long long* o = sp.out + 2 * slot;
+            o[0] = row_lo + (long long)s1 - 1;
+            o[1] = row_lo + (long long)e1;            // e1 = (end offset - 1) + 1
+        }
+    }
+}
+
 // Unpack the match-end queue of phase_a_cand into the row's hit mask (and its first two known starts).
 template <int NW>
 RRX_DEV void sparse_drain(TileState<NW>& ts, int t, uint32_t kq, uint32_t ks) {
@@ -679,7 +709,7 @@ RRX_DEV void sparse_drain(TileState<NW>& ts, int t, uint32_t kq, uint32_t ks) {
 }
 
 template <int NW, class F>
-RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t) {
+RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t, SparseTail& tail) {
     constexpr int ROWS = TILE_ROWS;
     const ProgHeader& h = pv.h();
     const uint32_t ngr = fw.sp_ngroups(pv), cand = fw.sp_cand(pv);
@@ -720,7 +750,7 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
     int budget = SPARSE_BUDGET;         // backward verification steps this row may spend
     uint32_t p = 0;
     uint32_t rs1 = 0;                   // 1 + lazy start of every match of the current run, or 0: not known
-    uint32_t kq = 0, ks = 0, nacc = 0;
+    uint32_t kq = 0, ks = 0, nacc = 0, drained = 0;
     uint32_t bail = ncand > SPARSE_MAX_CAND ? 1u : 0u;
     uint32_t live = 0;                  // OR of the words of H
     uint32_t work = bail ? 0u : (uint32_t)ncand;     // non-zero while the lane has something left to do
@@ -733,6 +763,7 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
         if (work != 0 && nacc >= 4) {
             sparse_drain<NW>(ts, t, kq, ks);
             kq = ks = nacc = 0;
+            drained = 1u;
         } else if (work != 0) {
             const uint32_t fresh = live == 0 ? 1u : 0u;
             if (fresh) {
@@ -830,7 +861,13 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
         work = live | (uint32_t)ncand;
     }
     if (bail) return false;
-    sparse_drain<NW>(ts, t, kq, ks);
+    // The queue is handed to the caller: a tile whose rows all kept their matches in the queue, with
+    // known starts, and whose rows receive no carried state writes them straight from registers
+    // (phase_tail_fast); otherwise the caller drains it into the hit masks (sparse_drain).
+    tail.kq = kq;
+    tail.ks = ks;
+    tail.nacc = nacc;
+    tail.drained = drained;
     return true;
 }
 

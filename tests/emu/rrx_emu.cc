@@ -22,7 +22,7 @@ namespace {
 // 0: dense row scans only; 1: candidate-driven row scan with dense fallback, as the kernel does;
 // 2: run both on every tile and report (err bit 0x80) any row where they disagree
 int g_sparse_mode = 1;
-unsigned long long g_sparse_rows = 0, g_dense_rows = 0;
+unsigned long long g_sparse_rows = 0, g_dense_rows = 0, g_fast_tiles = 0;
 
 template <int NW, int NT, int NB>
 int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t len, int64_t base,
@@ -89,6 +89,8 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
         bool sp_ok[ROWS];
         uint32_t sp_hits[ROWS][4], sp_b[ROWS][NW];
         uint16_t sp_kst[ROWS][2];
+        SparseTail tails[ROWS];
+        for (int t = 0; t < ROWS; t++) { tails[t].kq = tails[t].ks = tails[t].nacc = 0; tails[t].drained = 1; }
         if (h.sparse_ok && g_sparse_mode) {
             // as the kernel: exit sets first; candidates only if every row of the tile is closed
             bool all_closed = true;
@@ -105,9 +107,10 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
                     ProgView pv = view(t);
                     Prog<NW, NT, NB> fw;
                     fw.init(pv);
-                    sp_ok[t] = phase_a_cand<NW>(sp, pv, fw, ts, t);
+                    sp_ok[t] = phase_a_cand<NW>(sp, pv, fw, ts, t, tails[t]);
                     if (!sp_ok[t]) dense = true;
-                    else {
+                    else if (g_sparse_mode == 2) {
+                        sparse_drain<NW>(ts, t, tails[t].kq, tails[t].ks);      // materialise for the comparison
                         if (ts.sum_kind[t] != K_CLOSED) *err |= 0x80u;
                         for (int q = 0; q < 4; q++) sp_hits[t][q] = ts.hits[q * ROWS + t];
                         for (int w = 0; w < NW; w++) sp_b[t][w] = ts.sum_b[w * ROWS + t];
@@ -160,6 +163,24 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
             if (tile + 1 == num_tiles) store_comp_global<NW>(sp.shard_comp, inc);
         }
         uint32_t cnt[ROWS], off[ROWS], total_t = 0;
+        // fast tail, as in the kernel: every row simple and without carried state
+        bool fast = !dense;
+        if (!dense) {
+            for (int t = 0; t < ROWS; t++) {
+                uint32_t carried = 0;
+                for (int w = 0; w < NW; w++) carried |= t == 0 ? ts.misc[TS::M_ENTRY + w] : ts.sum_b[w * ROWS + t - 1];
+                if (!tails[t].simple() || carried) fast = false;
+            }
+            if (!fast) for (int t = 0; t < ROWS; t++) sparse_drain<NW>(ts, t, tails[t].kq, tails[t].ks);
+        }
+        if (fast) {
+            g_fast_tiles++;
+            for (int t = 0; t < ROWS; t++) { off[t] = total_t; total_t += tails[t].nacc; }
+            for (int t = 0; t < ROWS; t++) phase_tail_fast<NW>(sp, ts, t, tails[t], matches_so_far + off[t]);
+            matches_so_far += total_t;
+            if (tile + 1 == num_tiles) total[0] = matches_so_far;
+            continue;
+        }
         for (int t = 0; t < ROWS; t++) {
             ProgView pv = view(t);
             Prog<NW, NT, NB> fw;
@@ -250,8 +271,8 @@ uint32_t emu_pending_size(void) { return (uint32_t)sizeof(PendingStart); }
 void emu_set_sparse(int mode) { g_sparse_mode = mode; }
 // rows handled by the candidate-driven scan / by the dense scan since the last call (sparse-capable programs only)
 void emu_sparse_stats(unsigned long long* out, int reset) {
-    out[0] = g_sparse_rows; out[1] = g_dense_rows;
-    if (reset) g_sparse_rows = g_dense_rows = 0;
+    out[0] = g_sparse_rows; out[1] = g_dense_rows; out[2] = g_fast_tiles;
+    if (reset) g_sparse_rows = g_dense_rows = g_fast_tiles = 0;
 }
 
 }  // extern "C"

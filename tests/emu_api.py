@@ -42,9 +42,14 @@ def set_sparse(mode: int):
 
 
 def sparse_stats(reset=True):
-    out = np.zeros(2, dtype=np.uint64)
+    out = np.zeros(3, dtype=np.uint64)
     _lib().emu_sparse_stats(out.ctypes.data, int(reset))
+    global last_fast_tiles
+    last_fast_tiles = int(out[2])
     return int(out[0]), int(out[1])
+
+
+last_fast_tiles = 0
 
 
 def scan(pattern: str, text, reduce=True, fast=True, left_ctx=0, base=0, entry=None, cap=None):

@@ -46,6 +46,18 @@ template <int NW, int WARPS_> struct KCfg {
 // inclusive value — the producer only ever waits on smaller tile indices).
 // =====================================================================================================
 constexpr unsigned FULL = 0xffffffffu;
+// One lane's atomic add as ONE instruction: atomicAdd() would wrap it in warp-aggregation code
+// (vote, leader election, popc, shuffle) although only lane 0 ever calls it here.
+__device__ __forceinline__ uint32_t atom_add_u32(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ unsigned long long atom_add_u64(unsigned long long* p, unsigned long long v) {
+    unsigned long long old;
+    asm volatile("atom.global.add.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+    return old;
+}
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -111,7 +123,7 @@ __device__ __forceinline__ void lookback_publish(const ScanParams& sp, uint32_t 
     if (lane == 0) {
         publish_comp<NW>(sp.st_a0, sp.f_a0, tile, agg);
         if (NW > 1) __threadfence();
-        old = atomicAdd(sp.st_arrive + b, 1u);
+        old = atom_add_u32(sp.st_arrive + b, 1u);
     }
     old = __shfl_sync(FULL, old, 0);
     if (old == nblk - 1) {                                  // fold the block aggregate, in tile order
@@ -242,14 +254,14 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
     const uint32_t warps_in_flight = gridDim.x * (uint32_t)K::WARPS;
     int dense_left = 0;
     uint32_t tile = 0;
-    if (lane == 0) tile = atomicAdd(sp.ticket, 1u);
+    if (lane == 0) tile = atom_add_u32(sp.ticket, 1u);
     tile = __shfl_sync(FULL, tile, 0);
     for (;;) {
         if (tile >= sp.num_tiles) break;
         uint32_t next_raw = 0;
         bool have_next = false;
         if (sp.ticket_ahead == 2) {
-            if (lane == 0) next_raw = atomicAdd(sp.ticket, 1u);
+            if (lane == 0) next_raw = atom_add_u32(sp.ticket, 1u);
             have_next = true;
         } else {
             // guess which tile some warp will pick up about one round from now, and ask L2 for it
@@ -310,7 +322,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
                     lookback_publish<NW>(sp, tile, agg, lane);
                     published = true;
                     if (sp.ticket_ahead == 1) {
-                        if (lane == 0) next_raw = atomicAdd(sp.ticket, 1u);
+                        if (lane == 0) next_raw = atom_add_u32(sp.ticket, 1u);
                         have_next = true;
                     }
                     const bool ok = phase_a_cand<NW>(sp, pv, fw, ts, lane, tail);
@@ -376,7 +388,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             const uint32_t total = __shfl_sync(FULL, inc_c, 31);
             unsigned long long base = 0;
             if (lane == 0) {
-                if (total) base = atomicAdd(sp.total, (unsigned long long)total);
+                if (total) base = atom_add_u64(sp.total, (unsigned long long)total);
                 sp.tile_seg[tile] = base;
                 sp.tile_cnt[tile] = total;
             }
@@ -396,7 +408,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             RRX_T(5)
             // reserve the tile's segment of the staging list; the hit list is built while the atomic is in flight
             unsigned long long base = 0;
-            if (lane == 0 && total) base = atomicAdd(sp.total, (unsigned long long)total);
+            if (lane == 0 && total) base = atom_add_u64(sp.total, (unsigned long long)total);
             RRX_T(6)
             if (total) {
                 uint32_t hit[4];
@@ -424,7 +436,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         __syncwarp();
         RRX_T(7)
         if (!have_next) {
-            if (lane == 0) next_raw = atomicAdd(sp.ticket, 1u);
+            if (lane == 0) next_raw = atom_add_u32(sp.ticket, 1u);
             next_tile = __shfl_sync(FULL, next_raw, 0);
         }
         tile = next_tile;

@@ -87,15 +87,34 @@ __global__ void __launch_bounds__(CHUNK) gather_kernel(const uint32_t* tile_cnt,
     const unsigned long long v = t < num_tiles ? tile_cnt[t] : 0u;
     off[threadIdx.x] = chunk_off[blockIdx.x] + block_excl_1024(v, sh, nullptr);
     __syncthreads();
+    // Every warp moves the segments of its 32 consecutive tiles.  The copy is flattened over the
+    // matches of those tiles — element e of the warp's output range belongs to the tile j with
+    // pre[j] <= e < pre[j+1], found by a 5-step search over the lanes' prefix sums — so that all 32
+    // lanes copy in every iteration, the stores are contiguous and the loads independent.
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = warp; i < CHUNK; i += 32) {
-        const uint32_t tt = blockIdx.x * CHUNK + i;
-        if (tt >= num_tiles) break;
-        const uint32_t n = tile_cnt[tt];
-        if (!n) continue;
-        const unsigned long long src = tile_seg[tt], dst = off[i];
-        for (uint32_t k = lane; k < n; k += 32)
-            if (src + k < cap && dst + k < cap) out[dst + k] = staging[src + k];
+    const uint32_t tt = blockIdx.x * CHUNK + warp * 32 + lane;
+    const uint32_t n = tt < num_tiles ? tile_cnt[tt] : 0u;
+    const unsigned long long src = tt < num_tiles ? tile_seg[tt] : 0ull;
+    uint32_t inc = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += u;
+    }
+    const uint32_t pre = inc - n, E = __shfl_sync(0xffffffffu, inc, 31);
+    const unsigned long long dst0 = off[warp * 32];
+    for (uint32_t e0 = 0; e0 < E; e0 += 32) {
+        const uint32_t e = e0 + lane;
+        int j = 0;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            const uint32_t pc = __shfl_sync(0xffffffffu, pre, j + s);
+            if (pc <= e) j += s;
+        }
+        const unsigned long long sj = __shfl_sync(0xffffffffu, src, j);
+        const uint32_t pj = __shfl_sync(0xffffffffu, pre, j);
+        const unsigned long long from = sj + (e - pj), to = dst0 + e;
+        if (e < E && from < cap && to < cap) out[to] = staging[from];
     }
 }
 

@@ -271,7 +271,9 @@ int rrx_scanner_create_ex(const rrx_program* p, uint64_t max_len, uint64_t capac
     RRX_CUDA(cudaMalloc(&s->d_ctrl, s->ctrl_bytes));
     RRX_CUDA(cudaMalloc(&s->d_tpay, (2 * s->max_tiles + 2 * ((s->max_tiles + 31) / 32)) * (1 + 3 * (size_t)h.NW) * 4));
     RRX_CUDA(cudaMalloc(&s->d_out, s->capacity * 16));
-    RRX_CUDA(cudaMalloc(&s->d_stage, s->capacity * 16));
+    // staging list: fixed slots for tiles with few matches (at most capacity/2, see rrx_scanner_scan) in
+    // front of an overflow area that can hold every match
+    RRX_CUDA(cudaMalloc(&s->d_stage, (s->capacity + s->capacity / 2 + 64) * 16));
     RRX_CUDA(cudaMalloc(&s->d_tile_seg, s->max_tiles * 8));
     RRX_CUDA(cudaMalloc(&s->d_tile_cnt, s->max_tiles * 4));
     RRX_CUDA(cudaMalloc(&s->d_chunk, ((s->max_tiles + 1023) / 1024 + 1) * 8));
@@ -358,6 +360,15 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     sp.shard_comp = s->d_shard;
     sp.pending = s->d_pending;
     sp.pending_cap = s->pending_cap;
+    {
+        // fixed staging slots for tiles with few matches: at most half of the staging list, 8..64 per tile
+        uint64_t stride = sp.num_tiles ? s->capacity / (2ull * sp.num_tiles) : 0;
+        if (stride > 64) stride = 64;
+        if (stride < 8 || getenv("RRX_NO_FIXED_SLOTS")) stride = 0;
+        sp.seg_stride = (uint32_t)stride;
+        sp.ovf_base = stride * sp.num_tiles;          // <= capacity / 2
+        sp.out_cap = sp.ovf_base + s->capacity;       // staging slots
+    }
     if (opts && opts->entry) for (uint32_t w = 0; w < h.NW; w++) sp.entry[w] = opts->entry[w];
     s->launches = 0;
     s->h_shard_valid = false;
@@ -375,7 +386,8 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     cudaError_t e = s->jit ? jit_launch(s->jit, sp, s->sm_count, st, &grid) : launch_scan(sp, h, s->sm_count, st, &grid);
     if (e != cudaSuccess) return cuda_err(e, "rrx_scan_kernel launch");
     if (s->timing) RRX_CUDA(cudaEventRecord(s->ev1, st));
-    e = launch_order(s->d_tile_cnt, s->d_tile_seg, sp.num_tiles, s->d_chunk, s->d_stage, s->d_out, s->capacity, st);
+    e = launch_order(s->d_tile_cnt, s->d_tile_seg, sp.num_tiles, s->d_chunk, s->d_stage, sp.out_cap, s->d_out, s->capacity,
+                     reinterpret_cast<unsigned long long*>(s->d_ctrl + 24), st);
     if (e != cudaSuccess) return cuda_err(e, "ordering pass launch");
     s->launches = 4;
     return RRX_OK;
@@ -391,7 +403,13 @@ int rrx_scanner_result(rrx_scanner* s, rrx_scan_result* out, void* stream) {
     s->h_shard_valid = true;
     const uint32_t* w32 = reinterpret_cast<const uint32_t*>(s->h_ctr);
     out->error_bits = w32[1];
-    out->n_matches = s->h_ctr[1];
+    out->n_matches = s->h_ctr[3];            // written by the ordering pass (sum of the tile counts)
+    if (out->error_bits & ERR_STAGING_OVERFLOW) {
+        // the overflow area of the staging list ran out: report it as "more matches than capacity" so that
+        // callers take their resize-and-rescan path
+        out->error_bits &= ~(uint32_t)ERR_STAGING_OVERFLOW;
+        if (out->n_matches < 2 * s->capacity) out->n_matches = 2 * s->capacity;
+    }
     out->n_pending = s->h_ctr[2];
     out->capacity = s->capacity;
     out->launches = s->launches;
@@ -427,7 +445,18 @@ int rrx_scanner_copy_pending(rrx_scanner* s, void* host_out, uint64_t cap, uint6
     if (n > s->pending_cap) n = s->pending_cap;
     *n_out = n;
     if (n > cap) n = cap;
-    if (n && host_out) RRX_CUDA(cudaMemcpy(host_out, s->d_pending, n * sizeof(PendingStart), cudaMemcpyDeviceToHost));
+    if (n && host_out) {
+        RRX_CUDA(cudaMemcpy(host_out, s->d_pending, n * sizeof(PendingStart), cudaMemcpyDeviceToHost));
+        // (tile, rank in tile) -> index in the ordered match list: the ordering pass left every tile's
+        // offset in d_tile_seg
+        PendingStart* recs = reinterpret_cast<PendingStart*>(host_out);
+        for (uint64_t i = 0; i < n; i++) {
+            const uint64_t tile = recs[i].match_index >> 32, rank = recs[i].match_index & 0xffffffffull;
+            unsigned long long off = 0;
+            RRX_CUDA(cudaMemcpy(&off, s->d_tile_seg + tile, 8, cudaMemcpyDeviceToHost));
+            recs[i].match_index = off + rank;
+        }
+    }
     return RRX_OK;
 }
 int rrx_continue_starts(const rrx_program* p, const uint8_t* d_text, uint64_t len, uint64_t left_context, uint64_t base_offset,

@@ -196,6 +196,15 @@ __device__ __forceinline__ void lookback_wait(const ScanParams& sp, uint32_t til
     }
 }
 
+// First staging slot for a tile with `total` matches (lane 0 only; see ScanParams::seg_stride).
+__device__ __forceinline__ unsigned long long reserve_segment(const ScanParams& sp, uint32_t tile, uint32_t total) {
+    if (total == 0) return 0;
+    if (total <= sp.seg_stride) return (unsigned long long)tile * sp.seg_stride;
+    const unsigned long long b = sp.ovf_base + atom_add_u64(sp.total, (unsigned long long)total);
+    if (b + total > sp.out_cap) atomicOr(sp.err, ERR_STAGING_OVERFLOW);
+    return b;
+}
+
 #ifdef RRX_PHASE_TIMING
 #define RRX_T(i) { const long long now_ = clock64(); if (lane == 0 && sp.phase_cycles) atomicAdd(sp.phase_cycles + (i), (unsigned long long)(now_ - tprev_)); tprev_ = now_; }
 #else
@@ -253,14 +262,28 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
     // whenever tile times vary), so all other tiles take theirs when they are done.
     const uint32_t warps_in_flight = gridDim.x * (uint32_t)K::WARPS;
     int dense_left = 0;
+    // ticket_ahead == 3: no tickets at all — warp g of the grid takes tiles g, g + W, g + 2W, ...
+    // (W = warps in flight).  Every wait is still on a smaller tile index owned by a resident warp
+    // that reaches it before any larger one, so the look-back cannot deadlock; what is lost is
+    // dynamic balancing, what is won is one contended global atomic per tile.
+    const bool static_tiles = sp.ticket_ahead == 3;
     uint32_t tile = 0;
-    if (lane == 0) tile = atom_add_u32(sp.ticket, 1u);
-    tile = __shfl_sync(FULL, tile, 0);
+    if (static_tiles) {
+        tile = blockIdx.x * (uint32_t)K::WARPS + (uint32_t)warp;
+    } else {
+        if (lane == 0) tile = atom_add_u32(sp.ticket, 1u);
+        tile = __shfl_sync(FULL, tile, 0);
+    }
     for (;;) {
         if (tile >= sp.num_tiles) break;
         uint32_t next_raw = 0;
         bool have_next = false;
-        if (sp.ticket_ahead == 2) {
+        if (static_tiles) {
+            next_raw = tile + warps_in_flight;
+            have_next = true;
+            const int64_t g = (((int64_t)next_raw) * TILE_ROWS + lane) << ROW_SHIFT;
+            if (g < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp.text + g));
+        } else if (sp.ticket_ahead == 2) {
             if (lane == 0) next_raw = atom_add_u32(sp.ticket, 1u);
             have_next = true;
         } else {
@@ -340,7 +363,9 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             phase_a2<NW>(pv, fw, ts, lane);
         }
         uint32_t next_tile = 0;
-        if (have_next) {        // the next tile's ticket has arrived by now: ask L2 for its lines
+        if (static_tiles) {
+            next_tile = next_raw;
+        } else if (have_next) {        // the next tile's ticket has arrived by now: ask L2 for its lines
             next_tile = __shfl_sync(FULL, next_raw, 0);
             const int64_t g = (((int64_t)next_tile) * TILE_ROWS + lane) << ROW_SHIFT;
             if (g < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp.text + g));
@@ -388,7 +413,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             const uint32_t total = __shfl_sync(FULL, inc_c, 31);
             unsigned long long base = 0;
             if (lane == 0) {
-                if (total) base = atom_add_u64(sp.total, (unsigned long long)total);
+                base = reserve_segment(sp, tile, total);
                 sp.tile_seg[tile] = base;
                 sp.tile_cnt[tile] = total;
             }
@@ -408,7 +433,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             RRX_T(5)
             // reserve the tile's segment of the staging list; the hit list is built while the atomic is in flight
             unsigned long long base = 0;
-            if (lane == 0 && total) base = atom_add_u64(sp.total, (unsigned long long)total);
+            if (lane == 0) base = reserve_segment(sp, tile, total);
             RRX_T(6)
             if (total) {
                 uint32_t hit[4];

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(CHUNK) chunk_sums_kernel(const uint32_t* tile_
     if (threadIdx.x == 0) chunk_sum[blockIdx.x] = s;
 }
 
-__global__ void __launch_bounds__(CHUNK) chunk_scan_kernel(unsigned long long* chunk_sum, uint32_t nchunks) {
+__global__ void __launch_bounds__(CHUNK) chunk_scan_kernel(unsigned long long* chunk_sum, uint32_t nchunks, unsigned long long* n_total) {
     __shared__ unsigned long long sh[33];
     unsigned long long carry = 0;
     for (uint32_t base = 0; base < nchunks; base += CHUNK) {
@@ -76,11 +76,12 @@ __global__ void __launch_bounds__(CHUNK) chunk_scan_kernel(unsigned long long* c
         if (i < nchunks) chunk_sum[i] = carry + ex;
         carry += tot;
     }
+    if (threadIdx.x == 0 && n_total) *n_total = carry;       // number of matches of the scan
 }
 
-__global__ void __launch_bounds__(CHUNK) gather_kernel(const uint32_t* tile_cnt, const unsigned long long* tile_seg, uint32_t num_tiles,
-                                                       const unsigned long long* chunk_off, const longlong2* staging, longlong2* out,
-                                                       unsigned long long cap) {
+__global__ void __launch_bounds__(CHUNK) gather_kernel(const uint32_t* tile_cnt, const unsigned long long* tile_seg, unsigned long long* tile_seg_out, uint32_t num_tiles,
+                                                       const unsigned long long* chunk_off, const longlong2* staging,
+                                                       unsigned long long staging_cap, longlong2* out, unsigned long long cap) {
     __shared__ unsigned long long sh[33];
     __shared__ unsigned long long off[CHUNK];
     const uint32_t t = blockIdx.x * CHUNK + threadIdx.x;
@@ -114,21 +115,23 @@ __global__ void __launch_bounds__(CHUNK) gather_kernel(const uint32_t* tile_cnt,
         const unsigned long long sj = __shfl_sync(0xffffffffu, src, j);
         const uint32_t pj = __shfl_sync(0xffffffffu, pre, j);
         const unsigned long long from = sj + (e - pj), to = dst0 + e;
-        if (e < E && from < cap && to < cap) out[to] = staging[from];
+        if (e < E && from < staging_cap && to < cap) out[to] = staging[from];
     }
+    // leave the tile's offset in the ORDERED list behind (pending start scans refer to it)
+    if (tt < num_tiles) tile_seg_out[tt] = off[threadIdx.x];
 }
 
 }  // namespace
 
 cudaError_t launch_order(const uint32_t* tile_cnt, const unsigned long long* tile_seg, uint32_t num_tiles,
-                         unsigned long long* chunk_scratch, const long long* staging, long long* out, uint64_t cap,
-                         cudaStream_t st) {
+                         unsigned long long* chunk_scratch, const long long* staging, uint64_t staging_cap, long long* out, uint64_t cap,
+                         unsigned long long* n_total, cudaStream_t st) {
     if (!num_tiles) return cudaSuccess;
     const uint32_t nchunks = (num_tiles + CHUNK - 1) / CHUNK;
     chunk_sums_kernel<<<nchunks, CHUNK, 0, st>>>(tile_cnt, num_tiles, chunk_scratch);
-    chunk_scan_kernel<<<1, CHUNK, 0, st>>>(chunk_scratch, nchunks);
-    gather_kernel<<<nchunks, CHUNK, 0, st>>>(tile_cnt, tile_seg, num_tiles, chunk_scratch,
-                                             reinterpret_cast<const longlong2*>(staging), reinterpret_cast<longlong2*>(out), cap);
+    chunk_scan_kernel<<<1, CHUNK, 0, st>>>(chunk_scratch, nchunks, n_total);
+    gather_kernel<<<nchunks, CHUNK, 0, st>>>(tile_cnt, tile_seg, const_cast<unsigned long long*>(tile_seg), num_tiles, chunk_scratch,
+                                             reinterpret_cast<const longlong2*>(staging), staging_cap, reinterpret_cast<longlong2*>(out), cap);
     return cudaGetLastError();
 }
 

@@ -9,8 +9,8 @@ namespace rrx {
 struct ScanParams;
 cudaError_t launch_scan(const ScanParams& sp, const ProgHeader& h, int sm_count, cudaStream_t st, int* grid_out);
 cudaError_t launch_order(const uint32_t* tile_cnt, const unsigned long long* tile_seg, uint32_t num_tiles,
-                         unsigned long long* chunk_scratch, const long long* staging, long long* out, uint64_t cap,
-                         cudaStream_t st);
+                         unsigned long long* chunk_scratch, const long long* staging, uint64_t staging_cap, long long* out, uint64_t cap,
+                         unsigned long long* n_total, cudaStream_t st);
 cudaError_t launch_continue_starts(uint32_t NW, const uint32_t* d_prog, const uint8_t* d_text, uint64_t len, uint64_t left_ctx,
                                    uint64_t base, void* d_recs, uint64_t n, long long* d_start_out, cudaStream_t st);
 cudaError_t launch_accepts(uint32_t NW, const uint32_t* d_prog, const uint8_t* d_text, uint64_t len, int* d_out, cudaStream_t st);

@@ -51,7 +51,7 @@ constexpr int TILE_BYTES = TILE_ROWS * ROW_BYTES;     // 4 KiB
 constexpr int ROW_PITCH = 132;
 
 // error bits reported by the kernel
-enum : uint32_t { ERR_PENDING_OVERFLOW = 2u };
+enum : uint32_t { ERR_PENDING_OVERFLOW = 2u, ERR_STAGING_OVERFLOW = 4u };
 
 // Kinds of chunk transfer functions S_out = A*S_in | b:
 //   K_CLOSED  A = 0: the exit does not depend on the entry
@@ -353,7 +353,8 @@ template <int NW> RRX_HD void comp_closed(Comp<NW>& c, const uint32_t* b, uint32
 // ---- scan parameters (kernel argument) ------------------------------------------------------------
 constexpr int RRX_NW_MAX = 32;
 struct PendingStart {           // a start scan that ran off the left edge of the available text
-    uint64_t match_index;       // slot in the output list
+    uint64_t match_index;       // (tile << 32) | rank of the match inside its tile; the host turns it into the
+                                // index in the ordered list (rrx_scanner_copy_pending)
     int64_t next_offset;        // shard-local offset of the next byte to consume (negative)
     uint32_t R[RRX_NW_MAX];     // backward set before consuming that byte
 };
@@ -389,7 +390,12 @@ struct ScanParams {
     uint32_t* tile_cnt;             // [tiles] matches of the tile
     long long* out;             // staging list of (start,end) pairs
     uint64_t out_cap;
-    unsigned long long* total;  // [0] matches so far (staging allocator), [1] pending count
+    unsigned long long* total;  // [0] staging slots handed out by the allocator, [1] pending count
+    // Staging slots.  A tile with at most seg_stride matches writes them at slot tile*seg_stride (no
+    // atomic, no waiting); a fuller tile takes a segment of the overflow area [ovf_base, out_cap) with one
+    // atomicAdd on total[0].  seg_stride == 0: every tile allocates.  The ordering pass compacts.
+    uint32_t seg_stride, pad2_;
+    unsigned long long ovf_base;
     uint32_t* err;
     uint32_t* shard_comp;       // [1+3*NW] composite of the whole shard (relative to an unknown entry)
     PendingStart* pending;
@@ -1111,7 +1117,7 @@ RRX_DEV uint32_t phase_b(const ScanParams& sp, const ProgView& pv, const F& fw, 
 // at shard-local offset e-1; stops at the first (= right-most) start that works: lazy.
 template <int NW, class F>
 RRX_DEV void resolve_and_write(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW>& ts,
-                               int64_t e, unsigned long long slot) {
+                               int64_t e, unsigned long long slot, uint32_t rank_in_tile) {
     uint32_t R[NW], Bc[NW], x[NW];
 #pragma unroll
     for (int w = 0; w < NW; w++) R[w] = fw.accept(pv, w);
@@ -1152,7 +1158,7 @@ RRX_DEV void resolve_and_write(const ScanParams& sp, const ProgView& pv, const F
         const unsigned long long k = atomicAdd(sp.total + 1, 1ull);
         if (k < sp.pending_cap) {
             PendingStart& ps = sp.pending[k];
-            ps.match_index = slot;
+            ps.match_index = ((uint64_t)(ts.row0 / TILE_ROWS) << 32) | rank_in_tile;
             ps.next_offset = j;
 #pragma unroll
             for (int w = 0; w < NW; w++) ps.R[w] = R[w];
@@ -1200,7 +1206,7 @@ RRX_DEV void phase_c2_balanced(const ScanParams& sp, const ProgView& pv, const F
     for (uint32_t i = (uint32_t)lane; i < total; i += TILE_ROWS) {
         const uint32_t rel = ts.list[i];
         const int64_t e = ts.lo() + (int64_t)rel + 1;
-        if (!write_known<NW>(sp, ts, rel, base + i)) resolve_and_write<NW>(sp, pv, fw, ts, e, base + i);
+        if (!write_known<NW>(sp, ts, rel, base + i)) resolve_and_write<NW>(sp, pv, fw, ts, e, base + i, i);
     }
 }
 // C2 fallback (per lane): every row resolves its own matches (tiles with more hits than the list holds).
@@ -1214,7 +1220,7 @@ RRX_DEV void phase_c2_rows(const ScanParams& sp, const ProgView& pv, const F& fw
         while (v) {
             const int p = q * 32 + ctz32(v);
             v &= v - 1;
-            if (!write_known<NW>(sp, ts, ((uint32_t)t << ROW_SHIFT) + (uint32_t)p, slot)) resolve_and_write<NW>(sp, pv, fw, ts, row_lo + p + 1, slot);
+            if (!write_known<NW>(sp, ts, ((uint32_t)t << ROW_SHIFT) + (uint32_t)p, slot)) resolve_and_write<NW>(sp, pv, fw, ts, row_lo + p + 1, slot, (uint32_t)(slot - base));
             slot++;
         }
     }

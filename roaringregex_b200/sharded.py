@@ -98,7 +98,7 @@ class DeviceBackend:
         g = comm.allgather_device(self._msg)                    # (world, nw) uint32 on the host
         mine = g[comm.dist.get_rank()]
         ctr = mine[1 + 3 * W:]
-        err, n_matches, n_pending = int(ctr[1]), int(ctr[2]) | (int(ctr[3]) << 32), int(ctr[4]) | (int(ctr[5]) << 32)
+        err, n_matches, n_pending = int(ctr[1]), int(ctr[6]) | (int(ctr[7]) << 32), int(ctr[4]) | (int(ctr[5]) << 32)
         if err:
             raise RuntimeError(f"scan kernel error bits {err}")
         if n_matches > self.capacity:

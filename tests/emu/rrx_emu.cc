@@ -38,6 +38,7 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
     for (uint32_t i = 0; i < btab.size(); i++) btab[i] = prog.blob[h.off_B + (NW == 1 ? (i >> 5) : i)];
     std::vector<uint32_t> incl((size_t)(num_tiles + 1) * (1 + 3 * NW), 0);   // inclusive composite per tile
     unsigned long long matches_so_far = 0;
+    std::vector<unsigned long long> tile_base(num_tiles + 1, 0);
     unsigned long long total[2] = {0, 0};
     uint32_t ticket = 0;
     *err = 0;
@@ -173,6 +174,7 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
             }
             if (!fast) for (int t = 0; t < ROWS; t++) sparse_drain<NW>(ts, t, tails[t].kq, tails[t].ks);
         }
+        tile_base[tile] = matches_so_far;
         if (fast) {
             g_fast_tiles++;
             for (int t = 0; t < ROWS; t++) { off[t] = total_t; total_t += tails[t].nacc; }
@@ -211,6 +213,11 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
                 }
             }
         }
+    }
+    // (tile, rank in tile) -> index in the ordered list, as rrx_scanner_copy_pending does
+    for (unsigned long long i = 0; i < total[1] && i < pending_cap; i++) {
+        const uint64_t tl = pending[i].match_index >> 32, rank = pending[i].match_index & 0xffffffffull;
+        pending[i].match_index = tile_base[tl] + rank;
     }
     counts[0] = total[0];
     counts[1] = total[1];

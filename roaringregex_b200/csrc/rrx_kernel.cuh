@@ -114,17 +114,24 @@ template <int NW> __device__ __forceinline__ void wait_comp(const uint32_t* pay,
 // A tile whose aggregate is known early (all rows closed: the exit of its last row) publishes
 // before it looks for matches, so that its successors rarely wait.
 template <int NW>
-__device__ __forceinline__ void lookback_publish(const ScanParams& sp, uint32_t tile, const Comp<NW>& agg, int lane) {
-    const uint32_t b = tile >> 5;
-    const uint32_t rest = sp.num_tiles - (b << 5);
-    const uint32_t nblk = rest < 32u ? rest : 32u;
-    Comp<NW> mine, x, nxt;
+__device__ __forceinline__ uint32_t lookback_publish_issue(const ScanParams& sp, uint32_t tile, const Comp<NW>& agg, int lane) {
     uint32_t old = 0;
     if (lane == 0) {
         publish_comp<NW>(sp.st_a0, sp.f_a0, tile, agg);
         if (NW > 1) __threadfence();
-        old = atom_add_u32(sp.st_arrive + b, 1u);
+        old = atom_add_u32(sp.st_arrive + (tile >> 5), 1u);
     }
+    return old;        // lane 0: tiles of the block that had published before; consumed by lookback_publish_fold
+}
+// The LAST tile of a 32-tile block to arrive folds the block aggregate.  `old` is the value
+// lookback_publish_issue returned: keeping the two apart lets the atomic's latency hide behind
+// whatever the caller does in between.
+template <int NW>
+__device__ __forceinline__ void lookback_publish_fold(const ScanParams& sp, uint32_t tile, uint32_t old, int lane) {
+    const uint32_t b = tile >> 5;
+    const uint32_t rest = sp.num_tiles - (b << 5);
+    const uint32_t nblk = rest < 32u ? rest : 32u;
+    Comp<NW> mine, x, nxt;
     old = __shfl_sync(FULL, old, 0);
     if (old == nblk - 1) {                                  // fold the block aggregate, in tile order
         comp_ident(mine);
@@ -142,6 +149,11 @@ __device__ __forceinline__ void lookback_publish(const ScanParams& sp, uint32_t 
         if (has_wait) fold.kind = K_WAIT;
         if (lane == 0) publish_comp<NW>(sp.st_a1, sp.f_a1, b, fold);
     }
+}
+template <int NW>
+__device__ __forceinline__ void lookback_publish(const ScanParams& sp, uint32_t tile, const Comp<NW>& agg, int lane) {
+    const uint32_t old = lookback_publish_issue<NW>(sp, tile, agg, lane);
+    lookback_publish_fold<NW>(sp, tile, old, lane);
 }
 template <int NW>
 __device__ __forceinline__ void lookback_wait(const ScanParams& sp, uint32_t tile, int lane, Comp<NW>& acc) {
@@ -277,7 +289,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
     for (;;) {
         if (tile >= sp.num_tiles) break;
         uint32_t next_raw = 0;
-        bool have_next = false;
+        bool have_next = false, late_ticket = false;
         if (static_tiles) {
             next_raw = tile + warps_in_flight;
             have_next = true;
@@ -342,13 +354,14 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
 #pragma unroll
                     for (int w = 0; w < NW; w++) bl[w] = ts.sum_b[w * TILE_ROWS + (TILE_ROWS - 1)];
                     comp_closed(agg, bl, 0);
-                    lookback_publish<NW>(sp, tile, agg, lane);
+                    const uint32_t arrived = lookback_publish_issue<NW>(sp, tile, agg, lane);
                     published = true;
                     if (sp.ticket_ahead == 1) {
                         if (lane == 0) next_raw = atom_add_u32(sp.ticket, 1u);
                         have_next = true;
                     }
                     const bool ok = phase_a_cand<NW>(sp, pv, fw, ts, lane, tail);
+                    lookback_publish_fold<NW>(sp, tile, arrived, lane);       // the arrival count has long come back
                     dense = __any_sync(FULL, !ok) != 0;
                 }
                 if (dense) dense_left = 4;
@@ -381,6 +394,11 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             lookback_publish<NW>(sp, tile, agg, lane);
         }
         lookback_wait<NW>(sp, tile, lane, acc);
+        if (sp.ticket_ahead == 4 && !have_next) {       // the tile's tail is short: take the next ticket now
+            if (lane == 0) next_raw = atom_add_u32(sp.ticket, 1u);
+            have_next = true;
+            late_ticket = true;
+        }
         RRX_T(3)
         if (lane == 0) {
             phase_s2<NW>(sp, pv, fw, ts, L, acc, inc);
@@ -462,6 +480,8 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         RRX_T(7)
         if (!have_next) {
             if (lane == 0) next_raw = atom_add_u32(sp.ticket, 1u);
+            next_tile = __shfl_sync(FULL, next_raw, 0);
+        } else if (late_ticket) {
             next_tile = __shfl_sync(FULL, next_raw, 0);
         }
         tile = next_tile;

@@ -150,6 +150,8 @@ int rrx_scanner_message_device(rrx_scanner* s, uint32_t* d_out, uint64_t cap_wor
  * with): the caller must then rescan that shard with its exact entry and fold again. */
 int rrx_fold_entry(const rrx_program* p, const uint32_t* summaries, uint32_t n_shards, uint32_t rank,
                    uint32_t* entry_out, int* exact);
+/* The same for every shard at once: entries_out[n_shards][W], exact_out[n_shards]. */
+int rrx_fold_entries(const rrx_program* p, const uint32_t* summaries, uint32_t n_shards, uint32_t* entries_out, int* exact_out);
 /* exit = summary applied to entry (both words32 per rrx_info.words). */
 int rrx_apply_summary(const rrx_program* p, const uint32_t* summary, const uint32_t* entry, uint32_t* exit_out);
 /* Pending start scans of the last scan (those that ran off the left edge of the readable text):

@@ -102,6 +102,7 @@ def lib() -> C.CDLL:
         "rrx_scanner_copy_matches": (C.c_int, [vp, vp, u64, vp]),
         "rrx_scanner_copy_pending": (C.c_int, [vp, vp, u64, C.POINTER(u64), vp]),
         "rrx_fold_entry": (C.c_int, [vp, vp, u32, u32, vp, C.POINTER(C.c_int)]),
+        "rrx_fold_entries": (C.c_int, [vp, vp, u32, vp, vp]),
         "rrx_apply_summary": (C.c_int, [vp, vp, vp, vp]),
         "rrx_continue_starts": (C.c_int, [vp, vp, u64, u64, u64, vp, u64, vp, vp]),
         "rrx_corpus_iid_device": (C.c_int, [vp, u64, u64, u64, vp, vp]),
@@ -153,9 +154,12 @@ class RRegex:
     # -- introspection -------------------------------------------------------------------------
     @property
     def info(self) -> dict:
-        i = _Info()
-        lib().rrx_program_info(self._h, C.byref(i))
-        return {n: int(getattr(i, n)) for n, _ in _Info._fields_}
+        cached = getattr(self, "_info", None)           # the program is immutable
+        if cached is None:
+            i = _Info()
+            lib().rrx_program_info(self._h, C.byref(i))
+            cached = self._info = {n: int(getattr(i, n)) for n, _ in _Info._fields_}
+        return dict(cached)
 
     def flat_table(self, which: int) -> np.ndarray:
         need = -lib().rrx_program_flat_table(self._h, which, None, 0)

@@ -431,6 +431,12 @@ int rrx_fold_entry(const rrx_program* p, const uint32_t* summaries, uint32_t n_s
     fold_entry_host(p->prog.hdr().NW, summaries, n_shards, rank, entry_out, exact);
     return RRX_OK;
 }
+int rrx_fold_entries(const rrx_program* p, const uint32_t* summaries, uint32_t n_shards, uint32_t* entries_out, int* exact_out) {
+    if (!p || !summaries || !entries_out || !exact_out) return set_err(RRX_ERR_ARG, "null argument");
+    const uint32_t W = p->prog.hdr().NW;
+    for (uint32_t r = 0; r < n_shards; r++) fold_entry_host(W, summaries, n_shards, r, entries_out + (size_t)r * W, exact_out + r);
+    return RRX_OK;
+}
 int rrx_apply_summary(const rrx_program* p, const uint32_t* summary, const uint32_t* entry, uint32_t* exit_out) {
     if (!p || !summary || !entry || !exit_out) return set_err(RRX_ERR_ARG, "null argument");
     apply_summary_host(p->prog.hdr().NW, summary, entry, exit_out);

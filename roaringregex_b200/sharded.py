@@ -47,6 +47,9 @@ class DeviceBackend:
         self.regex, self.ptr, self.len, self.base, self.halo, self.stream = regex, d_text_ptr, shard_len, base, halo, stream
         self.capacity = capacity
         self.scanner = Scanner(regex, shard_len, capacity)
+        self.scanners = [self.scanner, None]      # the second one is created when steps are pipelined
+        self._msgs = [None, None]
+        self._turn = 0
         self.prefix_scanner = None
         self.words = regex.info["words"]
 
@@ -80,22 +83,32 @@ class DeviceBackend:
                 pend.append((int(mi), self.base + int(nxt), np.frombuffer(rec[16:].tobytes(), dtype=np.uint32).copy()))
         return pend
 
-    def scan_gather(self, comm, fetch: bool):
-        """Speculative scan of the whole shard fused with the exchange: scan kernels, a device-side copy of
-        [composite | counters] and the all-gather are enqueued back to back on one stream; a single
-        device-to-host copy of the gathered messages then gives this rank its own counters and every
-        rank's composite.  One synchronisation per step.  -> (ShardScan, (world, 1+3W+1) uint32 message
-        array in the format scan_sharded exchanges), or None if `comm` cannot gather device buffers."""
-        if not hasattr(comm, "allgather_device"):
+    def scan_gather_begin(self, comm):
+        """Enqueue — without waiting for anything — the speculative scan of the whole shard, a device-side
+        copy of [composite | counters], the all-gather of that message and the device-to-host copy of the
+        gathered messages, all on one stream.  Two sets of buffers alternate, so the next step may be
+        enqueued before this one has been collected (scan_gather_end).  Returns a token, or None if
+        `comm` cannot gather device buffers."""
+        if not hasattr(comm, "allgather_device_begin"):
             return None
         import torch
-        sc, W = self.scanner, self.words
+        slot = self._turn
+        self._turn ^= 1
+        if self.scanners[slot] is None:
+            self.scanners[slot] = Scanner(self.regex, self.len, self.capacity)
+        sc, W = self.scanners[slot], self.words
         nw = 1 + 3 * W + 8
-        if getattr(self, "_msg", None) is None:
-            self._msg = torch.zeros(nw, dtype=torch.int32, device="cuda")
+        if self._msgs[slot] is None:
+            self._msgs[slot] = torch.zeros(nw, dtype=torch.int32, device="cuda")
         sc.scan(self.ptr, self.len, self.base, self.halo, None, self.stream)
-        sc.message_device(self._msg.data_ptr(), nw, self.stream)
-        g = comm.allgather_device(self._msg)                    # (world, nw) uint32 on the host
+        sc.message_device(self._msgs[slot].data_ptr(), nw, self.stream)
+        return dict(slot=slot, scanner=sc, gather=comm.allgather_device_begin(self._msgs[slot], slot))
+
+    def scan_gather_end(self, comm, token, fetch: bool):
+        """Wait for the step enqueued by scan_gather_begin: ONE synchronisation (on the event behind
+        its device-to-host copy).  -> (ShardScan, (world, 1+3W+1) uint32 messages as scan_sharded exchanges)."""
+        sc, W = token["scanner"], self.words
+        g = comm.allgather_device_end(token["gather"])          # (world, nw) uint32 on the host
         mine = g[comm.dist.get_rank()]
         ctr = mine[1 + 3 * W:]
         err, n_matches, n_pending = int(ctr[1]), int(ctr[6]) | (int(ctr[7]) << 32), int(ctr[4]) | (int(ctr[5]) << 32)
@@ -143,6 +156,17 @@ def fold_entry(regex: RRegex, summaries: np.ndarray, rank: int):
     return entry, bool(exact.value)
 
 
+def fold_entries(regex: RRegex, summaries: np.ndarray):
+    """fold_entry for every rank in one call -> [(entry, exact)] * world."""
+    w = regex.info["words"]
+    s = np.ascontiguousarray(summaries, dtype=np.uint32)
+    world = s.shape[0]
+    entries = np.zeros((world, w), dtype=np.uint32)
+    exact = np.zeros(world, dtype=np.int32)
+    _check(lib().rrx_fold_entries(regex._h, s.ctypes.data, world, entries.ctypes.data, exact.ctypes.data))
+    return [(entries[r], bool(exact[r])) for r in range(world)]
+
+
 def apply_summary(regex: RRegex, summary: np.ndarray, entry: np.ndarray) -> np.ndarray:
     w = regex.info["words"]
     out = np.zeros(w, dtype=np.uint32)
@@ -172,16 +196,28 @@ class ShardResult:
         return out
 
 
-def scan_sharded(regex: RRegex, backend, comm, rank: int, world: int, fetch: bool = False) -> ShardResult:
+def scan_sharded_begin(regex: RRegex, backend, comm):
+    """Enqueue one sharded step on the device and return at once (a token for scan_sharded_finish), or
+    None when the backend/communicator pair has no asynchronous path.  Steps begun back to back
+    overlap the host side of one with the device side of the next."""
+    return backend.scan_gather_begin(comm) if hasattr(backend, "scan_gather_begin") else None
+
+
+def scan_sharded_finish(regex: RRegex, backend, comm, rank: int, world: int, token, fetch: bool = False) -> "ShardResult":
+    return scan_sharded(regex, backend, comm, rank, world, fetch, _token=token)
+
+
+def scan_sharded(regex: RRegex, backend, comm, rank: int, world: int, fetch: bool = False, _token=None) -> ShardResult:
     """The per-rank procedure.  `comm.allgather(np.ndarray) -> (world, ...) ndarray` is the only
     collective on the data path: ONE message of 1+3W+1 words per rank (the shard summary and the
     number of unfinished start scans).  Everything else each rank derives locally from the gathered
     summaries (every rank can fold every other rank's entry), so in the common case — no entry set
     survives into any shard, no start scan crosses a halo — a step has exactly one collective.
     `comm.allgather_obj(obj)` (pickled, tiny) serves the rare hand-over of unfinished start scans."""
-    fused = backend.scan_gather(comm, fetch) if hasattr(backend, "scan_gather") else None
-    if fused is not None:
-        spec, first_gather = fused                                # scan + exchange already done, one sync
+    if _token is None:
+        _token = scan_sharded_begin(regex, backend, comm)
+    if _token is not None:
+        spec, first_gather = backend.scan_gather_end(comm, _token, fetch)    # scan + exchange already enqueued, one sync
     else:
         spec, first_gather = backend.scan(backend.len, None, fetch), None     # speculative: empty entry
     advertised, result, last_entry = spec, None, None
@@ -192,7 +228,7 @@ def scan_sharded(regex: RRegex, backend, comm, rank: int, world: int, fetch: boo
             msg = np.concatenate([advertised.summary.astype(np.uint32), np.array([len(spec.pending)], dtype=np.uint32)])
             gathered = comm.allgather(msg)
         summaries, spec_pending = gathered[:, :-1], gathered[:, -1]
-        folds = [fold_entry(regex, summaries, r) for r in range(world)]
+        folds = fold_entries(regex, summaries)
         entry, _ = folds[rank]
         if result is None or not np.array_equal(entry, last_entry):
             last_entry = entry
@@ -279,20 +315,31 @@ class TorchComm:
             torch.cuda.current_stream(self.device).synchronize()
         return self._h_out.numpy().view(np.uint32).reshape(world, n).copy()
 
-    def allgather_device(self, d_msg) -> np.ndarray:
-        """All-gather of a device tensor enqueued on the current stream; -> (world, n) uint32 on the host."""
+    def allgather_device_begin(self, d_msg, slot: int = 0):
+        """All-gather of a device tensor + copy of the result to pinned host memory, both enqueued on the
+        current stream; an event marks the end.  Two buffer sets (slot 0/1)."""
         import torch
         if self.device.type != "cuda":
             raise RuntimeError("device all-gather needs a CUDA communicator")
         n, world = d_msg.numel(), self.dist.get_world_size()
-        if getattr(self, "_dkey", None) != (n, world):
-            self._dkey = (n, world)
-            self._g_out = torch.empty(world * n, dtype=d_msg.dtype, device=self.device)
-            self._g_host = torch.empty(world * n, dtype=d_msg.dtype, pin_memory=True)
-        self.dist.all_gather_into_tensor(self._g_out, d_msg)
-        self._g_host.copy_(self._g_out, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return self._g_host.numpy().view(np.uint32).reshape(world, n).copy()
+        bufs = getattr(self, "_dbufs", None)
+        if bufs is None or bufs["key"] != (n, world):
+            bufs = self._dbufs = dict(key=(n, world),
+                                      g_out=[torch.empty(world * n, dtype=d_msg.dtype, device=self.device) for _ in range(2)],
+                                      g_host=[torch.empty(world * n, dtype=d_msg.dtype, pin_memory=True) for _ in range(2)],
+                                      ev=[torch.cuda.Event() for _ in range(2)])
+        self.dist.all_gather_into_tensor(bufs["g_out"][slot], d_msg)
+        bufs["g_host"][slot].copy_(bufs["g_out"][slot], non_blocking=True)
+        bufs["ev"][slot].record(torch.cuda.current_stream(self.device))
+        return (slot, n, world)
+
+    def allgather_device_end(self, handle) -> np.ndarray:
+        slot, n, world = handle
+        self._dbufs["ev"][slot].synchronize()
+        return self._dbufs["g_host"][slot].numpy().view(np.uint32).reshape(world, n).copy()
+
+    def allgather_device(self, d_msg) -> np.ndarray:
+        return self.allgather_device_end(self.allgather_device_begin(d_msg, 0))
 
     def allgather_obj(self, obj):
         out = [None] * self.dist.get_world_size()

@@ -37,6 +37,17 @@ def _worker(rank, world, port, cfg_id, n, q):
     res = None
     for _ in range(3):                                   # repeated steps reuse every buffer
         res = sharded.scan_sharded(regex, be, comm, rank, world, fetch=True)
+    first = res.to_host(be)
+    # software-pipelined steps (begin k+1 before finishing k) must give the same list every time
+    prev = None
+    for _ in range(4):
+        tok = sharded.scan_sharded_begin(regex, be, comm)
+        assert tok is not None
+        if prev is not None:
+            r = sharded.scan_sharded_finish(regex, be, comm, rank, world, prev, fetch=True)
+            assert np.array_equal(r.to_host(be), first)
+        prev = tok
+    res = sharded.scan_sharded_finish(regex, be, comm, rank, world, prev, fetch=True)
     q.put((rank, res.to_host(be), res.rescans))
     dist.barrier()
     dist.destroy_process_group()

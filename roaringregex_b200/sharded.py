@@ -53,8 +53,8 @@ class DeviceBackend:
         self.prefix_scanner = None
         self.words = regex.info["words"]
 
-    def scan(self, length: int, entry, fetch: bool, prefix: bool = False) -> ShardScan:
-        sc = self.scanner
+    def scan(self, length: int, entry, fetch: bool, prefix: bool = False, scanner=None) -> ShardScan:
+        sc = scanner or self.scanner
         if prefix:
             if self.prefix_scanner is None:
                 self.prefix_scanner = Scanner(self.regex, min(self.len, PREFIX_WINDOW), min(self.len, PREFIX_WINDOW) + 16, jit=False)
@@ -259,7 +259,10 @@ def _repair(regex, backend, spec: ShardScan, entry: np.ndarray, fetch: bool) -> 
         skip = a.n                                                # speculative matches ending inside the window
         pend = [("tail", i, nxt, R) for i, nxt, R in spec.pending if i >= skip] + [("head", i, nxt, R) for i, nxt, R in b.pending]
         return ShardResult(len(b.matches) + spec.n - skip, b.matches, skip, spec, 1, pend)
-    full = backend.scan(backend.len, entry, fetch)                # the entry's influence never died: rescan
+    # the entry's influence never died: rescan — into the buffers of the speculative scan it replaces
+    # (with pipelined steps the other scanner may already hold the next step)
+    kw = {"scanner": spec.handle} if isinstance(backend, DeviceBackend) and spec.handle is not None else {}
+    full = backend.scan(backend.len, entry, fetch, **kw)
     return ShardResult(full.n, np.zeros((0, 2), np.int64), 0, full, 2, [("tail", i, nxt, R) for i, nxt, R in full.pending])
 
 

@@ -626,6 +626,64 @@ Cut find_cut(const std::vector<Pos>& pos, const std::vector<Bits>& fol, const st
     return best;
 }
 
+// ---- reverse-walk skip state -----------------------------------------------------------------------
+// The lazy start scan walks the reversed automaton from the accepting positions:  x = R & B[c];
+// found if x meets first; R = rfollow'(x).  Explore the reverse state sets reachable from `accept`
+// (breadth first, bounded) and look for one that almost every byte leaves unchanged: in that state
+// the walk can run over the text looking only for the few bytes that matter ("z.*q": after the q the
+// state is {z, .} until a z turns up).
+struct RSkip {
+    uint32_t n = 0;
+    uint32_t bytes[2] = {0, 0};
+    Bits F;
+};
+
+RSkip find_reverse_skip(const std::vector<Pos>& pos, const std::vector<Bits>& rfol, const Bits& first, const Bits& accept) {
+    const uint32_t P = (uint32_t)pos.size();
+    std::vector<Bits> Bc(128, Bits(P));
+    for (uint32_t c = 0; c < 128; c++)
+        for (uint32_t k = 0; k < P; k++)
+            if ((pos[k].cls[c >> 6] >> (c & 63)) & 1ull) Bc[c].add(k);
+    auto step = [&](const Bits& R, uint32_t c, bool* hit) {
+        Bits x(P), nx(P);
+        for (uint32_t k : R.list()) if (Bc[c].has(k)) x.add(k);
+        *hit = x.intersects(first);
+        for (uint32_t k : x.list()) nx.unite(rfol[k]);
+        return nx;
+    };
+    std::vector<Bits> seen;
+    std::vector<Bits> queue;
+    queue.push_back(accept);
+    seen.push_back(accept);
+    RSkip best;
+    for (size_t qi = 0; qi < queue.size() && qi < 48; qi++) {
+        const Bits R = queue[qi];
+        if (!R.any()) continue;
+        std::vector<uint32_t> odd;           // bytes that change R or find a start
+        for (uint32_t c = 0; c < 128 && odd.size() <= 2; c++) {
+            bool hit = false;
+            Bits nx = step(R, c, &hit);
+            if (hit || !nx.equals(R)) odd.push_back(c);
+        }
+        if (odd.size() >= 1 && odd.size() <= 2 && (best.n == 0 || odd.size() < best.n)) {
+            best.n = (uint32_t)odd.size();
+            best.bytes[0] = odd[0];
+            best.bytes[1] = odd.size() > 1 ? odd[1] : odd[0];
+            best.F = R;
+        }
+        if (seen.size() < 96)
+            for (uint32_t c = 0; c < 128; c++) {
+                bool hit = false;
+                Bits nx = step(R, c, &hit);
+                if (hit || !nx.any()) continue;                 // the walk ends there
+                bool known = false;
+                for (auto& s : seen) if (s.equals(nx)) { known = true; break; }
+                if (!known) { seen.push_back(nx); queue.push_back(nx); }
+            }
+    }
+    return best;
+}
+
 }  // namespace
 
 Program build_program(const Automaton& a, const std::string& pattern, bool reduce) {
@@ -703,6 +761,10 @@ Program build_program(const Automaton& a, const std::string& pattern, bool reduc
     h.sparse_ok = cut.ok ? 1u : 0u;
     h.cand_byte = cut.byte;
     h.n_groups = cut.ok ? (uint32_t)cut.groups.size() : 0u;
+    const RSkip rskip = find_reverse_skip(pos, rfol, first, accept);
+    h.off_rskip = take(NW);
+    h.rskip_n = rskip.n;
+    h.rskip_bytes = rskip.bytes[0] | (rskip.bytes[1] << 8);
     h.off_B = take(256 * NW);
     h.off_follow = take(P * NW); h.off_rfollow = take(P * NW);
     h.off_rows = take(P * NW); h.off_rrows = take(P * NW);
@@ -725,6 +787,7 @@ Program build_program(const Automaton& a, const std::string& pattern, bool reduc
             pr.blob[o + 2 * NW] = cut.groups[g].flags;
         }
     }
+    if (rskip.n) put_bits(pr.blob, h.off_rskip, rskip.F, NW);
     auto put_decomp = [&](const Decomp& d, uint32_t o_terms, uint32_t o_bicl, uint32_t o_rowsrc, uint32_t o_rows) {
         for (size_t i = 0; i < d.terms.size(); i++) {
             uint32_t o = o_terms + (uint32_t)i * (1 + NW);

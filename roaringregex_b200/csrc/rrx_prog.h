@@ -41,7 +41,12 @@ struct ProgHeader {
     // {kmask[NW], pred[NW], flags} — the K positions grouped by predecessor set; flags bit 0: the
     // group's positions are first-positions (injected without looking back).
     uint32_t sparse_ok, cand_byte, n_groups, off_sparse;
-    uint32_t reserved[3];
+    // Reverse-walk skip state (lazy start scans, rrx_tile.cuh resolve_and_write): a reverse state set F
+    // (off_rskip, NW words) that every 7-bit byte except rskip_bytes[0..rskip_n) maps to itself without
+    // reaching a first-position.  While the backward walk is in F it only has to look for those bytes.
+    uint32_t rskip_n;           // 0: no such state; else 1 or 2
+    uint32_t rskip_bytes;       // byte0 | byte1 << 8
+    uint32_t off_rskip;
 };
 constexpr uint32_t RRX_MAX_GROUPS = 4;
 

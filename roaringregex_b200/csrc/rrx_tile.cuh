@@ -239,6 +239,10 @@ template <int NW> struct SparseFromSmem {
     RRX_DEV uint32_t sp_gk(const ProgView& pv, uint32_t g, int w) const { return pv.sm[pv.h().off_sparse + NW + g * (2 * NW + 1) + w]; }
     RRX_DEV uint32_t sp_gpred(const ProgView& pv, uint32_t g, int w) const { return pv.sm[pv.h().off_sparse + NW + g * (2 * NW + 1) + NW + w]; }
     RRX_DEV uint32_t sp_gflags(const ProgView& pv, uint32_t g) const { return pv.sm[pv.h().off_sparse + NW + g * (2 * NW + 1) + 2 * NW]; }
+    // reverse-walk skip state (rrx_prog.h)
+    RRX_DEV uint32_t rs_n(const ProgView& pv) const { return pv.h().rskip_n; }
+    RRX_DEV uint32_t rs_bytes(const ProgView& pv) const { return pv.h().rskip_bytes; }
+    RRX_DEV uint32_t rs_F(const ProgView& pv, int w) const { return pv.sm[pv.h().off_rskip + w]; }
 };
 
 // Follow policy.  NT >= 0: one-word automaton whose forward AND reverse decompositions (up to NT
@@ -1123,10 +1127,43 @@ RRX_DEV void resolve_and_write(const ScanParams& sp, const ProgView& pv, const F
     for (int w = 0; w < NW; w++) R[w] = fw.accept(pv, w);
     const int64_t tile_lo = ts.lo(), left_edge = -(int64_t)sp.left_ctx;
     bool pend = false, found = false, dead = false;
+    // Skip state: while R equals F, bytes other than b0/b1 (and below 0x80) neither find a start nor
+    // change R, so the walk just runs over them.
+    const uint32_t rsn = fw.rs_n(pv), rsb = fw.rs_bytes(pv);
+    const uint32_t b0 = rsb & 0xffu, b1 = (rsb >> 8) & 0xffu;
     // fast path: while the walk stays inside the tile (32-bit tile-relative offsets, shared memory)
     int rel = (int)(e - 1 - tile_lo);
     for (; rel >= 0; rel--) {
-        load_B<NW>(pv, ts.rel_byte((uint32_t)rel), Bc);
+        uint32_t c = ts.rel_byte((uint32_t)rel);
+        if (rsn) {
+            uint32_t d = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) d |= R[w] ^ fw.rs_F(pv, w);
+            if (d == 0) {
+                // bytes down to a word boundary, then whole words (SWAR: does the word hold b0, b1 or a
+                // byte >= 0x80?), then the bytes of the word that does
+                while (c != b0 && c != b1 && c < 128u && rel > 0 && (rel & 3) != 0) { rel--; c = ts.rel_byte((uint32_t)rel); }
+                if (c != b0 && c != b1 && c < 128u && rel >= 4 && (rel & 3) == 0) {
+                    const uint32_t* t32 = reinterpret_cast<const uint32_t*>(ts.text);
+                    const uint32_t B0 = b0 * 0x01010101u, B1 = b1 * 0x01010101u;
+                    int wi = (rel >> 2) - 1;                 // last whole word before byte rel
+                    for (; wi >= 0; wi--) {
+                        const uint32_t w = t32[wi + (wi >> 5)];          // 33 words per staged row
+                        const uint32_t x0 = w ^ B0, x1 = w ^ B1;
+                        const uint32_t z = ((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | w;
+                        if (z & 0x80808080u) break;
+                    }
+                    rel = wi * 4 + 3;                        // last byte of the word that stopped the run (or -1)
+                    if (rel < 0) break;                      // ran to the tile start inside F
+                    c = ts.rel_byte((uint32_t)rel);
+                    while (c != b0 && c != b1 && c < 128u && rel > 0) { rel--; c = ts.rel_byte((uint32_t)rel); }
+                } else {
+                    while (c != b0 && c != b1 && c < 128u && rel > 0) { rel--; c = ts.rel_byte((uint32_t)rel); }
+                }
+                if (c != b0 && c != b1 && c < 128u) { rel = -1; break; }      // ran to the tile start inside F
+            }
+        }
+        load_B<NW>(pv, c, Bc);
         uint32_t m = 0;
 #pragma unroll
         for (int w = 0; w < NW; w++) { x[w] = R[w] & Bc[w]; m |= x[w] & fw.first(pv, w); }
@@ -1139,7 +1176,17 @@ RRX_DEV void resolve_and_write(const ScanParams& sp, const ProgView& pv, const F
         // slow path: the walk left the tile; continue in global memory
         for (;;) {
             if (j < left_edge) { pend = true; break; }
-            load_B<NW>(pv, (uint32_t)sp.text[j], Bc);
+            uint32_t c = (uint32_t)sp.text[j];
+            if (rsn) {
+                uint32_t d = 0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) d |= R[w] ^ fw.rs_F(pv, w);
+                if (d == 0) {
+                    while (c != b0 && c != b1 && c < 128u && j > left_edge) { j--; c = (uint32_t)sp.text[j]; }
+                    if (c != b0 && c != b1 && c < 128u) { j = left_edge - 1; pend = true; break; }   // still in F at the edge
+                }
+            }
+            load_B<NW>(pv, c, Bc);
             uint32_t m = 0;
 #pragma unroll
             for (int w = 0; w < NW; w++) { x[w] = R[w] & Bc[w]; m |= x[w] & fw.first(pv, w); }

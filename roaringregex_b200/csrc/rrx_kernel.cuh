@@ -253,6 +253,8 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
     fw.init(pv);
     TS ts;
     ts.carve(regions + (size_t)warp * K::REGION);
+    // pad bytes behind every staged row: a byte that no position accepts (see phase_a_cand)
+    *reinterpret_cast<uint32_t*>(ts.text + lane * ROW_PITCH + ROW_BYTES) = 0xffffffffu;
     const int64_t len = (int64_t)sp.len;
 #ifdef RRX_PHASE_TIMING
     long long tprev_ = clock64();

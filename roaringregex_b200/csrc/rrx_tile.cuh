@@ -838,11 +838,14 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
         // ---- inner: plain steps while the run lives and no candidate byte comes up ----
         // (branch-free: every lane computes the step, lanes that are not in a run or stand on a
         // candidate byte just do not commit it)
-        // Two steps per vote: the second one is harmless for lanes that have stopped.
+        // Two steps per vote: the second one is harmless for lanes that have stopped.  There is no
+        // end-of-row test: the 4 pad bytes behind every staged row hold 0xff (set once per warp by the
+        // kernel; the emulator's fill pattern is >= 0x80 too), a byte no position accepts, so a run that
+        // reaches the row end dies there — and every candidate has been consumed by then.
         uint32_t go = nacc < 4 ? live : 0u;
 #define RRX_SPARSE_STEP()                                                                       \
         {                                                                                           \
-            const uint32_t c = rb.at(p & (uint32_t)(ROW_BYTES - 1));                                \
+            const uint32_t c = rb.at(p);                /* p == 128: the row's pad, a byte >= 0x80 */ \
             load_B<NW>(pv, c, Bc);                                                                  \
             fw.follow(pv, H, f);                                                                    \
             const bool step = go != 0 && c != cand;     /* c == cand: parked for the outer loop */  \
@@ -858,9 +861,7 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
             kq = take ? ((kq << 8) | p) : kq;                                                       \
             ks = take ? ((ks << 8) | rs1) : ks;                                                     \
             nacc += take ? 1u : 0u;                                                                 \
-            const bool end = step && p == (uint32_t)ROW_BYTES;                                      \
-            ncand = end ? 0 : ncand;                                                                \
-            live = step ? (end ? 0u : lv) : live;                                                   \
+            live = step ? lv : live;                    /* dies on the pad at the latest */          \
             go = (step && nacc < 4) ? live : 0u;        /* queue full: parked until drained */     \
         }
         while (RRX_WARP_ANY(go != 0)) {

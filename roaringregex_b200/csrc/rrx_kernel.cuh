@@ -385,16 +385,20 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             const int64_t g = (((int64_t)next_tile) * TILE_ROWS + lane) << ROW_SHIFT;
             if (g < len) asm volatile("prefetch.global.L2 [%0];" ::"l"(sp.text + g));
         }
-        const uint32_t my_kind = ts.sum_kind[lane];
-        const bool any_open = __any_sync(FULL, my_kind == K_RANK1 || my_kind == K_HARD) != 0;
-        __syncwarp();
+        // A tile that published early has 32 closed rows: its aggregate (= its inclusive composite, a
+        // closed map absorbs whatever precedes it) is the last row's exit, and row t's entry is row
+        // t-1's exit — phases S1/S2 have nothing to compute beyond the tile's entry set.
+        bool any_open = false;
         SLocal<NW> L;
-        if (lane == 0) { phase_s1<NW>(sp, pv, fw, ts, any_open, L); agg = L.run; } else { comp_ident(agg); }
-        RRX_T(2)
         if (!published) {
+            const uint32_t my_kind = ts.sum_kind[lane];
+            any_open = __any_sync(FULL, my_kind == K_RANK1 || my_kind == K_HARD) != 0;
+            __syncwarp();
+            if (lane == 0) { phase_s1<NW>(sp, pv, fw, ts, any_open, L); agg = L.run; } else { comp_ident(agg); }
             bcast_comp(agg, 0);
             lookback_publish<NW>(sp, tile, agg, lane);
         }
+        RRX_T(2)
         lookback_wait<NW>(sp, tile, lane, acc);
         if (sp.ticket_ahead == 4 && !have_next) {       // the tile's tail is short: take the next ticket now
             if (lane == 0) next_raw = atom_add_u32(sp.ticket, 1u);
@@ -403,7 +407,15 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         }
         RRX_T(3)
         if (lane == 0) {
-            phase_s2<NW>(sp, pv, fw, ts, L, acc, inc);
+            if (published) {
+                uint32_t E[NW];
+                comp_apply<NW>(acc, sp.entry, E);
+#pragma unroll
+                for (int w = 0; w < NW; w++) ts.misc[TS::M_ENTRY + w] = E[w];
+                inc = agg;
+            } else {
+                phase_s2<NW>(sp, pv, fw, ts, L, acc, inc);
+            }
             publish_comp<NW>(sp.st_i0, sp.f_i0, tile, inc);
             const uint32_t rest = sp.num_tiles - (tile & ~31u);
             if ((tile & 31u) == (rest < 32u ? rest : 32u) - 1u) publish_comp<NW>(sp.st_i1, sp.f_i1, tile >> 5, inc);
@@ -424,13 +436,20 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             __syncwarp();
         }
         if (fast) {
-            uint32_t inc_c = tail.nacc;
+            uint32_t inc_c, total;
+            if (__all_sync(FULL, tail.nacc <= 1u)) {       // the usual case: a vote and two popcounts
+                const uint32_t have = __ballot_sync(FULL, tail.nacc != 0u);
+                inc_c = (uint32_t)__popc(have & (0xffffffffu >> (31 - lane)));
+                total = (uint32_t)__popc(have);
+            } else {
+                inc_c = tail.nacc;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(FULL, inc_c, d);
-                if (lane >= d) inc_c += v;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(FULL, inc_c, d);
+                    if (lane >= d) inc_c += v;
+                }
+                total = __shfl_sync(FULL, inc_c, 31);
             }
-            const uint32_t total = __shfl_sync(FULL, inc_c, 31);
             unsigned long long base = 0;
             if (lane == 0) {
                 base = reserve_segment(sp, tile, total);

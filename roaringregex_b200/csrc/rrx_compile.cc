@@ -626,6 +626,62 @@ Cut find_cut(const std::vector<Pos>& pos, const std::vector<Bits>& fol, const st
     return best;
 }
 
+// ---- forward skip state of the sparse row scan ------------------------------------------------------
+// Runs of dominated states start at an injected cut group and evolve by  X' = follow'(X) & D & B[c]
+// (no injection inside a run unless another candidate byte comes up).  Explore the reachable X and
+// look for one that a whole range of bytes maps to itself, match-free.
+struct FSkip {
+    uint32_t n = 0, lo = 0, hi = 0;
+    Bits G;
+};
+
+FSkip find_forward_skip(const std::vector<Pos>& pos, const std::vector<Bits>& fol, const Cut& cut, const Bits& accept) {
+    FSkip best;
+    if (!cut.ok) return best;
+    const uint32_t P = (uint32_t)pos.size();
+    std::vector<Bits> Bc(128, Bits(P));
+    for (uint32_t c = 0; c < 128; c++)
+        for (uint32_t k = 0; k < P; k++)
+            if (((pos[k].cls[c >> 6] >> (c & 63)) & 1ull) && cut.D.has(k)) Bc[c].add(k);
+    auto step = [&](const Bits& X, uint32_t c) {
+        Bits nx(P), out(P);
+        for (uint32_t k : X.list()) nx.unite(fol[k]);
+        for (uint32_t k : nx.list()) if (Bc[c].has(k)) out.add(k);
+        return out;
+    };
+    std::vector<Bits> seen, queue;
+    for (auto& g : cut.groups) {
+        bool known = false;
+        for (auto& s : seen) if (s.equals(g.k)) known = true;
+        if (!known) { seen.push_back(g.k); queue.push_back(g.k); }
+    }
+    for (size_t qi = 0; qi < queue.size() && qi < 48; qi++) {
+        const Bits X = queue[qi];
+        if (!X.any()) continue;
+        if (!X.intersects(accept)) {
+            uint32_t run_lo = 0, run_len = 0;
+            for (uint32_t c = 1; c <= 128; c++) {
+                const bool stay = c < 128 && c != cut.byte && step(X, c).equals(X);
+                if (stay) { if (!run_len) run_lo = c; run_len++; }
+                else {
+                    if (run_len >= 4 && run_len > best.n) { best.n = run_len; best.lo = run_lo; best.hi = run_lo + run_len - 1; best.G = X; }
+                    run_len = 0;
+                }
+            }
+        }
+        if (seen.size() < 96)
+            for (uint32_t c = 1; c < 128; c++) {
+                if (c == cut.byte) continue;
+                Bits nx = step(X, c);
+                if (!nx.any()) continue;
+                bool known = false;
+                for (auto& s : seen) if (s.equals(nx)) { known = true; break; }
+                if (!known) { seen.push_back(nx); queue.push_back(nx); }
+            }
+    }
+    return best;
+}
+
 // ---- reverse-walk skip state -----------------------------------------------------------------------
 // The lazy start scan walks the reversed automaton from the accepting positions:  x = R & B[c];
 // found if x meets first; R = rfollow'(x).  Explore the reverse state sets reachable from `accept`
@@ -762,6 +818,9 @@ Program build_program(const Automaton& a, const std::string& pattern, bool reduc
     h.cand_byte = cut.byte;
     h.n_groups = cut.ok ? (uint32_t)cut.groups.size() : 0u;
     const RSkip rskip = find_reverse_skip(pos, rfol, first, accept);
+    const FSkip fskip = find_forward_skip(pos, fol, cut, accept);
+    h.off_fskip = take(NW);
+    h.fskip_n = fskip.n; h.fskip_lo = fskip.lo; h.fskip_hi = fskip.hi;
     h.off_rskip = take(NW);
     h.rskip_n = rskip.n;
     h.rskip_bytes = rskip.bytes[0] | (rskip.bytes[1] << 8);
@@ -788,6 +847,7 @@ Program build_program(const Automaton& a, const std::string& pattern, bool reduc
         }
     }
     if (rskip.n) put_bits(pr.blob, h.off_rskip, rskip.F, NW);
+    if (fskip.n) put_bits(pr.blob, h.off_fskip, fskip.G, NW);
     auto put_decomp = [&](const Decomp& d, uint32_t o_terms, uint32_t o_bicl, uint32_t o_rowsrc, uint32_t o_rows) {
         for (size_t i = 0; i < d.terms.size(); i++) {
             uint32_t o = o_terms + (uint32_t)i * (1 + NW);

@@ -24,7 +24,7 @@ template <int NW, int WARPS_> struct KCfg {
     static constexpr uint32_t BT_BYTES = (NW == 1 ? 256u * 128u : 256u * (uint32_t)NW * 4u);
     static constexpr size_t REGION = (TileState<NW>::bytes() + 15) & ~(size_t)15;
     // small program part: header + 3 sets + 2 decompositions
-    static constexpr size_t SMALL = sizeof(ProgHeader) + 4u * (3 * NW + 2 * (RRX_MAX_TERMS * (1 + NW) + RRX_MAX_BICL * 2 * NW + NW) + NW + RRX_MAX_GROUPS * (2 * NW + 1) + NW);
+    static constexpr size_t SMALL = sizeof(ProgHeader) + 4u * (3 * NW + 2 * (RRX_MAX_TERMS * (1 + NW) + RRX_MAX_BICL * 2 * NW + NW) + NW + RRX_MAX_GROUPS * (2 * NW + 1) + 2 * NW);
     static constexpr size_t SMEM = BT_BYTES + (size_t)WARPS * REGION + SMALL + 64;
 };
 

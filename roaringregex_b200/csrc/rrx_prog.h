@@ -47,6 +47,11 @@ struct ProgHeader {
     uint32_t rskip_n;           // 0: no such state; else 1 or 2
     uint32_t rskip_bytes;       // byte0 | byte1 << 8
     uint32_t off_rskip;
+    // Forward skip state of the candidate-driven row scan: a set G of dominated states (off_fskip, NW
+    // words) that every byte of the range [fskip_lo, fskip_hi] maps to itself without a match end
+    // ("[a-z]+" inside a run).  While a run is in G it advances four bytes at a time as long as they
+    // all lie in the range.  fskip_n = hi - lo + 1, 0: none.  The candidate byte is outside the range.
+    uint32_t fskip_n, fskip_lo, fskip_hi, off_fskip;
 };
 constexpr uint32_t RRX_MAX_GROUPS = 4;
 

@@ -243,6 +243,11 @@ template <int NW> struct SparseFromSmem {
     RRX_DEV uint32_t rs_n(const ProgView& pv) const { return pv.h().rskip_n; }
     RRX_DEV uint32_t rs_bytes(const ProgView& pv) const { return pv.h().rskip_bytes; }
     RRX_DEV uint32_t rs_F(const ProgView& pv, int w) const { return pv.sm[pv.h().off_rskip + w]; }
+    // forward skip state of the sparse row scan (rrx_prog.h)
+    RRX_DEV uint32_t fs_n(const ProgView& pv) const { return pv.h().fskip_n; }
+    RRX_DEV uint32_t fs_lo(const ProgView& pv) const { return pv.h().fskip_lo; }
+    RRX_DEV uint32_t fs_hi(const ProgView& pv) const { return pv.h().fskip_hi; }
+    RRX_DEV uint32_t fs_G(const ProgView& pv, int w) const { return pv.sm[pv.h().off_fskip + w]; }
 };
 
 // Follow policy.  NT >= 0: one-word automaton whose forward AND reverse decompositions (up to NT
@@ -765,6 +770,10 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
     uint32_t live = 0;                  // OR of the words of H
     uint32_t work = bail ? 0u : (uint32_t)ncand;     // non-zero while the lane has something left to do
     const SmemBytes rb(rp);
+    const bool fs_on = fw.fs_n(pv) != 0;
+    const uint32_t fsHM = (127u - fw.fs_hi(pv)) * 0x01010101u, fsLO = fw.fs_lo(pv) * 0x01010101u;
+    const uint32_t* rw32 = reinterpret_cast<const uint32_t*>(rp);
+    uint32_t fs_tried = 0;
 #pragma unroll
     for (int q = 0; q < 4; q++) ts.hits[q * ROWS + t] = 0;
     ts.kst[2 * t] = ts.kst[2 * t + 1] = (uint16_t)KST_NONE;
@@ -865,6 +874,26 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
             go = (step && nacc < 4) ? live : 0u;        /* queue full: parked until drained */     \
         }
         while (RRX_WARP_ANY(go != 0)) {
+            // skip: a run in the forward skip state G advances four bytes at a time while they all lie
+            // in [lo, hi] (they map G to itself, no match ends, no candidate among them).  A lane tries
+            // once per stay in G; runs start together, so the whole warp skips in the same few rounds.
+            if (fs_on) {
+                uint32_t dG = 0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) dG |= H[w] ^ fw.fs_G(pv, w);
+                uint32_t sk = (go != 0 && dG == 0 && !fs_tried) ? 1u : 0u;
+                while (RRX_WARP_ANY(sk != 0)) {
+                    if (sk) {
+                        const uint32_t i = p >> 2;                       // p <= 128: word 32 is the pad (0xff bytes)
+                        const uint32_t w0 = rw32[i], w1 = rw32[i < 32u ? i + 1 : i];
+                        const uint32_t w = fshr(w0, w1, 8u * (p & 3u));   // the four bytes at p
+                        // any byte >= 0x80, > hi or < lo?  (carries/borrows can only add flags, never hide one)
+                        const uint32_t bad = (w | (w + fsHM) | (w - fsLO)) & 0x80808080u;
+                        if (bad == 0) p += 4; else { sk = 0; fs_tried = 1u; }
+                    }
+                }
+                if (dG != 0) fs_tried = 0u;
+            }
             RRX_SPARSE_STEP()
             RRX_SPARSE_STEP()
         }

@@ -321,7 +321,7 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
         const char* sv = getenv("RRX_SPARSE");     // 0 forces the dense row scan (A/B measurements)
         sp.sparse = (h.sparse_ok && !(sv && sv[0] == '0')) ? 1u : 0u;
         const char* ta = getenv("RRX_TICKET_AHEAD");
-        sp.ticket_ahead = ta ? (uint32_t)atoi(ta) : 0u;
+        sp.ticket_ahead = ta ? (uint32_t)atoi(ta) : 5u;
     }
 #ifdef RRX_PHASE_TIMING
     {

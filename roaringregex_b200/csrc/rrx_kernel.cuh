@@ -281,6 +281,11 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
     // that reaches it before any larger one, so the look-back cannot deadlock; what is lost is
     // dynamic balancing, what is won is one contended global atomic per tile.
     const bool static_tiles = sp.ticket_ahead == 3;
+    // ticket_ahead == 5: a tile on the fast tail (its text is dead by then) takes the next ticket right
+    // after its look-back and, before it writes its matches, starts asynchronous copies (cp.async,
+    // no registers involved) of the next tile straight into its staging rows: the ticket and the
+    // HBM/L2 latency hide behind the tail instead of heading the next tile.
+    bool preloaded = false;
     uint32_t tile = 0;
     if (static_tiles) {
         tile = blockIdx.x * (uint32_t)K::WARPS + (uint32_t)warp;
@@ -312,7 +317,9 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         {
             const int64_t g0 = ts.lo();
             uint4 v[8];
-            if (g0 + TILE_BYTES <= len) {                 // whole tile inside the text: no per-load checks
+            if (preloaded) {                              // copies started during the previous tile's tail
+                asm volatile("cp.async.wait_all;" ::: "memory");
+            } else if (g0 + TILE_BYTES <= len) {          // whole tile inside the text: no per-load checks
                 const uint4* src = reinterpret_cast<const uint4*>(sp.text + g0) + lane;
 #pragma unroll
                 for (int k = 0; k < 8; k++) v[k] = __ldcs(src + k * 32);
@@ -329,11 +336,14 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
                     }
                 }
             }
+            if (!preloaded) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                uint32_t* dst = ts.chunk_ptr(k * 32 + lane);
-                dst[0] = v[k].x; dst[1] = v[k].y; dst[2] = v[k].z; dst[3] = v[k].w;
+                for (int k = 0; k < 8; k++) {
+                    uint32_t* dst = ts.chunk_ptr(k * 32 + lane);
+                    dst[0] = v[k].x; dst[1] = v[k].y; dst[2] = v[k].z; dst[3] = v[k].w;
+                }
             }
+            preloaded = false;
         }
         if (lane == 0) ts.misc[TS::M_RQCNT] = 0;
         __syncwarp();
@@ -400,7 +410,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         }
         RRX_T(2)
         lookback_wait<NW>(sp, tile, lane, acc);
-        if (sp.ticket_ahead == 4 && !have_next) {       // the tile's tail is short: take the next ticket now
+        if (((sp.ticket_ahead == 4) || (sp.ticket_ahead == 5 && published && !dense)) && !have_next) {       // the tile's tail is short: take the next ticket now
             if (lane == 0) next_raw = atom_add_u32(sp.ticket, 1u);
             have_next = true;
             late_ticket = true;
@@ -457,6 +467,19 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
                 sp.tile_cnt[tile] = total;
             }
             base = __shfl_sync(FULL, base, 0);
+            if (sp.ticket_ahead == 5 && late_ticket) {
+                const uint32_t nt = __shfl_sync(FULL, next_raw, 0);
+                const int64_t n0 = ((int64_t)nt * TILE_ROWS) << ROW_SHIFT;
+                if (nt < sp.num_tiles && n0 + TILE_BYTES <= len) {
+                    // word j = 32k + lane of the tile -> staged row k, word `lane` (rows are 33 words apart)
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(sp.text + n0) + lane;
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ts.text) + 4u * (uint32_t)lane;
+#pragma unroll
+                    for (int k = 0; k < 32; k++)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 132u * k), "l"(src + 32 * k) : "memory");
+                    preloaded = true;
+                }
+            }
             phase_tail_fast<NW>(sp, ts, lane, tail, base + (inc_c - tail.nacc));
         } else {
             const uint32_t c = phase_b<NW>(sp, pv, fw, ts, lane, any_open);

@@ -3,14 +3,18 @@
 // `ProgJit` policy that has the automaton's masks and shifts baked in as immediates).
 //
 // One persistent CTA per SM; every WARP walks tiles (32 rows of 128 B) in ticket order:
-//   load   8 x 128-bit coalesced loads per lane -> shared memory rows (132-byte pitch)
-//   A      every lane scans its row from the empty set (register state word(s)), finds match ends
+//   load   8 x 128-bit coalesced loads per lane -> shared memory rows (132-byte pitch); or already there,
+//          copied asynchronously (cp.async) during the previous tile's fast tail
+//   A      sparse variant (automata with a cut): exit sets first (aggregate published at once when all rows
+//          are closed), then candidate-driven match ends with known lazy starts; dense variant: every
+//          lane scans its row from the empty set (register state word(s))
 //   S      row transfer functions composed; tile aggregate published; two-level decoupled
 //          look-back over predecessor tiles yields the tile's exact entry set
 //   B      rows replay their prefix from the exact entry (dies within a few bytes unless the
 //          automaton has an absorbing loop)
-//   C      one atomicAdd reserves the tile's segment of the staging list; balanced lazy start scans;
-//          (start,end) writes.  rrx_order.cu puts the segments in text order afterwards.
+//   C      the tile's matches go to its fixed staging slots (or an overflow segment); balanced lazy start
+//          scans for the matches whose start is not known yet; (start,end) writes.  Fast tail: B and C are
+//          skipped when there is nothing to replay or resolve.  rrx_order.cu puts the segments in text order.
 // The phase bodies live in rrx_tile.cuh (shared with the host-side test emulator).
 #pragma once
 #include "rrx_tile.cuh"

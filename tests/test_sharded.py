@@ -193,3 +193,25 @@ def test_world_size_2_over_gloo(oracle_api):
     [p.join(timeout=60) for p in procs]
     want = oracle_api.Oracle(CONFIGS[5].pattern).lazy_matches(cpu_corpus(CONFIGS[5], 0, n))
     assert np.array_equal(np.concatenate([got[0], got[1]]), want)
+
+
+def test_fold_entries_equals_fold_entry(rrx):
+    """rrx_fold_entries (all ranks in one call) against rrx_fold_entry rank by rank, on random
+    closed / rank-1 / identity / opaque summaries."""
+    rnd = random.Random(21)
+    for pat in ("(x|y)*z.*q", "a{1,100}b", "[a-z]+@[a-z]+\\.(com|org|net)"):
+        r = rrx.RRegex(pat)
+        w = r.info["words"]
+        for _ in range(50):
+            world = rnd.randint(1, 8)
+            s = np.zeros((world, 1 + 3 * w), dtype=np.uint32)
+            for k in range(world):
+                kind = rnd.choice([0, 0, 1, 2, 0x100])          # closed, rank-1, identity, opaque closed
+                s[k, 0] = kind
+                s[k, 1:] = [rnd.getrandbits(32) & rnd.getrandbits(32) for _ in range(3 * w)]
+                if kind & 0xff != 1:
+                    s[k, 1 + w:] = 0
+            both = sharded.fold_entries(r, s)
+            for k in range(world):
+                e, ex = sharded.fold_entry(r, s, k)
+                assert np.array_equal(both[k][0], e) and both[k][1] == ex

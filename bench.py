@@ -33,7 +33,10 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--config", default="2", help="1..5 or 2v (BASELINE.json configs; 2v = config 2 on variable-length lines)")
+    ap.add_argument("--sub", default=None, help="comma list of configs measured as sub-records at their named sizes "
+                    "(default at N=1 with --config 2: 1,2v,3,4,5; at N>1: 5 = config 5 strong); 'none' to skip")
+    ap.add_argument("--prefix", type=int, default=256 << 20, help="bytes of each corpus the oracle re-scans for the parity digests")
     ap.add_argument("--size", type=int, default=0, help="corpus bytes per rank (default: the config's size, capped for N>1)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -86,7 +89,7 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(cfg, sample_per_thread: int):
+def cpu_baseline(cfg, sample_per_thread: int, text=None, repeats: int = 1):
     """The oracle port (reference algorithm: per-active-state row OR, injection, flag test, backward
     start scan) on all host cores, each core scanning its own contiguous piece of the corpus."""
     from oracle import api as oracle_api
@@ -94,9 +97,10 @@ def cpu_baseline(cfg, sample_per_thread: int):
     cores = os.cpu_count() or 1
     o = oracle_api.Oracle(cfg.pattern)
     n = sample_per_thread * cores
-    text = oracle_api.corpus_iid(cfg.seed, cfg.alpha, 0, n) if cfg.mode == "iid" else oracle_api.corpus_records(cfg.seed, 0, n)
+    if text is None:
+        text = oracle_api.corpus(cfg, 0, n)
     o.time_parallel(text, min(sample_per_thread, 1 << 20), cores)         # warm
-    sec, m = o.time_parallel(text, sample_per_thread, cores)
+    sec, m = min(o.time_parallel(text, sample_per_thread, cores) for _ in range(max(repeats, 1)))
     out = {"value": n / sec / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
            "sample": f"first {n >> 20} MiB of the corpus, {sample_per_thread >> 20} MiB per thread, {cores} threads, full LAZY-v1 match lists ({m} matches)"}
     # the compiled, unmodified reference can only do whole-string acceptance (its lazy iterator is
@@ -118,11 +122,18 @@ def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_thread = 32 << 20
+    # the same bytes as the GPU arm's step: the config's size (1 GiB for config 2, capped at 1 GiB for the
+    # larger ones so that the run ends within minutes), split evenly over the host threads
+    from oracle import api as oracle_api
+    oracle_api.build(ref=False)
+    cores = os.cpu_count() or 1
+    total = args.size or min(cfg.length, 1 << 30)
+    per_thread = max(total // cores, 1 << 16)
+    text = oracle_api.corpus(cfg, 0, per_thread * cores)
     vals, res = [], None
     t_start = time.perf_counter()
     for i in range(args.warmup + args.steps):
-        res = cpu_baseline(cfg, per_thread)
+        res = cpu_baseline(cfg, per_thread, text=text)
         if i >= args.warmup:
             vals.append(res["value"])
         if time.perf_counter() - t_start > 150 and vals:        # keep the whole run within a few minutes
@@ -133,8 +144,8 @@ def run_reference(args, cfg):
             "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup, "ms_per_step": nbytes / val / 1e6,
             "higher_is_better": True, "scaling": "weak",
             "dtype": "u64 bitsets", "data": "synthetic", "vs_baseline": None,
-            "config": {"workload": f"{cfg.name}: regex {cfg.pattern!r}; each step = the first {nbytes >> 20} MiB of the corpus "
-                                   f"({per_thread >> 20} MiB per host thread), full LAZY-v1 match lists"},
+            "config": {"workload": f"{cfg.name}: regex {cfg.pattern!r} over {nbytes} bytes per step (the first {nbytes >> 20} MiB of the corpus, "
+                                   f"{per_thread >> 20} MiB per host thread), full LAZY-v1 match lists", "bytes_per_step": nbytes},
             "cpu_baseline": {**res, "value": val},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -152,10 +163,236 @@ def measured_traffic(cfg_name: str, size: int):
 
 
 # ---------------------------------------------------------------------------------------------------
+# Parity at scale: the device digest of the ordered match list against (a) the oracle's
+# digest over a prefix of the same corpus, (b) a count that does not come from any scan kernel.
+def closed_form_count(torch, cfg, d_text, size, off=0):
+    """Number of LAZY-v1 matches the corpus must contain, from plain torch reductions over the device text
+    (iid corpora: the regex's last byte preceded by what the regex needs) or from the generator's own
+    record kinds (log corpora).  Independent of librrx.  Shard-local for off > 0 (config 5 only counts
+    q's; the caller subtracts those before the corpus's first z)."""
+    from oracle import api as oracle_api
+    name = cfg.name
+    if name == "config2":
+        assert off == 0 and size % 128 == 0
+        return oracle_api.records_valid(cfg.seed, size // 128)
+    if name == "config2v":
+        assert off == 0 and size % 2048 == 0
+        return oracle_api.lines_valid(cfg.seed, size // 2048)
+    a, b, c, e, q, z = (ord(ch) for ch in "abceqz")
+    total, first_z, CH = 0, None, 1 << 30
+    for lo in range(0, size, CH):
+        hi = min(size, lo + CH)
+        t = d_text[lo:hi]
+        if name == "config1":
+            total += int((t == e).sum())
+        elif name in ("config3", "config4"):
+            last = b if name == "config3" else c
+            p = d_text[max(lo - 1, 0):hi - 1] if lo else torch.cat([torch.zeros(1, dtype=torch.uint8, device=t.device), d_text[:hi - 1]])
+            ok = (p == a) if name == "config3" else ((p == a) | (p == b))
+            total += int(((t == last) & ok).sum())
+        elif name == "config5":
+            isq = t == q
+            if first_z is None:
+                zpos = torch.nonzero(t == z)
+                if len(zpos):
+                    first_z = lo + int(zpos[0])
+                    total += int(isq[first_z - lo:].sum())
+            else:
+                total += int(isq.sum())
+        else:
+            return None
+    return (total, first_z) if name == "config5" else total
+
+
+def oracle_prefix_digest(cfg, prefix):
+    """Digest of the oracle's LAZY-v1 list over corpus[0:prefix).  Configs 3/4 (bounded match length) are
+    scanned in parallel pieces with 4 KiB of overlap, which is exact for them; the others in one piece."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import api as oracle_api
+    o = oracle_api.Oracle(cfg.pattern)
+    t0 = time.perf_counter()
+    if cfg.name in ("config3", "config4"):
+        cores = os.cpu_count() or 1
+        piece = -(-prefix // cores)
+        def work(i):
+            lo, hi = i * piece, min(prefix, (i + 1) * piece)
+            if lo >= hi:
+                return np.zeros((0, 2), np.int64)
+            ov = min(lo, 4096)
+            m = o.lazy_matches(oracle_api.corpus(cfg, lo - ov, hi - lo + ov), base=lo - ov)
+            return m[m[:, 1] > lo]
+        with ThreadPoolExecutor(cores) as ex:
+            m = np.concatenate(list(ex.map(work, range(cores))))
+    else:
+        m = o.lazy_matches(oracle_api.corpus(cfg, 0, prefix))
+    return oracle_api.digest(m), time.perf_counter() - t0
+
+
+def parity_record(rrx, torch, cfg, sc, d_text, size, off, n_matches, prefix, sh, closed=True):
+    prefix = min(prefix, size)
+    full = sc.digest(1 << 62, sh)
+    pre = sc.digest(off + prefix, sh) if off == 0 else None
+    rec = {"digest": "count, sum and xor (mod 2^64) of sm64(sm64(start)+end) over the ordered list, computed on the device (rrx_hash.cu)",
+           "hash_gpu": [full[0], f"{full[1]:016x}", f"{full[2]:016x}"], "order_violations": full[3], "count_gpu": n_matches}
+    ok = full[0] == n_matches and full[3] == 0
+    if pre is not None:
+        (oc, os_, ox, ob), secs = oracle_prefix_digest(cfg, prefix)
+        rec.update({"prefix_bytes": prefix, "hash_gpu_prefix": [pre[0], f"{pre[1]:016x}", f"{pre[2]:016x}"],
+                    "hash_oracle_prefix": [oc, f"{os_:016x}", f"{ox:016x}"], "oracle_seconds": round(secs, 2)})
+        ok = ok and (pre[0], pre[1], pre[2]) == (oc, os_, ox) and ob == 0
+    if closed:
+        cf = closed_form_count(torch, cfg, d_text, size, off)
+        if isinstance(cf, tuple):
+            cf = cf[0]
+        rec["count_closed_form"] = cf
+        ok = ok and (cf is None or cf == n_matches)
+    rec["ok"] = bool(ok)
+    return rec
+
+
+def _scan_setup(rrx, torch, cfg, size, off, halo, sh):
+    d_buf = torch.empty(halo + size + 256, dtype=torch.uint8, device="cuda")
+    d_text = d_buf[halo:]
+    rrx.corpus_device(cfg, d_buf.data_ptr(), off - halo, halo + size, sh)
+    torch.cuda.synchronize()
+    return d_buf, d_text
+
+
+def sub_record(rrx, torch, cfg, peak, prefix, sh, steps=3):
+    """One configuration at its named size on one GPU: throughput, the scan kernel's own time, roofline
+    fraction, match count and the parity digests."""
+    size = cfg.length
+    regex = rrx.RRegex(cfg.pattern)
+    d_buf, d_text = _scan_setup(rrx, torch, cfg, size, 0, 0, sh)
+    cap = max(1 << 16, size // (48 if cfg.mode != "iid" else 160))
+    sc = rrx.Scanner(regex, size, cap)
+    sc.scan(d_text.data_ptr(), size, 0, 0, None, sh)
+    res = sc.result(sh)
+    if res["n_matches"] > cap:
+        cap = res["n_matches"] + 1024
+        del sc
+        torch.cuda.empty_cache()
+        sc = rrx.Scanner(regex, size, cap)
+    sc.enable_timing(True)
+    for _ in range(2):
+        sc.scan(d_text.data_ptr(), size, 0, 0, None, sh)
+    torch.cuda.synchronize()
+    step_ms, kern_ms = [], []
+    for _ in range(steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(torch.cuda.current_stream())
+        sc.scan(d_text.data_ptr(), size, 0, 0, None, sh)
+        b.record(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        step_ms.append(a.elapsed_time(b))
+        kern_ms.append(sc.kernel_ms())
+    res = sc.result(sh)
+    assert res["error_bits"] == 0 and res["n_matches"] <= cap, res
+    n = res["n_matches"]
+    k_ms, s_ms = float(np.mean(kern_ms)), float(np.mean(step_ms))
+    alg = size + 16 * n
+    info = regex.info
+    rec = {"workload": f"{cfg.name}: regex {cfg.pattern!r} over {size} bytes ({cfg.note})", "bytes": size, "matches": n,
+           "value": size / (s_ms * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": s_ms, "kernel_ms": k_ms, "steps": steps,
+           "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "frac": alg / (k_ms * 1e-3) / 1e9 / peak,
+                        "algorithmic_bytes_per_launch": alg},
+           "kernel_variant": "run-time specialised (NVRTC)" if sc.is_jit else "pre-compiled generic",
+           "states_device": info["n_device"], "words": info["words"],
+           "parity": parity_record(rrx, torch, cfg, sc, d_text, size, 0, n, prefix, sh)}
+    if cfg.name in ("config3", "config4"):
+        rec["parity"]["note"] = "the compiled reference cannot run this regex (>256 raw states, SURVEY.md §0.4): the oracle is the restated scanner, itself checked on scaled shapes and against Python re"
+    return rec
+
+
+def sub_record_sharded(rrx, torch, dist, cfg, peak, prefix, sh, rank, world, local, steps=3):
+    """Config 5 as BASELINE.json names it: ONE 64 GiB corpus cut into `world` contiguous shards (strong
+    scaling).  Sum/xor digests add up over the shards, so the whole-job digest must equal the 1-GPU one."""
+    from roaringregex_b200 import sharded
+    size = (cfg.length // world) & ~4095
+    off = rank * size
+    halo = min(off, 1 << 20)
+    regex = rrx.RRegex(cfg.pattern)
+    d_buf, d_text = _scan_setup(rrx, torch, cfg, size, off, halo, sh)
+    comm = sharded.TorchComm(dist, torch.device("cuda", local))
+    cap = max(1 << 16, size // 160)
+    probe = rrx.Scanner(regex, size, cap)
+    probe.scan(d_text.data_ptr(), size, off, halo, None, sh)
+    cap = max(cap, probe.result(sh)["n_matches"] + (1 << 16))
+    del probe
+    torch.cuda.empty_cache()
+    be = sharded.DeviceBackend(regex, d_text.data_ptr(), size, off, halo, cap, sh)
+    res = None
+    for _ in range(2):
+        res = sharded.scan_sharded(regex, be, comm, rank, world, fetch=False)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = sharded.scan_sharded(regex, be, comm, rank, world, fetch=False)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    # digest of this rank's exact list (repaired head on the host + device tail), summed/xored over the ranks
+    from oracle import api as oracle_api
+    tail_sc = res.tail.handle
+    dg_tail = tail_sc.digest(1 << 62, sh)
+    head_dg = oracle_api.digest(res.head) if len(res.head) else (0, 0, 0, 0)
+    skip_dg = (0, 0, 0, 0)
+    if res.skip:
+        skip_dg = oracle_api.digest(be.head(res.tail, res.skip))
+    cnt = dg_tail[0] - skip_dg[0] + head_dg[0]
+    s = (dg_tail[1] - skip_dg[1] + head_dg[1]) % (1 << 64)
+    x = dg_tail[2] ^ skip_dg[2] ^ head_dg[2]
+    patched = len(res.patches)
+    cf = closed_form_count(torch, cfg, d_text, size, off)
+    t = torch.tensor([cnt, s >> 32, s & 0xffffffff, dg_tail[3], cf[0], -1 if cf[1] is None else cf[1], res.rescans, patched, res.count],
+                     device="cuda", dtype=torch.int64)
+    g = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(g, t)
+    tx = torch.tensor([x >> 32, x & 0xffffffff], device="cuda", dtype=torch.int64)
+    gx = [torch.zeros_like(tx) for _ in range(world)]
+    dist.all_gather(gx, tx)
+    tm = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms = float(tm.item())
+    g = [v.tolist() for v in g]
+    total = sum(v[0] for v in g)
+    ssum = sum((v[1] << 32) | v[2] for v in g) % (1 << 64)
+    sx = 0
+    for v in gx:
+        hi, lo = v.tolist()
+        sx ^= (hi << 32) | lo
+    # closed form: q's after the corpus's first z.  Shard r counted q's after ITS first z; q's of shards right of
+    # the globally first z that precede their own first z are owed too.
+    cf_total = sum(v[4] for v in g)
+    zs = [v[5] for v in g]
+    note = None
+    if any(z >= 0 for z in zs):
+        first_rank = next(i for i, z in enumerate(zs) if z >= 0)
+        # every shard of the synthetic corpus has a z within its first KiB; count the q's before it exactly
+        lo_fix = torch.tensor([0], device="cuda", dtype=torch.int64)
+        if rank > first_rank:
+            zloc = (zs[rank] - off) if zs[rank] >= 0 else size
+            lo_fix[0] = int((d_text[:zloc] == ord("q")).sum())
+        dist.all_reduce(lo_fix)
+        cf_total += int(lo_fix.item())
+    full_bytes = size * world
+    rec = {"workload": f"{cfg.name}: regex {cfg.pattern!r}, ONE corpus of {full_bytes} bytes cut into {world} contiguous shards (strong scaling)",
+           "bytes_total": full_bytes, "bytes_per_gpu": size, "matches": total, "value": full_bytes / (ms * 1e-3) / 1e9, "unit": "GB/s",
+           "ms_per_step": ms, "steps": steps, "scaling": "strong",
+           "roofline_frac_per_gpu": (size + 16 * total / world) / (ms * 1e-3) / 1e9 / peak,
+           "rescans_per_rank": [v[6] for v in g], "start_patches_per_rank": [v[7] for v in g],
+           "parity": {"hash_gpu": [total, f"{ssum:016x}", f"{sx:016x}"], "order_violations": sum(v[3] for v in g),
+                      "count_closed_form": cf_total, "ok": bool(total == cf_total and sum(v[3] for v in g) == 0 and total == sum(v[8] for v in g)),
+                      "note": "sum/xor digests are order-free: this triple must equal config5's hash_gpu in the 1-GPU record"}}
+    del be, d_text, d_buf
+    return rec
+
+
+# ---------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
     from roaringregex_b200.configs import CONFIGS
-    cfg = CONFIGS[args.config]
+    key = args.config if args.config in CONFIGS else int(args.config)
+    cfg = CONFIGS[key]
     if args.impl == "reference":
         run_reference(args, cfg)
         return
@@ -174,7 +411,7 @@ def main():
 
     # config 2 (the headline): the config's size PER GPU (weak scaling); config 5 is defined as one
     # 64 GiB corpus sharded over the GPUs (strong scaling)
-    strong = args.config == 5 and not args.size
+    strong = key == 5 and not args.size
     size = args.size or (cfg.length // world if strong else min(cfg.length, 8 << 30))
     size = min(size, 120 << 30) & ~4095
     regex = rrx.RRegex(cfg.pattern)
@@ -189,10 +426,7 @@ def main():
     d_buf = torch.empty(halo + size + 256, dtype=torch.uint8, device="cuda")
     d_text = d_buf[halo:]
     assert d_text.data_ptr() % 16 == 0
-    if cfg.mode == "iid":
-        rrx.corpus_iid(d_buf.data_ptr(), off - halo, halo + size, cfg.seed, cfg.alpha, sh)
-    else:
-        rrx.corpus_records(d_buf.data_ptr(), off - halo, halo + size, cfg.seed, sh)
+    rrx.corpus_device(cfg, d_buf.data_ptr(), off - halo, halo + size, sh)
     torch.cuda.synchronize()
 
     cap = max(1 << 20, size // 48)
@@ -339,12 +573,50 @@ def main():
         e2e = {"value": e_size * world / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": e_size, "d2h_bytes_per_step": 16 * n_e,
                "bytes_scanned_per_rank": e_size, "ms_per_step": dt * 1e3, "pinned_h2d_copy_alone_gbs": h2d_gbs,
                "call": "rrx_scan_host (C ABI) on a pinned host buffer: H2D copy, scan kernels, D2H of the match list into pinned memory"}
+        if world == 1:
+            # the same call on PAGEABLE memory — what the C++ drop-in's getline buffer is (src/test/main.cpp:17-26)
+            pg = np.array(host_np, copy=True)
+            regex.scan_host(pg, off)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                n_p = len(regex.scan_host(pg, off))
+            dtp = (time.perf_counter() - t0) / 2
+            assert n_p == n_e
+            e2e["pageable"] = {"value": e_size / dtp / 1e9, "unit": "GB/s", "ms_per_step": dtp * 1e3,
+                               "note": "same call, host buffer NOT page-locked (plain malloc'ed memory)"}
+            del pg
+        del h_text, host_np
 
+    peak, peak_src = measured_peaks()
+    # ---- parity of the list that was just timed: device digest vs oracle on a prefix, closed-form count ----
+    parity = None
+    if world == 1:
+        parity = parity_record(rrx, torch, cfg, sc, d_text, size, off, n_matches, args.prefix, sh)
+    # ---- the other configurations at their named sizes (sub-records) ------------------------------------
+    sub_keys = []
+    if args.sub is None:
+        sub_keys = ([1, "2v", 3, 4, 5] if world == 1 else [5]) if key == 2 and not args.size else []
+    elif args.sub != "none":
+        sub_keys = [k if k in CONFIGS else int(k) for k in args.sub.split(",") if k]
+    sc = timed_scanner = step = be = prev = tok = comm = None        # release the headline's device buffers
+    if world > 1:
+        last.clear()
+    d_text = d_buf = None
+    torch.cuda.empty_cache()
+    subs = {}
+    for k in sub_keys:
+        try:
+            if world == 1:
+                subs[CONFIGS[k].name] = sub_record(rrx, torch, CONFIGS[k], peak, args.prefix, sh)
+            else:
+                subs[CONFIGS[k].name + "_strong"] = sub_record_sharded(rrx, torch, dist, CONFIGS[k], peak, args.prefix, sh, rank, world, local)
+        except Exception as e:      # a sub-record must not take the headline line down with it
+            subs[CONFIGS[k].name] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-    peak, peak_src = measured_peaks()
     k_ms = float(np.mean(scan_kernel_ms)) if scan_kernel_ms else float(np.mean(kern_ms))
     alg_bytes = size + 16 * n_matches
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
@@ -362,6 +634,7 @@ def main():
                      "peak_source": peak_src},
         "e2e": e2e, "gpu_launches": args.steps * launches_per_step, "clocks": clocks,
         "kernel_variant": "run-time specialised (NVRTC)" if is_jit else "pre-compiled generic",
+        "parity": parity, "configs": subs,
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(cfg, 32 << 20)

@@ -21,7 +21,7 @@ enum {
     RRX_OK = 0,
     RRX_ERR_PARSE = 1,        /* the reference would throw std::runtime_error (Parser.cpp:36,155) or has UB */
     RRX_ERR_CUDA = 2,         /* no device / CUDA runtime failure; there is no CPU fallback */
-    RRX_ERR_UNSUPPORTED = 3,  /* automaton/text combination outside the implemented transfer-function rank */
+    RRX_ERR_UNSUPPORTED = 3,  /* the request is outside what this build implements (e.g. an unknown scan mode) */
     RRX_ERR_ARG = 4
 };
 
@@ -99,7 +99,8 @@ typedef struct rrx_scan_result {
     uint64_t n_matches;        /* total found (may exceed capacity: then only the first `capacity` were written) */
     uint64_t capacity;
     uint64_t n_pending;        /* start scans that ran off the left edge (sharded use) */
-    uint32_t error_bits;       /* kernel-reported: 1 = transfer function not rank<=1 (results invalid) */
+    uint32_t error_bits;       /* kernel-reported, 0 = fine: 2 pending-start list overflow, 4 staging overflow (reported as
+                                * n_matches > capacity), 8 a start walk died (the entry set given was not exact) */
     uint32_t launches;         /* kernels launched by the scan */
     const int64_t* d_matches;  /* device pairs */
 } rrx_scan_result;
@@ -107,7 +108,9 @@ typedef struct rrx_scan_result {
 int rrx_scanner_create(const rrx_program* p, uint64_t max_len, uint64_t match_capacity, rrx_scanner** out);
 /* flags: RRX_SCANNER_JIT / RRX_SCANNER_NO_JIT force / forbid the run-time specialised kernel (NVRTC);
  * default: specialise when max_len >= 32 MiB and the automaton fits one 32-bit word.
- * The environment variable RRX_JIT=0/1 overrides the default. */
+ * The environment variable RRX_JIT=0/1 overrides the default.  If the default policy wants the specialised
+ * kernel but NVRTC is unavailable, the scanner falls back to the pre-compiled kernel (same results), prints one
+ * warning line to stderr and leaves the text in rrx_last_error(); with RRX_SCANNER_JIT it fails instead. */
 enum { RRX_SCANNER_DEFAULT = 0, RRX_SCANNER_JIT = 1, RRX_SCANNER_NO_JIT = 2 };
 int rrx_scanner_create_ex(const rrx_program* p, uint64_t max_len, uint64_t match_capacity, uint32_t flags, rrx_scanner** out);
 /* 1 if the scanner runs a run-time specialised kernel, 0 if a pre-compiled one. */
@@ -155,18 +158,31 @@ int rrx_fold_entries(const rrx_program* p, const uint32_t* summaries, uint32_t n
 /* exit = summary applied to entry (both words32 per rrx_info.words). */
 int rrx_apply_summary(const rrx_program* p, const uint32_t* summary, const uint32_t* entry, uint32_t* exit_out);
 /* Pending start scans of the last scan (those that ran off the left edge of the readable text):
- * copies up to cap records {uint64 match_index; int64 next_offset; uint32 R[32]} to host. */
+ * copies up to cap records {uint64 match_index; int64 next_offset; uint32 R[32]} to host.
+ * next_offset is the GLOBAL offset (base_offset of that scan included) of the next byte to consume. */
 int rrx_scanner_copy_pending(rrx_scanner* s, void* host_out, uint64_t cap, uint64_t* n_out, void* stream);
 /* Continue start scans handed over by the shard to the right: for each record walk backwards from
- * the END of this shard's text (record.next_offset is rewritten relative to this shard: -1 = its
- * last byte).  On return start_out[i] is the global start offset, or -1 if the walk ran off this
- * shard's left edge too (then the record is updated for the next shard to the left). */
+ * record.next_offset, a GLOBAL offset that must lie inside this shard's readable text
+ * [base_offset - left_context - 1, base_offset + len) (RRX_ERR_ARG otherwise).  On return start_out[i]
+ * is the global start offset, -2 if no start exists (inconsistent record), or -1 if the walk ran off
+ * this shard's left edge too (then the record is updated, still global, for the next shard to the left). */
 int rrx_continue_starts(const rrx_program* p, const uint8_t* d_text, uint64_t len, uint64_t left_context,
                         uint64_t base_offset, void* records_host, uint64_t n, int64_t* start_out, void* stream);
+
+/* ---- parity at scale: digest of a device match list (csrc/rrx_hash.cu) --------------------------
+ * digest[0] = matches with end <= end_limit, [1] = sum and [2] = xor over those of
+ * sm64(sm64(start) + end) (splitmix64 finaliser), [3] = order violations in the WHOLE list
+ * (end not ascending, or start >= end; must be 0).  Sum/xor are order-free: shard digests add/xor up.
+ * Synchronous (waits for `stream`). */
+int rrx_digest_device(const int64_t* d_pairs, uint64_t n, int64_t end_limit, uint64_t digest[4], void* stream);
+/* The same for the match list of the scanner's last scan. */
+int rrx_scanner_digest(rrx_scanner* s, int64_t end_limit, uint64_t digest[4], void* stream);
 
 /* ---- measurement harness: synthetic corpora of SURVEY.md §8d, generated in device memory ------ */
 int rrx_corpus_iid_device(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, const uint8_t alpha[256], void* stream);
 int rrx_corpus_records_device(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, void* stream);
+/* config 2 variant: the same log lines unpadded (variable length, unaligned); oracle/corpus.c corpus_fill_lines */
+int rrx_corpus_lines_device(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, void* stream);
 
 const char* rrx_last_error(void);
 const char* rrx_version(void);

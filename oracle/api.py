@@ -45,6 +45,12 @@ def _lib():
     lib.corpus_fill_iid.argtypes = [C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
     lib.corpus_fill_records.restype = None
     lib.corpus_fill_records.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+    lib.corpus_fill_lines.restype = None
+    lib.corpus_fill_lines.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+    lib.corpus_lines_valid.restype = C.c_uint64
+    lib.corpus_lines_valid.argtypes = [C.c_uint64, C.c_uint64]
+    lib.corpus_records_valid.restype = C.c_uint64
+    lib.corpus_records_valid.argtypes = [C.c_uint64, C.c_uint64]
     lib.corpus_h.restype = C.c_uint64
     lib.corpus_h.argtypes = [C.c_uint64, C.c_uint64]
     return lib
@@ -170,6 +176,27 @@ def ref_dump(pattern: str):
     return n, finals, fwd, bwd
 
 
+def _sm64(z: np.ndarray) -> np.ndarray:
+    z = z + np.uint64(0x9E3779B97F4A7C15)
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def digest(matches: np.ndarray, end_limit: int = (1 << 62)) -> tuple:
+    """(count, sum, xor, order_violations) of a host match list — the CPU twin of csrc/rrx_hash.cu
+    (count + sum/xor of splitmix over the (start,end) pairs)."""
+    m = np.ascontiguousarray(matches, dtype=np.int64).reshape(-1, 2)
+    bad = int(np.count_nonzero(m[:, 0] >= m[:, 1])) + (int(np.count_nonzero(m[1:, 1] <= m[:-1, 1])) if len(m) > 1 else 0)
+    m = m[m[:, 1] <= end_limit]
+    if len(m) == 0:
+        return (0, 0, 0, bad)
+    with np.errstate(over="ignore"):
+        h = _sm64(_sm64(m[:, 0].astype(np.uint64)) + m[:, 1].astype(np.uint64))
+        s = int(np.add.reduce(h, dtype=np.uint64))
+    return (len(m), s, int(np.bitwise_xor.reduce(h)), bad)
+
+
 def corpus_iid(seed: int, alpha: bytes, offset: int, length: int) -> np.ndarray:
     assert len(alpha) == 256
     out = np.empty(length, dtype=np.uint8)
@@ -182,3 +209,27 @@ def corpus_records(seed: int, offset: int, length: int) -> np.ndarray:
     out = np.empty(length, dtype=np.uint8)
     _lib().corpus_fill_records(seed, offset, length, out.ctypes.data)
     return out
+
+
+def corpus_lines(seed: int, offset: int, length: int) -> np.ndarray:
+    """Config 2 variant: unpadded variable-length log lines (oracle/corpus.c corpus_fill_lines)."""
+    out = np.empty(length, dtype=np.uint8)
+    _lib().corpus_fill_lines(seed, offset, length, out.ctypes.data)
+    return out
+
+
+def corpus(cfg, offset: int, length: int) -> np.ndarray:
+    """Bytes [offset, offset+length) of a configuration's corpus (roaringregex_b200/configs.py)."""
+    if cfg.mode == "iid":
+        return corpus_iid(cfg.seed, cfg.alpha, offset, length)
+    if cfg.mode == "lines":
+        return corpus_lines(cfg.seed, offset, length)
+    return corpus_records(cfg.seed, offset, length)
+
+
+def lines_valid(seed: int, n_blocks: int) -> int:
+    return int(_lib().corpus_lines_valid(seed, n_blocks))
+
+
+def records_valid(seed: int, n_records: int) -> int:
+    return int(_lib().corpus_records_valid(seed, n_records))

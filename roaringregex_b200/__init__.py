@@ -26,7 +26,7 @@ import numpy as np
 
 from . import _build
 
-__all__ = ["RRegex", "Match", "InvalidExpression", "RrxError", "Scanner", "lib", "corpus_iid", "corpus_records"]
+__all__ = ["RRegex", "Match", "InvalidExpression", "RrxError", "Scanner", "lib", "corpus_iid", "corpus_records", "corpus_lines", "corpus_device"]
 
 RRX_OK, RRX_ERR_PARSE, RRX_ERR_CUDA, RRX_ERR_UNSUPPORTED, RRX_ERR_ARG = range(5)
 MODE_LAZY_V1, MODE_NO_OVERLAP = 0, 1
@@ -105,8 +105,11 @@ def lib() -> C.CDLL:
         "rrx_fold_entries": (C.c_int, [vp, vp, u32, vp, vp]),
         "rrx_apply_summary": (C.c_int, [vp, vp, vp, vp]),
         "rrx_continue_starts": (C.c_int, [vp, vp, u64, u64, u64, vp, u64, vp, vp]),
+        "rrx_digest_device": (C.c_int, [vp, u64, i64, vp, vp]),
+        "rrx_scanner_digest": (C.c_int, [vp, i64, vp, vp]),
         "rrx_corpus_iid_device": (C.c_int, [vp, u64, u64, u64, vp, vp]),
         "rrx_corpus_records_device": (C.c_int, [vp, u64, u64, u64, vp]),
+        "rrx_corpus_lines_device": (C.c_int, [vp, u64, u64, u64, vp]),
         "rrx_last_error": (C.c_char_p, []),
         "rrx_version": (C.c_char_p, []),
     }
@@ -367,6 +370,12 @@ class Scanner:
         _check(lib().rrx_scanner_copy_matches(self._h, out.ctypes.data, n, stream))
         return out
 
+    def digest(self, end_limit: int = (1 << 62), stream: int = 0) -> tuple:
+        """(count, sum, xor, order_violations) of the last scan's device match list (rrx_scanner_digest)."""
+        d = np.zeros(4, dtype=np.uint64)
+        _check(lib().rrx_scanner_digest(self._h, end_limit, d.ctypes.data, stream))
+        return tuple(int(x) for x in d)
+
     def enable_timing(self, on: bool = True):
         _check(lib().rrx_scanner_enable_timing(self._h, int(on)))
 
@@ -395,3 +404,17 @@ def corpus_iid(d_ptr: int, offset: int, length: int, seed: int, alpha: bytes, st
 
 def corpus_records(d_ptr: int, offset: int, length: int, seed: int, stream: int = 0):
     _check(lib().rrx_corpus_records_device(d_ptr, offset, length, seed, stream))
+
+
+def corpus_lines(d_ptr: int, offset: int, length: int, seed: int, stream: int = 0):
+    _check(lib().rrx_corpus_lines_device(d_ptr, offset, length, seed, stream))
+
+
+def corpus_device(cfg, d_ptr: int, offset: int, length: int, stream: int = 0):
+    """Bytes [offset, offset+length) of a configuration's corpus (configs.py), generated in device memory."""
+    if cfg.mode == "iid":
+        corpus_iid(d_ptr, offset, length, cfg.seed, cfg.alpha, stream)
+    elif cfg.mode == "lines":
+        corpus_lines(d_ptr, offset, length, cfg.seed, stream)
+    else:
+        corpus_records(d_ptr, offset, length, cfg.seed, stream)

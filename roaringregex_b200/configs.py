@@ -36,6 +36,9 @@ CONFIGS = {
               "test_regex analogue; <=64-state path"),
     2: Config("config2", "[a-z]+@[a-z]+\\.(com|org|net)", 1 << 30, 2, "records", None,
               "1 GiB synthetic log records; <=64-state register path, HBM-bound"),
+    # config 2 on unpadded, variable-length (39..254 B), unaligned lines: addresses straddle the scanner's rows
+    "2v": Config("config2v", "[a-z]+@[a-z]+\\.(com|org|net)", 1 << 30, 2, "lines", None,
+                 "config 2's regex over 1 GiB of variable-length unaligned log lines (robustness variant)"),
     3: Config("config3", "a{1,100}b", 1 << 32, 3, "iid",
               _alpha([("a", 240), ("b", 1), (" ", 8), ("\n", 1), ("c", 6)]),
               "<=256-state path (flattened N=102)"),

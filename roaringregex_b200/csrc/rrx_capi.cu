@@ -110,6 +110,7 @@ struct rrx_scanner {
     PendingStart* d_pending = nullptr;
     uint32_t pending_cap = 4096;
     uint32_t launches = 0;
+    int64_t last_base = 0;           // base_offset of the last scan (pending records are handed out with global offsets)
     bool owns_out = true;
     JitKernel* jit = nullptr;        // run-time specialised kernel (owned by the process-wide cache)
     // pinned host mirror of [ticket, err, total0, total1] followed by the shard composite (1+3*NW words)
@@ -289,7 +290,10 @@ int rrx_scanner_create_ex(const rrx_program* p, uint64_t max_len, uint64_t capac
             s->jit = jit_get(p->prog, &err);
             if (!s->jit) {
                 if (flags & RRX_SCANNER_JIT) return set_err(RRX_ERR_CUDA, "run-time specialisation failed: " + err);
-                if (getenv("RRX_JIT_VERBOSE")) fprintf(stderr, "rrx: run-time specialisation unavailable (%s); using the pre-compiled kernel\n", err.c_str());
+                // not fatal (the pre-compiled kernel gives the same results, slower), but never silent: one line on
+                // stderr, and the text stays readable through rrx_last_error() although the call returns RRX_OK
+                g_err = "warning: run-time specialisation unavailable (" + err + "); using the pre-compiled kernel";
+                fprintf(stderr, "rrx: %s\n", g_err.c_str());
             }
         }
     }
@@ -371,6 +375,7 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     }
     if (opts && opts->entry) for (uint32_t w = 0; w < h.NW; w++) sp.entry[w] = opts->entry[w];
     s->launches = 0;
+    s->last_base = (int64_t)base_offset;
     s->h_shard_valid = false;
     RRX_CUDA(cudaMemsetAsync(s->d_ctrl, 0, used, st));
     if (h.NW == 1)      // one-word automata keep the ready bit inside the 16-byte composite words
@@ -461,6 +466,7 @@ int rrx_scanner_copy_pending(rrx_scanner* s, void* host_out, uint64_t cap, uint6
             unsigned long long off = 0;
             RRX_CUDA(cudaMemcpy(&off, s->d_tile_seg + tile, 8, cudaMemcpyDeviceToHost));
             recs[i].match_index = off + rank;
+            recs[i].next_offset += s->last_base;          // shard-local -> global
         }
     }
     return RRX_OK;
@@ -469,6 +475,14 @@ int rrx_continue_starts(const rrx_program* p, const uint8_t* d_text, uint64_t le
                         void* records_host, uint64_t n, int64_t* start_out, void* stream) {
     if (!p || (!records_host && n) || (!start_out && n)) return set_err(RRX_ERR_ARG, "null argument");
     if (!n) return RRX_OK;
+    {
+        // every record must point into this shard's readable text (global offsets)
+        const PendingStart* recs = reinterpret_cast<const PendingStart*>(records_host);
+        const int64_t lo = (int64_t)base_offset - (int64_t)left_context, hi = (int64_t)base_offset + (int64_t)len;
+        for (uint64_t i = 0; i < n; i++)
+            if (recs[i].next_offset < lo - 1 || recs[i].next_offset >= hi)
+                return set_err(RRX_ERR_ARG, "rrx_continue_starts: record offset outside this shard's text");
+    }
     cudaStream_t st = (cudaStream_t)stream;
     uint32_t* d_prog = nullptr;
     PendingStart* d_recs = nullptr;
@@ -698,9 +712,33 @@ void rrx_matches_free(rrx_matches* m) {
     delete m;
 }
 
+int rrx_digest_device(const int64_t* d_pairs, uint64_t n, int64_t end_limit, uint64_t digest[4], void* stream) {
+    if (!digest || (!d_pairs && n)) return set_err(RRX_ERR_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* d = nullptr;
+    RRX_CUDA(cudaMalloc(&d, 32));
+    cudaError_t e = launch_digest(reinterpret_cast<const long long*>(d_pairs), n, end_limit, d, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(digest, d, 32, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    return e == cudaSuccess ? RRX_OK : cuda_err(e, "rrx_digest_device");
+}
+int rrx_scanner_digest(rrx_scanner* s, int64_t end_limit, uint64_t digest[4], void* stream) {
+    if (!s) return set_err(RRX_ERR_ARG, "null argument");
+    rrx_scan_result r;
+    int rc = rrx_scanner_result(s, &r, stream);
+    if (rc) return rc;
+    const uint64_t n = r.n_matches < r.capacity ? r.n_matches : r.capacity;
+    return rrx_digest_device(r.d_matches, n, end_limit, digest, stream);
+}
+
 int rrx_corpus_iid_device(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, const uint8_t alpha[256], void* stream) {
     cudaError_t e = launch_corpus_iid(d_out, offset, len, seed, alpha, (cudaStream_t)stream);
     return e == cudaSuccess ? RRX_OK : cuda_err(e, "corpus_iid");
+}
+int rrx_corpus_lines_device(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, void* stream) {
+    cudaError_t e = launch_corpus_lines(d_out, offset, len, seed, (cudaStream_t)stream);
+    return e == cudaSuccess ? RRX_OK : cuda_err(e, "corpus_lines");
 }
 int rrx_corpus_records_device(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, void* stream) {
     cudaError_t e = launch_corpus_records(d_out, offset, len, seed, (cudaStream_t)stream);

@@ -1,5 +1,5 @@
 // Measurement harness: the synthetic corpora of SURVEY.md §8d generated directly in HBM.
-// Must produce the same bytes as oracle/corpus.c (tests/test_corpus.py compares them).
+// Must produce the same bytes as oracle/corpus.c (tests/test_gpu_parity.py::test_device_corpus_equals_cpu_corpus compares them).
 #include "rrx_scan.h"
 
 namespace rrx {
@@ -94,8 +94,68 @@ __global__ void corpus_records_kernel(uint8_t* out, uint64_t offset, uint64_t le
     }
 }
 
+// lines mode (config 2 variant): unpadded variable-length log lines, one 2048-byte block per thread; layout
+// documented in oracle/corpus.c (corpus_fill_lines).
+__global__ void corpus_lines_kernel(uint8_t* out, uint64_t offset, uint64_t len, uint64_t sseed) {
+    const char* MSG = "abcdefghijklmnopqrstuvwxyz 0123 ";
+    const uint64_t b0 = offset >> 11, b1 = (offset + len + 2047) >> 11;
+    for (uint64_t b = b0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < b1; b += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t o = b << 11;
+        int pos = 0, i = 0;
+        uint8_t rec[256];
+        while (2048 - pos >= 256) {
+            uint64_t f[10];
+#pragma unroll
+            for (int k = 0; k < 10; k++) f[k] = sm64(sseed + 1024 * b + 16 * (uint64_t)i + (uint64_t)k);
+            i++;
+            int p = 0;
+            p += put_dec(rec + p, f[0] & 0xFFFFFFFFull, 10);
+            p += put_str(rec + p, " INFO svc");
+            p += put_dec(rec + p, f[1] % 100, 2);
+            p += put_str(rec + p, " user=");
+            const unsigned kind = (unsigned)(f[2] & 3);
+            if (kind == 3) {
+                rec[p++] = '-';
+            } else {
+                const unsigned variant = (unsigned)((f[7] >> 8) % 5);
+                p += put_letters(rec + p, f[3], f[4]);
+                rec[p++] = (kind == 2 && variant == 4) ? '#' : '@';
+                p += put_letters(rec + p, f[5], f[6]);
+                rec[p++] = '.';
+                if (kind == 2 && variant < 4) {
+                    const char* bad = variant == 0 ? "con" : variant == 1 ? "ogr" : variant == 2 ? "ne." : "COM";
+                    p += put_str(rec + p, bad);
+                } else {
+                    const unsigned t = (unsigned)(f[7] % 3);
+                    p += put_str(rec + p, t == 0 ? "com" : t == 1 ? "org" : "net");
+                }
+            }
+            p += put_str(rec + p, " rc=");
+            p += put_dec(rec + p, (f[7] >> 32) % 1000, 3);
+            p += put_str(rec + p, " m=");
+            const int L = (int)(f[8] % 188);
+            for (int j = 0; j < L; j++) rec[p++] = (uint8_t)MSG[(sm64(f[9] + (uint64_t)(j / 12)) >> (5 * (j % 12))) & 31];
+            rec[p++] = '\n';
+            for (int k = 0; k < p; k++) {
+                const uint64_t ok = o + (uint64_t)(pos + k);
+                if (ok >= offset && ok < offset + len) out[ok - offset] = rec[k];
+            }
+            pos += p;
+        }
+        for (; pos < 2048; pos++) {
+            const uint64_t ok = o + (uint64_t)pos;
+            if (ok >= offset && ok < offset + len) out[ok - offset] = pos == 2047 ? (uint8_t)'\n' : (uint8_t)' ';
+        }
+    }
+}
+
 }  // namespace
 
+cudaError_t launch_corpus_lines(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, cudaStream_t st) {
+    if (!len) return cudaSuccess;
+    corpus_lines_kernel<<<148 * 8, 64, 0, st>>>(d_out, offset, len, sm64(seed));
+    return cudaGetLastError();
+}
 cudaError_t launch_corpus_iid(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, const uint8_t* alpha256, cudaStream_t st) {
     if (!len) return cudaSuccess;
     Alpha al;

@@ -1,5 +1,5 @@
 // The rrx scan kernel body (sm_100a), shared by the pre-compiled instantiations (rrx_scan.cu) and
-// the run-time specialised ones (rrx_jit.cc feeds this header to NVRTC together with a generated
+// the run-time specialised ones (rrx_jit.cu feeds this header to NVRTC together with a generated
 // `ProgJit` policy that has the automaton's masks and shifts baked in as immediates).
 //
 // One persistent CTA per SM; every WARP walks tiles (32 rows of 128 B) in ticket order:

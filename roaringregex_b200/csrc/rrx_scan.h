@@ -19,6 +19,8 @@ cudaError_t launch_no_overlap(const longlong2* in, uint64_t n, longlong2* out, u
                               size_t workspace_bytes, cudaStream_t st);
 void fold_entry_host(uint32_t NW, const uint32_t* summaries, uint32_t n, uint32_t rank, uint32_t* entry_out, int* exact);
 void apply_summary_host(uint32_t NW, const uint32_t* s, const uint32_t* entry, uint32_t* out);
+cudaError_t launch_digest(const long long* d_pairs, uint64_t n, int64_t end_limit, unsigned long long* d_out4, cudaStream_t st);
 cudaError_t launch_corpus_iid(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, const uint8_t* alpha256, cudaStream_t st);
+cudaError_t launch_corpus_lines(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, cudaStream_t st);
 cudaError_t launch_corpus_records(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, cudaStream_t st);
 }  // namespace rrx

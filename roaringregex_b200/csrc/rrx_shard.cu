@@ -17,8 +17,7 @@ __global__ void continue_starts_kernel(const uint32_t* prog, const uint8_t* text
     uint32_t R[NW], x[NW], Bc[NW];
 #pragma unroll
     for (int w = 0; w < NW; w++) R[w] = rec.R[w];
-    long long j = rec.next_offset - base;          // record carries a GLOBAL offset
-    if (j >= len) j = len - 1;
+    long long j = rec.next_offset - base;          // record carries a GLOBAL offset (validated by the host)
     long long found = -1;
     for (;;) {
         if (j < -left_ctx) break;

@@ -51,7 +51,9 @@ constexpr int TILE_BYTES = TILE_ROWS * ROW_BYTES;     // 4 KiB
 constexpr int ROW_PITCH = 132;
 
 // error bits reported by the kernel
-enum : uint32_t { ERR_PENDING_OVERFLOW = 2u, ERR_STAGING_OVERFLOW = 4u };
+// ERR_START_LOST: a lazy start walk died without finding a start and without reaching the left edge (only
+// possible when the entry set handed to the scan was not the exact one)
+enum : uint32_t { ERR_PENDING_OVERFLOW = 2u, ERR_STAGING_OVERFLOW = 4u, ERR_START_LOST = 8u };
 
 // Kinds of chunk transfer functions S_out = A*S_in | b:
 //   K_CLOSED  A = 0: the exit does not depend on the entry
@@ -364,7 +366,8 @@ constexpr int RRX_NW_MAX = 32;
 struct PendingStart {           // a start scan that ran off the left edge of the available text
     uint64_t match_index;       // (tile << 32) | rank of the match inside its tile; the host turns it into the
                                 // index in the ordered list (rrx_scanner_copy_pending)
-    int64_t next_offset;        // shard-local offset of the next byte to consume (negative)
+    int64_t next_offset;        // offset of the next byte to consume: shard-local (negative) as the kernel writes it,
+                                // GLOBAL once rrx_scanner_copy_pending has handed it out (what rrx_continue_starts expects)
     uint32_t R[RRX_NW_MAX];     // backward set before consuming that byte
 };
 struct ScanParams {
@@ -478,7 +481,9 @@ RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
     // (1) survivor scan: U = all positions, no injection.  Dead before the row ends => the row's
     //     exit does not depend on its entry (closed).  Otherwise remember the first point where
     //     exactly one survivor is left: from there on the row acts as a rank-1 map.
-    if (nb && !sp.static_closed) {
+    // (static_closed: a FULL row outlasts every path of an acyclic automaton of depth < ROW_BYTES; a partial
+    // last row does not, so it is analysed like any other row)
+    if (nb && !(sp.static_closed && nb == ROW_BYTES)) {
         uint32_t U[NW];
 #pragma unroll
         for (int w = 0; w < NW; w++) U[w] = fw.all(pv, w);
@@ -1231,6 +1236,7 @@ RRX_DEV void resolve_and_write(const ScanParams& sp, const ProgView& pv, const F
         o[0] = found ? sp.base + j : -1;        // -1: the start lies left of the available text
         o[1] = sp.base + e;
     }
+    if (!found && !pend) atomicOr(sp.err, ERR_START_LOST);
     if (pend) {
         const unsigned long long k = atomicAdd(sp.total + 1, 1ull);
         if (k < sp.pending_cap) {

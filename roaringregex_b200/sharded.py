@@ -80,7 +80,7 @@ class DeviceBackend:
             for i in range(int(n.value)):
                 rec = buf[i * PENDING_RECORD:(i + 1) * PENDING_RECORD]
                 mi, nxt = np.frombuffer(rec[:16].tobytes(), dtype=np.int64)
-                pend.append((int(mi), self.base + int(nxt), np.frombuffer(rec[16:].tobytes(), dtype=np.uint32).copy()))
+                pend.append((int(mi), int(nxt), np.frombuffer(rec[16:].tobytes(), dtype=np.uint32).copy()))   # offsets are global
         return pend
 
     def scan_gather_begin(self, comm):

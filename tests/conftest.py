@@ -29,6 +29,4 @@ def rrx():
 
 def cpu_corpus(cfg, offset, length):
     from oracle import api
-    if cfg.mode == "iid":
-        return api.corpus_iid(cfg.seed, cfg.alpha, offset, length)
-    return api.corpus_records(cfg.seed, offset, length)
+    return api.corpus(cfg, offset, length)

@@ -52,7 +52,7 @@ def test_sizes_around_row_and_tile_edges(rrx, oracle_api, torch_cuda, n):
         _check(rrx, oracle_api, pat, text)
 
 
-@pytest.mark.parametrize("cfg_id,n", [(1, 1 << 20), (2, 16 << 20), (3, 16 << 20), (4, 4 << 20), (5, 16 << 20)])
+@pytest.mark.parametrize("cfg_id,n", [(1, 1 << 20), (2, 16 << 20), ("2v", 16 << 20), (3, 16 << 20), (4, 4 << 20), (5, 16 << 20)])
 def test_config_corpora(rrx, oracle_api, torch_cuda, cfg_id, n):
     cfg = CONFIGS[cfg_id]
     text = cpu_corpus(cfg, 0, n)
@@ -113,14 +113,11 @@ def test_random_regexes(rrx, oracle_api, torch_cuda):
 
 def test_device_corpus_equals_cpu_corpus(rrx, oracle_api, torch_cuda):
     torch = torch_cuda
-    for cid in (1, 2, 3, 4, 5):
+    for cid in (1, 2, "2v", 3, 4, 5):
         cfg = CONFIGS[cid]
         for off, n in ((0, 1 << 20), (12345, 100003), (1 << 33, 4096 + 5)):
             d = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
-            if cfg.mode == "iid":
-                rrx.corpus_iid(d.data_ptr(), off, n, cfg.seed, cfg.alpha)
-            else:
-                rrx.corpus_records(d.data_ptr(), off, n, cfg.seed)
+            rrx.corpus_device(cfg, d.data_ptr(), off, n)
             torch.cuda.synchronize()
             assert np.array_equal(d[:n].cpu().numpy(), cpu_corpus(cfg, off, n)), (cid, off, n)
 
@@ -347,3 +344,57 @@ def test_large_corpora_properties(rrx, oracle_api, torch_cuda, cfg_id, n):
     pre = 32 << 20
     want = oracle_api.Oracle(cfg.pattern).lazy_matches(cpu_corpus(cfg, 0, pre))
     assert np.array_equal(got[:len(want)], want)
+
+
+def test_device_digest_equals_host_digest(rrx, oracle_api, torch_cuda):
+    """rrx_digest_device / rrx_scanner_digest (csrc/rrx_hash.cu) against oracle.api.digest (numpy) on the
+    same lists: full, with an end limit, empty, and a list with order violations."""
+    torch = torch_cuda
+    cfg = CONFIGS[5]
+    text = cpu_corpus(cfg, 0, 4 << 20)
+    want = oracle_api.Oracle(cfg.pattern).lazy_matches(text)
+    r = rrx.RRegex(cfg.pattern)
+    sc = rrx.Scanner(r, len(text), len(want) + 16)
+    sc.scan(torch.from_numpy(text).cuda().data_ptr(), len(text))
+    for lim in (1 << 62, 1 << 20, 12345, 0):
+        assert sc.digest(lim) == oracle_api.digest(want, lim), lim
+    import ctypes as C
+    bad = want[::-1].copy()
+    d = torch.from_numpy(bad).cuda()
+    out = np.zeros(4, dtype=np.uint64)
+    assert rrx.lib().rrx_digest_device(d.data_ptr(), len(bad), 1 << 62, out.ctypes.data, None) == 0
+    assert tuple(int(x) for x in out) == oracle_api.digest(bad) and out[3] == len(bad) - 1
+    assert rrx.lib().rrx_digest_device(None, 0, 1 << 62, out.ctypes.data, None) == 0 and not out.any()
+
+
+def test_offsets_beyond_4gib(rrx, oracle_api, torch_cuda):
+    """A 5 GiB shard whose global offsets start above 2^32 (config 3's corpus from offset 2^32 + 12345*128 on):
+    tile counts, staging slots and every offset the kernels form exceed 32 bits.  Bit-exact against the
+    oracle on windows at the start, around local offset 4 GiB, and at the end; match count against the
+    closed form ('ab' occurrences); digest consistent with the count."""
+    torch = torch_cuda
+    cfg = CONFIGS[3]
+    n = 5 << 30
+    off = (1 << 32) + 12345 * 128
+    d = torch.empty(n + 256, dtype=torch.uint8, device="cuda")
+    rrx.corpus_device(cfg, d.data_ptr(), off, n)
+    torch.cuda.synchronize()
+    r = rrx.RRegex(cfg.pattern)
+    sc = rrx.Scanner(r, n, n // 160)
+    sc.scan(d.data_ptr(), n, off)
+    res = sc.result()
+    assert res["error_bits"] == 0 and res["n_matches"] <= res["capacity"]
+    import bench
+    assert res["n_matches"] == bench.closed_form_count(torch, cfg, d[:n], n)
+    dg = sc.digest()
+    assert dg[0] == res["n_matches"] and dg[3] == 0
+    got = sc.matches()
+    assert got[0, 1] > off and got[-1, 1] <= off + n
+    o = oracle_api.Oracle(cfg.pattern)
+    W = 1 << 20
+    for lo in (0, (1 << 32) - W // 2, (4 << 30) - 4096 * 3 - 77, n - W):
+        ov = min(lo, 4096)
+        want = o.lazy_matches(cpu_corpus(cfg, off + lo - ov, W + ov), base=off + lo - ov)
+        want = want[want[:, 1] > off + lo]
+        sel = got[(got[:, 1] > off + lo) & (got[:, 1] <= off + lo + W)]
+        assert np.array_equal(sel, want), lo

@@ -167,6 +167,27 @@ def test_random_texts_random_cuts(rrx, oracle_api):
             assert np.array_equal(got, o.lazy_matches(text)), (pat, n, cuts)
 
 
+def test_unaligned_cuts_with_static_closed_patterns(rrx, oracle_api):
+    """Shard lengths that are not multiples of the 128-byte row: the partial last row of a shard must
+    not be taken as closed by construction (acyclic automaton), or matches crossing the cut are lost."""
+    pat = "abcdefgh"
+    text = np.full(400, ord(" "), dtype=np.uint8)
+    text[126:134] = np.frombuffer(b"abcdefgh", dtype=np.uint8)
+    for cut in (127, 129, 131, 133):
+        got, _ = run_world(rrx, pat, text, 2, halo=64, cuts=[0, cut, 400])
+        assert got.tolist() == [[126, 134]], cut
+    rnd = random.Random(77)
+    for pat, alpha in [("abcab", b"abc "), ("a{1,100}b", b"aaaab "), ("(ab|cd)e(f|g)h", b"abcdefgh"), ("[a-z]+@[a-z]+\\.(com|org|net)", b"ab@.comrgnet ")]:
+        o = oracle_api.Oracle(pat)
+        for _ in range(2):
+            n = rnd.randint(1500, 4000)
+            text = np.frombuffer(bytes(rnd.choices(alpha, k=n)), dtype=np.uint8)
+            world = rnd.randint(2, 4)
+            cuts = sorted(rnd.sample([c for c in range(100, n - 100) if c % 128 in (1, 3, 64, 127)], world - 1))
+            got, _ = run_world(rrx, pat, text, world, halo=rnd.choice([0, 128, 1024]), cuts=[0] + cuts + [n])
+            assert np.array_equal(got, o.lazy_matches(text)), (pat, n, cuts)
+
+
 def _gloo_worker(rank, world, port, pattern, n, seed, q):
     import torch.distributed as dist
     import roaringregex_b200 as rrx

@@ -30,7 +30,8 @@ enum {
  * computed on the device (csrc/rrx_overlap.cu) by the one-shot calls rrx_scan_host / rrx_scan_device;
  * the reusable scanner (rrx_scanner_scan) produces LAZY-v1 only. */
 enum { RRX_MODE_LAZY_V1 = 0, RRX_MODE_NO_OVERLAP = 1 };
-enum { RRX_COMPILE_DEFAULT = 0, RRX_COMPILE_NO_REDUCE = 1 };
+/* RRX_COMPILE_NO_DONLY: never choose the thread-owned candidate scan (rrx_info.donly) for this program. */
+enum { RRX_COMPILE_DEFAULT = 0, RRX_COMPILE_NO_REDUCE = 1, RRX_COMPILE_NO_DONLY = 2 };
 
 typedef struct rrx_program rrx_program;   /* compiled regex: replaces Regex::RRegex's NFA<S> + MemoryPool (regex.h:16-75,212-228) */
 typedef struct rrx_scanner rrx_scanner;   /* reusable device-side scan context (one per CUDA stream) */
@@ -47,6 +48,8 @@ typedef struct rrx_info {
     uint32_t static_closed;  /* no chunk's exit can depend on its entry (acyclic pruned follow, depth < 128) */
     uint32_t sparse_ok;      /* a single-byte cut exists: rows are scanned candidate-driven (DESIGN.md "Sparse row scan") */
     uint32_t cand_byte;      /* that byte */
+    uint32_t donly;          /* thread-owned candidate scan: only the states dominated by the cut are carried between rows,
+                              * tiles and shards; candidates are verified by backward walks (DESIGN.md "Thread-owned scan") */
 } rrx_info;
 
 /* ---- compile: replaces RRegex::RRegex(const char*) (regex.h:224, Parser.cpp:161-170) ---------- */
@@ -92,8 +95,13 @@ typedef struct rrx_scan_opts {
     uint64_t left_context;     /* bytes readable before d_text (for start scans crossing the left edge) */
     const uint32_t* entry;     /* forward set carried into d_text[0] (words32 per rrx_info.words), or NULL */
     int mode;
-    uint32_t reserved;
+    uint32_t flags;            /* RRX_SCAN_* */
 } rrx_scan_opts;
+/* RRX_SCAN_NO_DONLY: run this scan with the row-bounded candidate scan even if the program has rrx_info.donly
+ * (what a sharded driver asks for when a thread-owned scan reported RRX_SOFT_VERIFY_EDGE on a shard that has
+ * text to its left).  A thread-owned program also takes this path by itself when `entry` holds states outside
+ * the dominated set, and when a verification walk runs out of its step budget. */
+enum { RRX_SCAN_NO_DONLY = 1 };
 
 typedef struct rrx_scan_result {
     uint64_t n_matches;        /* total found (may exceed capacity: then only the first `capacity` were written) */
@@ -103,7 +111,13 @@ typedef struct rrx_scan_result {
                                 * n_matches > capacity), 8 a start walk died (the entry set given was not exact) */
     uint32_t launches;         /* kernels launched by the scan */
     const int64_t* d_matches;  /* device pairs */
+    uint32_t soft_bits;        /* RRX_SOFT_*: the list is valid under the stated assumption */
+    uint32_t reserved;
 } rrx_scan_result;
+/* RRX_SOFT_VERIFY_EDGE: a backward verification walk of the thread-owned scan reached the left edge of the readable
+ * text (d_text - left_context) still alive and assumed that nothing precedes it.  True for a whole text or its first
+ * shard; a shard with text to its left needs more left context or RRX_SCAN_NO_DONLY. */
+enum { RRX_SOFT_VERIFY_EDGE = 16 };
 
 int rrx_scanner_create(const rrx_program* p, uint64_t max_len, uint64_t match_capacity, rrx_scanner** out);
 /* flags: RRX_SCANNER_JIT / RRX_SCANNER_NO_JIT force / forbid the run-time specialised kernel (NVRTC);
@@ -115,6 +129,8 @@ enum { RRX_SCANNER_DEFAULT = 0, RRX_SCANNER_JIT = 1, RRX_SCANNER_NO_JIT = 2 };
 int rrx_scanner_create_ex(const rrx_program* p, uint64_t max_len, uint64_t match_capacity, uint32_t flags, rrx_scanner** out);
 /* 1 if the scanner runs a run-time specialised kernel, 0 if a pre-compiled one. */
 int rrx_scanner_is_jit(const rrx_scanner* s);
+/* 1 if the last scan ran on the fallback (row-bounded) scanner of a thread-owned program. */
+int rrx_scanner_used_fallback(const rrx_scanner* s);
 /* CUDA source of the specialised follow functions for this program (for inspection); returns the
  * length needed (including the NUL), copies at most cap bytes. */
 uint64_t rrx_program_jit_source(const rrx_program* p, char* buf, uint64_t cap);

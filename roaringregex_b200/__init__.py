@@ -30,7 +30,9 @@ __all__ = ["RRegex", "Match", "InvalidExpression", "RrxError", "Scanner", "lib",
 
 RRX_OK, RRX_ERR_PARSE, RRX_ERR_CUDA, RRX_ERR_UNSUPPORTED, RRX_ERR_ARG = range(5)
 MODE_LAZY_V1, MODE_NO_OVERLAP = 0, 1
-COMPILE_DEFAULT, COMPILE_NO_REDUCE = 0, 1
+COMPILE_DEFAULT, COMPILE_NO_REDUCE, COMPILE_NO_DONLY = 0, 1, 2
+SCAN_NO_DONLY = 1
+SOFT_VERIFY_EDGE = 16
 
 
 class RrxError(RuntimeError):
@@ -43,16 +45,17 @@ class InvalidExpression(RrxError):
 
 class _Info(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("n_raw", "ref_width_class", "n_flat", "n_device", "words", "nullable",
-                                          "n_terms", "n_bicliques", "uses_rows", "static_closed", "sparse_ok", "cand_byte")]
+                                          "n_terms", "n_bicliques", "uses_rows", "static_closed", "sparse_ok", "cand_byte", "donly")]
 
 
 class _Opts(C.Structure):
-    _fields_ = [("left_context", C.c_uint64), ("entry", C.c_void_p), ("mode", C.c_int), ("reserved", C.c_uint32)]
+    _fields_ = [("left_context", C.c_uint64), ("entry", C.c_void_p), ("mode", C.c_int), ("flags", C.c_uint32)]
 
 
 class _Result(C.Structure):
     _fields_ = [("n_matches", C.c_uint64), ("capacity", C.c_uint64), ("n_pending", C.c_uint64),
-                ("error_bits", C.c_uint32), ("launches", C.c_uint32), ("d_matches", C.c_void_p)]
+                ("error_bits", C.c_uint32), ("launches", C.c_uint32), ("d_matches", C.c_void_p),
+                ("soft_bits", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 _LIB = None
@@ -90,6 +93,7 @@ def lib() -> C.CDLL:
         "rrx_scanner_create": (C.c_int, [vp, u64, u64, C.POINTER(vp)]),
         "rrx_scanner_create_ex": (C.c_int, [vp, u64, u64, u32, C.POINTER(vp)]),
         "rrx_scanner_is_jit": (C.c_int, [vp]),
+        "rrx_scanner_used_fallback": (C.c_int, [vp]),
         "rrx_program_jit_source": (u64, [vp, vp, u64]),
         "rrx_program_jit_compile": (C.c_int, [vp, C.c_char_p]),
         "rrx_scanner_free": (None, [vp]),
@@ -349,8 +353,14 @@ class Scanner:
     def is_jit(self) -> bool:
         return bool(lib().rrx_scanner_is_jit(self._h))
 
-    def scan(self, d_ptr: int, length: int, base_offset: int = 0, left_context: int = 0, entry=None, stream: int = 0):
-        o = _Opts(left_context, None, MODE_LAZY_V1, 0)
+    @property
+    def used_fallback(self) -> bool:
+        """The last scan ran on the fallback (row-bounded) scanner of a thread-owned program."""
+        return bool(lib().rrx_scanner_used_fallback(self._h))
+
+    def scan(self, d_ptr: int, length: int, base_offset: int = 0, left_context: int = 0, entry=None, stream: int = 0,
+             no_donly: bool = False):
+        o = _Opts(left_context, None, MODE_LAZY_V1, SCAN_NO_DONLY if no_donly else 0)
         if entry is not None:
             self._entry_keep = np.ascontiguousarray(entry, dtype=np.uint32)
             o.entry = self._entry_keep.ctypes.data
@@ -360,7 +370,8 @@ class Scanner:
         r = _Result()
         _check(lib().rrx_scanner_result(self._h, C.byref(r), stream))
         return dict(n_matches=int(r.n_matches), capacity=int(r.capacity), n_pending=int(r.n_pending),
-                    error_bits=int(r.error_bits), launches=int(r.launches), d_matches=int(r.d_matches or 0))
+                    error_bits=int(r.error_bits), launches=int(r.launches), d_matches=int(r.d_matches or 0),
+                    soft_bits=int(r.soft_bits))
 
     def matches(self, stream: int = 0) -> np.ndarray:
         """Match list of the last scan as an (M,2) int64 host array."""

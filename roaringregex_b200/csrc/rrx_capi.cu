@@ -89,6 +89,12 @@ struct HostCtx {
 struct rrx_program {
     Automaton automaton;   // reference-equivalent view (atoms, flattened positions)
     Program prog;          // device program
+    uint32_t flags = 0;    // rrx_compile_ex flags
+    std::string pattern;
+    // the same regex compiled WITHOUT the thread-owned candidate scan: what a scan falls back to when it is given
+    // an entry set outside D, or when a verification walk runs out of budget (built on first use)
+    std::mutex alt_mu;
+    rrx_program* alt = nullptr;
     std::shared_ptr<HostCtx> host = std::make_shared<HostCtx>();
 };
 
@@ -111,6 +117,11 @@ struct rrx_scanner {
     uint32_t pending_cap = 4096;
     uint32_t launches = 0;
     int64_t last_base = 0;           // base_offset of the last scan (pending records are handed out with global offsets)
+    // fallback scanner on p->alt (see rrx_program::alt), created on first use; `use_alt`: the last scan ran there
+    rrx_scanner* alt = nullptr;
+    bool use_alt = false;
+    uint32_t create_flags = 0;
+    struct { const uint8_t* text; uint64_t len, base, left_ctx; bool has_entry; uint32_t entry[RRX_NW_MAX]; void* stream; } last = {};
     bool owns_out = true;
     JitKernel* jit = nullptr;        // run-time specialised kernel (owned by the process-wide cache)
     // pinned host mirror of [ticket, err, total0, total1] followed by the shard composite (1+3*NW words)
@@ -141,7 +152,9 @@ int rrx_compile_ex(const char* ere, uint32_t flags, rrx_program** out) {
     try {
         std::unique_ptr<rrx_program> p(new rrx_program);
         p->automaton = compile_ere(ere);
-        p->prog = build_program(p->automaton, ere, !(flags & RRX_COMPILE_NO_REDUCE));
+        p->prog = build_program(p->automaton, ere, !(flags & RRX_COMPILE_NO_REDUCE), !(flags & RRX_COMPILE_NO_DONLY));
+        p->flags = flags;
+        p->pattern = ere;
         *out = p.release();
         return RRX_OK;
     } catch (const std::runtime_error& e) {
@@ -153,6 +166,7 @@ int rrx_compile_ex(const char* ere, uint32_t flags, rrx_program** out) {
 int rrx_compile(const char* ere, rrx_program** out) { return rrx_compile_ex(ere, RRX_COMPILE_DEFAULT, out); }
 void rrx_program_free(rrx_program* p) {
     if (!p) return;
+    if (p->alt) { rrx_program_free(p->alt); p->alt = nullptr; }
     if (p->host && p->host->sc) { rrx_scanner_free(p->host->sc); p->host->sc = nullptr; }
     delete p;
 }
@@ -171,6 +185,7 @@ void rrx_program_info(const rrx_program* p, rrx_info* o) {
     o->static_closed = (h.static_depth != 0xffffffffu && h.static_depth + 1 <= (uint32_t)ROW_BYTES) ? 1u : 0u;
     o->sparse_ok = h.sparse_ok;
     o->cand_byte = h.cand_byte;
+    o->donly = h.donly;
 }
 
 int64_t rrx_program_flat_table(const rrx_program* p, int which, uint32_t* out, uint64_t cap) {
@@ -212,8 +227,11 @@ int64_t rrx_program_raw_finals(const rrx_program* p, uint32_t* out, uint64_t cap
 }
 
 // ---- scanner ---------------------------------------------------------------------------------------
+static rrx_scanner* act(rrx_scanner* s) { return (s && s->use_alt && s->alt) ? s->alt : s; }
+
 void rrx_scanner_free(rrx_scanner* s) {
     if (!s) return;
+    if (s->alt) { rrx_scanner_free(s->alt); s->alt = nullptr; }
     cudaFree(s->d_prog); cudaFree(s->d_ctrl); cudaFree(s->d_tpay);
     if (s->owns_out) cudaFree(s->d_out);
     cudaFree(s->d_stage); cudaFree(s->d_tile_seg); cudaFree(s->d_tile_cnt); cudaFree(s->d_chunk);
@@ -228,6 +246,7 @@ int rrx_scanner_create(const rrx_program* p, uint64_t max_len, uint64_t capacity
     return rrx_scanner_create_ex(p, max_len, capacity, RRX_SCANNER_DEFAULT, out);
 }
 int rrx_scanner_is_jit(const rrx_scanner* s) { return s && s->jit ? 1 : 0; }
+int rrx_scanner_used_fallback(const rrx_scanner* s) { return s && s->use_alt ? 1 : 0; }
 uint64_t rrx_program_jit_source(const rrx_program* p, char* buf, uint64_t cap) {
     const std::string src = jit_applicable(p->prog) ? jit_policy_source(p->prog) : std::string();
     if (buf && cap) { const size_t n = src.size() + 1 < cap ? src.size() + 1 : cap; std::memcpy(buf, src.c_str(), n); buf[n - 1] = 0; }
@@ -257,6 +276,7 @@ int rrx_scanner_create_ex(const rrx_program* p, uint64_t max_len, uint64_t capac
         return set_err(RRX_ERR_CUDA, "no CUDA device: librrx has no CPU fallback");
     std::unique_ptr<rrx_scanner, void (*)(rrx_scanner*)> s(new rrx_scanner, rrx_scanner_free);
     s->p = p;
+    s->create_flags = flags;
     RRX_CUDA(cudaGetDevice(&s->device));
     RRX_CUDA(cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device));
     const ProgHeader& h = p->prog.hdr();
@@ -301,6 +321,28 @@ int rrx_scanner_create_ex(const rrx_program* p, uint64_t max_len, uint64_t capac
     return RRX_OK;
 }
 
+// Run the scan recorded in s->last on the fallback scanner (created on first use).
+static int scan_on_alt(rrx_scanner* s) {
+    rrx_program* p = const_cast<rrx_program*>(s->p);
+    {
+        std::lock_guard<std::mutex> lk(p->alt_mu);
+        if (!p->alt) {
+            int rc = rrx_compile_ex(p->pattern.c_str(), p->flags | RRX_COMPILE_NO_DONLY, &p->alt);
+            if (rc) return rc;
+        }
+    }
+    if (!s->alt) {
+        int rc = rrx_scanner_create_ex(p->alt, s->max_len, s->capacity, s->create_flags, &s->alt);
+        if (rc) return rc;
+        if (s->timing) rrx_scanner_enable_timing(s->alt, 1);
+    }
+    rrx_scan_opts o;
+    std::memset(&o, 0, sizeof(o));
+    o.left_context = s->last.left_ctx;
+    o.entry = s->last.has_entry ? s->last.entry : nullptr;
+    return rrx_scanner_scan(s->alt, s->last.text, s->last.len, s->last.base, &o, s->last.stream);
+}
+
 int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64_t base_offset,
                      const rrx_scan_opts* opts, void* stream) {
     if (!s || (!d_text && len)) return set_err(RRX_ERR_ARG, "null argument");
@@ -309,6 +351,24 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     if (opts && opts->mode != RRX_MODE_LAZY_V1) return set_err(RRX_ERR_UNSUPPORTED, "only RRX_MODE_LAZY_V1 is implemented on the device");
     cudaStream_t st = (cudaStream_t)stream;
     const ProgHeader& h = s->p->prog.hdr();
+    if (h.donly) {
+        // The thread-owned candidate scan carries dominated states only.  An entry set with other states, or an
+        // explicit request (RRX_SCAN_NO_DONLY), goes to the fallback scanner: the same regex, row-bounded scan.
+        s->last.text = d_text; s->last.len = len; s->last.base = base_offset; s->last.left_ctx = opts ? opts->left_context : 0;
+        s->last.has_entry = opts && opts->entry; s->last.stream = stream;
+        bool outside = opts && (opts->flags & RRX_SCAN_NO_DONLY);
+        for (uint32_t w = 0; w < h.NW; w++) {
+            s->last.entry[w] = s->last.has_entry ? opts->entry[w] : 0u;
+            if (s->last.entry[w] & ~s->p->prog.blob[h.off_sparse + w]) outside = true;
+        }
+        s->use_alt = false;
+        if (outside) {
+            int rc = scan_on_alt(s);
+            if (rc) return rc;
+            s->use_alt = true;
+            return RRX_OK;
+        }
+    }
     const uint64_t tile_bytes = (uint64_t)TILE_BYTES;
     ScanParams sp;
     std::memset(&sp, 0, sizeof(sp));
@@ -324,6 +384,7 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
         sp.stagger_ns = e ? (uint32_t)atoi(e) : 1500u;
         const char* sv = getenv("RRX_SPARSE");     // 0 forces the dense row scan (A/B measurements)
         sp.sparse = (h.sparse_ok && !(sv && sv[0] == '0')) ? 1u : 0u;
+        sp.donly = h.donly;
         const char* ta = getenv("RRX_TICKET_AHEAD");
         sp.ticket_ahead = ta ? (uint32_t)atoi(ta) : 5u;
     }
@@ -400,6 +461,7 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
 
 int rrx_scanner_result(rrx_scanner* s, rrx_scan_result* out, void* stream) {
     if (!s || !out) return set_err(RRX_ERR_ARG, "null argument");
+    if (s->use_alt && s->alt) return rrx_scanner_result(s->alt, out, stream);
     cudaStream_t st = (cudaStream_t)stream;
     // counters and the shard composite come back together: one synchronisation per scan
     RRX_CUDA(cudaMemcpyAsync(s->h_ctr, s->d_ctrl, 32, cudaMemcpyDeviceToHost, st));
@@ -407,7 +469,17 @@ int rrx_scanner_result(rrx_scanner* s, rrx_scan_result* out, void* stream) {
     RRX_CUDA(cudaStreamSynchronize(st));
     s->h_shard_valid = true;
     const uint32_t* w32 = reinterpret_cast<const uint32_t*>(s->h_ctr);
-    out->error_bits = w32[1];
+    out->error_bits = w32[1] & ~(uint32_t)ERR_VERIFY_EDGE;
+    out->soft_bits = w32[1] & (uint32_t)ERR_VERIFY_EDGE;
+    out->reserved = 0;
+    if ((w32[1] & ERR_VERIFY_BUDGET) && s->p->prog.hdr().donly) {
+        // a verification walk of the thread-owned scan ran out of budget: the list is void.  Scan again with the
+        // row-bounded candidate scan (same regex, same arguments) and report that result.
+        int rc = scan_on_alt(s);
+        if (rc) return rc;
+        s->use_alt = true;
+        return rrx_scanner_result(s->alt, out, stream);
+    }
     out->n_matches = s->h_ctr[3];            // written by the ordering pass (sum of the tile counts)
     if (out->error_bits & ERR_STAGING_OVERFLOW) {
         // the overflow area of the staging list ran out: report it as "more matches than capacity" so that
@@ -424,6 +496,7 @@ int rrx_scanner_result(rrx_scanner* s, rrx_scan_result* out, void* stream) {
 
 int rrx_scanner_copy_matches(rrx_scanner* s, int64_t* host_out, uint64_t n, void* stream) {
     if (!s || (!host_out && n)) return set_err(RRX_ERR_ARG, "null argument");
+    s = act(s);
     if (n > s->capacity) return set_err(RRX_ERR_ARG, "more matches requested than the scanner holds");
     cudaStream_t st = (cudaStream_t)stream;
     if (n) RRX_CUDA(cudaMemcpyAsync(host_out, s->d_out, n * 16, cudaMemcpyDeviceToHost, st));
@@ -449,6 +522,7 @@ int rrx_apply_summary(const rrx_program* p, const uint32_t* summary, const uint3
 }
 int rrx_scanner_copy_pending(rrx_scanner* s, void* host_out, uint64_t cap, uint64_t* n_out, void* stream) {
     if (!s || !n_out) return set_err(RRX_ERR_ARG, "null argument");
+    s = act(s);
     cudaStream_t st = (cudaStream_t)stream;
     RRX_CUDA(cudaMemcpyAsync(s->h_ctr, s->d_ctrl, 32, cudaMemcpyDeviceToHost, st));
     RRX_CUDA(cudaStreamSynchronize(st));
@@ -502,6 +576,7 @@ int rrx_continue_starts(const rrx_program* p, const uint8_t* d_text, uint64_t le
 }
 
 int rrx_scanner_shard_summary(rrx_scanner* s, uint32_t* out, uint64_t cap_words, void* stream) {
+    s = act(s);
     const size_t n = 1 + 3 * (size_t)s->NW;
     if (!out || cap_words < n) return set_err(RRX_ERR_ARG, "summary buffer too small");
     if (s->h_shard_valid) {          // already fetched with the counters (rrx_scanner_result)
@@ -521,9 +596,11 @@ int rrx_scanner_enable_timing(rrx_scanner* s, int on) {
         RRX_CUDA(cudaEventCreate(&s->ev1));
     }
     s->timing = on != 0;
+    if (s->alt) rrx_scanner_enable_timing(s->alt, on);
     return RRX_OK;
 }
 int rrx_scanner_kernel_ms(rrx_scanner* s, float* ms) {
+    s = act(s);
     if (!s || !ms || !s->ev0) return set_err(RRX_ERR_ARG, "timing was not enabled");
     RRX_CUDA(cudaEventSynchronize(s->ev1));
     RRX_CUDA(cudaEventElapsedTime(ms, s->ev0, s->ev1));
@@ -532,6 +609,7 @@ int rrx_scanner_kernel_ms(rrx_scanner* s, float* ms) {
 
 int rrx_scanner_message_device(rrx_scanner* s, uint32_t* d_out, uint64_t cap_words, void* stream) {
     if (!s || !d_out) return set_err(RRX_ERR_ARG, "null argument");
+    s = act(s);
     const size_t n = 1 + 3 * (size_t)s->NW;
     if (cap_words < n + 8) return set_err(RRX_ERR_ARG, "message buffer too small");
     cudaStream_t st = (cudaStream_t)stream;
@@ -563,8 +641,9 @@ int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, u
         if (r.n_matches <= r.capacity) {
             rrx_matches* m = new rrx_matches;
             m->count = r.n_matches;
-            m->d_pairs = s->d_out;
-            s->owns_out = false;
+            rrx_scanner* owner = act(s);              // the list may live in the fallback scanner
+            m->d_pairs = owner->d_out;
+            owner->owns_out = false;
             rrx_scanner_free(s);
             if (mode == RRX_MODE_NO_OVERLAP) {
                 long long* filtered = nullptr;

@@ -517,6 +517,8 @@ namespace {
 struct Cut {
     bool ok = false;
     uint32_t byte = 0;
+    bool run_broad = false;      // a run of dominated states can loop on a broad byte class: it need never die
+    bool ver_broad = false;      // the backward verification walk can loop on a broad byte class without finding a start
     Bits D;
     struct Group { Bits k, pred; uint32_t flags; };
     std::vector<Group> groups;
@@ -567,6 +569,34 @@ uint32_t longest_run(const std::vector<Bits>& edges, const Bits& nodes, const Bi
     return std::min(best, cap);
 }
 
+// Does the sub-graph of `nodes` reachable from `from` contain a cycle through a position whose byte class
+// is broad (>= 96 of the 128 byte values, e.g. '.')?  Such a loop keeps a walk alive on almost any text.
+bool has_broad_cycle(const std::vector<Pos>& pos, const std::vector<Bits>& edges, const Bits& nodes, const Bits& from) {
+    const uint32_t P = (uint32_t)edges.size();
+    Bits reach(P);
+    std::vector<uint32_t> work;
+    for (uint32_t k : from.list()) if (nodes.has(k) && !reach.has(k)) { reach.add(k); work.push_back(k); }
+    while (!work.empty()) {
+        const uint32_t k = work.back();
+        work.pop_back();
+        for (uint32_t t : edges[k].list()) if (nodes.has(t) && !reach.has(t)) { reach.add(t); work.push_back(t); }
+    }
+    for (uint32_t b : reach.list()) {
+        if (__builtin_popcountll(pos[b].cls[0]) + __builtin_popcountll(pos[b].cls[1]) < 96) continue;
+        Bits seen(P);
+        std::vector<uint32_t> st;
+        for (uint32_t t : edges[b].list()) if (nodes.has(t) && !seen.has(t)) { seen.add(t); st.push_back(t); }
+        while (!st.empty()) {
+            const uint32_t k = st.back();
+            st.pop_back();
+            if (k == b) return true;
+            for (uint32_t t : edges[k].list()) if (nodes.has(t) && !seen.has(t)) { seen.add(t); st.push_back(t); }
+        }
+        if (seen.has(b)) return true;
+    }
+    return false;
+}
+
 Cut find_cut(const std::vector<Pos>& pos, const std::vector<Bits>& fol, const std::vector<Bits>& rfol,
              const Bits& first, const Bits& accept) {
     const uint32_t P = (uint32_t)pos.size();
@@ -613,12 +643,20 @@ Cut find_cut(const std::vector<Pos>& pos, const std::vector<Bits>& fol, const st
             }
         }
         if (too_many || c.groups.empty()) continue;
-        // static cost estimate
+        // static cost estimate.  A run of dominated states that can loop on a broad class ("z.*q" cut at z)
+        // leaves every row open — far worse than a verification walk that loops on one ("z.*q" cut at q: the
+        // walk back to the last z has a skip state and costs about what any cyclic walk is charged, 16).
         const uint32_t run = longest_run(fol, c.D, K, 16);
         uint32_t ver = 0;
-        for (auto& g : c.groups) if (!(g.flags & 1u)) ver = std::max(ver, longest_run(rfol, all, g.pred, 16));
+        Bits nonfirst(P);
+        for (uint32_t k = 0; k < P; k++) if (!first.has(k)) nonfirst.add(k);
+        for (auto& g : c.groups) if (!(g.flags & 1u)) {
+            ver = std::max(ver, longest_run(rfol, all, g.pred, 16));
+            if (has_broad_cycle(pos, rfol, nonfirst, g.pred)) c.ver_broad = true;
+        }
+        c.run_broad = has_broad_cycle(pos, fol, c.D, K);
         // ties: the smaller dominated set (more of the automaton is skipped between candidates)
-        const uint64_t cost = (uint64_t)byte_freq_score(v) * (run + ver) * 1024 + c.D.count();
+        const uint64_t cost = (uint64_t)byte_freq_score(v) * ((c.run_broad ? 1024u : run) + ver) * 1024 + c.D.count();
         if (cost < best_cost) { best_cost = cost; best = c; }
     }
     // not worth it when candidates are expected every few bytes and each starts a long run
@@ -694,7 +732,8 @@ struct RSkip {
     Bits F;
 };
 
-RSkip find_reverse_skip(const std::vector<Pos>& pos, const std::vector<Bits>& rfol, const Bits& first, const Bits& accept) {
+RSkip find_reverse_skip(const std::vector<Pos>& pos, const std::vector<Bits>& rfol, const Bits& first, const Bits& accept,
+                        const std::vector<Bits>& more_seeds) {
     const uint32_t P = (uint32_t)pos.size();
     std::vector<Bits> Bc(128, Bits(P));
     for (uint32_t c = 0; c < 128; c++)
@@ -711,6 +750,11 @@ RSkip find_reverse_skip(const std::vector<Pos>& pos, const std::vector<Bits>& rf
     std::vector<Bits> queue;
     queue.push_back(accept);
     seen.push_back(accept);
+    for (auto& s : more_seeds) {          // the verification walks of the candidate scan start at the cut groups' predecessors
+        bool known = false;
+        for (auto& k : seen) if (k.equals(s)) known = true;
+        if (!known && s.any()) { queue.push_back(s); seen.push_back(s); }
+    }
     RSkip best;
     for (size_t qi = 0; qi < queue.size() && qi < 48; qi++) {
         const Bits R = queue[qi];
@@ -742,7 +786,7 @@ RSkip find_reverse_skip(const std::vector<Pos>& pos, const std::vector<Bits>& rf
 
 }  // namespace
 
-Program build_program(const Automaton& a, const std::string& pattern, bool reduce) {
+Program build_program(const Automaton& a, const std::string& pattern, bool reduce, bool allow_donly) {
     std::vector<Pos> pos(a.P);
     for (uint32_t k = 0; k < a.P; k++) {
         pos[k].cls[0] = a.atoms[k].cls[0]; pos[k].cls[1] = a.atoms[k].cls[1];
@@ -817,7 +861,12 @@ Program build_program(const Automaton& a, const std::string& pattern, bool reduc
     h.sparse_ok = cut.ok ? 1u : 0u;
     h.cand_byte = cut.byte;
     h.n_groups = cut.ok ? (uint32_t)cut.groups.size() : 0u;
-    const RSkip rskip = find_reverse_skip(pos, rfol, first, accept);
+    std::vector<Bits> vseeds;
+    if (cut.ok) for (auto& g : cut.groups) if (!(g.flags & 1u)) vseeds.push_back(g.pred);
+    const RSkip rskip = find_reverse_skip(pos, rfol, first, accept, vseeds);
+    // thread-owned candidate scan (rrx_prog.h `donly`): runs of dominated states must die by themselves, and the
+    // verification walk must be short or have a skip state to run on
+    h.donly = (allow_donly && cut.ok && !cut.run_broad && (!cut.ver_broad || rskip.n >= 1)) ? 1u : 0u;
     const FSkip fskip = find_forward_skip(pos, fol, cut, accept);
     h.off_fskip = take(NW);
     h.fskip_n = fskip.n; h.fskip_lo = fskip.lo; h.fskip_hi = fskip.hi;

@@ -98,6 +98,7 @@ struct Program {
 
 // `reduce`: merge positions that are indistinguishable (same predecessors+class-union rule, or
 // same class/successors/accept) before laying out the device program.  Language-preserving.
-Program build_program(const Automaton& a, const std::string& pattern, bool reduce);
+// `allow_donly`: let the compiler choose the thread-owned candidate scan (rrx_prog.h `donly`) where it applies.
+Program build_program(const Automaton& a, const std::string& pattern, bool reduce, bool allow_donly = true);
 
 }  // namespace rrx

@@ -334,8 +334,10 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
                     if (g + 16 <= len) {
                         v[k] = __ldcs(reinterpret_cast<const uint4*>(sp.text + g));
                     } else {
-                        uint32_t w[4] = {0, 0, 0, 0};
-                        for (int b = 0; b < 16 && g + b < len; b++) w[b >> 2] |= (uint32_t)sp.text[g + b] << (8 * (b & 3));
+                        // bytes behind the end of the text: 0xff, a byte no position accepts (the thread-owned scan
+                        // relies on it; the other scans never look at them)
+                        uint32_t w[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+                        for (int b = 0; b < 16 && g + b < len; b++) w[b >> 2] = (w[b >> 2] & ~(0xffu << (8 * (b & 3)))) | ((uint32_t)sp.text[g + b] << (8 * (b & 3)));
                         v[k] = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
@@ -359,9 +361,28 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         bool dense = true, published = false;
         Comp<NW> agg, acc, inc;
         SparseTail tail;
-        tail.kq = tail.ks = tail.nacc = 0;
+        tail.kq = tail.ks = tail.nacc = tail.nruns = 0;
+        tail.rt = 0ull;
         tail.drained = 1;
-        if (sp.sparse) {
+        if (fw.donly(pv)) {
+            // Thread-owned candidate scan: every row — full, partial or empty — goes through it; there is no dense
+            // fallback.  The rows' exits (dominated states only) are known once the candidates have been followed;
+            // what a row does to carried states is decided by phase_d_kind.  All rows closed: the tile's aggregate
+            // is the last row's exit.
+            phase_a_cand<NW, F, true>(sp, pv, fw, ts, lane, tail);
+            const uint32_t kind = phase_d_kind<NW>(sp, pv, fw, ts, lane);
+            dense = false;
+            __syncwarp();
+            if (__all_sync(FULL, kind == K_CLOSED)) {
+                uint32_t bl[NW];
+#pragma unroll
+                for (int w = 0; w < NW; w++) bl[w] = ts.sum_b[w * TILE_ROWS + (TILE_ROWS - 1)];
+                comp_closed(agg, bl, 0);
+                const uint32_t arrived = lookback_publish_issue<NW>(sp, tile, agg, lane);
+                published = true;
+                lookback_publish_fold<NW>(sp, tile, arrived, lane);
+            }
+        } else if (sp.sparse) {
             if (dense_left == 0) {
                 const bool closed = phase_a_exit<NW>(sp, pv, fw, ts, lane);
                 if (__all_sync(FULL, closed)) {
@@ -376,7 +397,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
                         if (lane == 0) next_raw = atom_add_u32(sp.ticket, 1u);
                         have_next = true;
                     }
-                    const bool ok = phase_a_cand<NW>(sp, pv, fw, ts, lane, tail);
+                    const bool ok = phase_a_cand<NW, F, false>(sp, pv, fw, ts, lane, tail);
                     lookback_publish_fold<NW>(sp, tile, arrived, lane);       // the arrival count has long come back
                     dense = __any_sync(FULL, !ok) != 0;
                 }
@@ -445,8 +466,9 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             uint32_t carried = 0;
 #pragma unroll
             for (int w = 0; w < NW; w++) carried |= lane == 0 ? ts.misc[TS::M_ENTRY + w] : ts.sum_b[w * TILE_ROWS + lane - 1];
-            fast = __all_sync(FULL, tail.simple() && carried == 0) != 0;
-            if (!fast) sparse_drain<NW>(ts, lane, tail.kq, tail.ks);
+            // (only tiles that published early still have the rows' exits in sum_b: phase S1 rewrites them otherwise)
+            fast = published && __all_sync(FULL, tail.simple() && carried == 0) != 0;
+            if (!fast) sparse_drain<NW>(ts, lane, tail);
             __syncwarp();
         }
         if (fast) {

@@ -52,6 +52,14 @@ struct ProgHeader {
     // ("[a-z]+" inside a run).  While a run is in G it advances four bytes at a time as long as they
     // all lie in the range.  fskip_n = hi - lo + 1, 0: none.  The candidate byte is outside the range.
     uint32_t fskip_n, fskip_lo, fskip_hi, off_fskip;
+    // "Thread-owned" candidate scan (rrx_tile.cuh, DONLY): only the dominated states D are ever carried from
+    // row to row, tile to tile and shard to shard.  Whether a cut position is entered at a candidate byte is
+    // decided by a backward walk that may leave the row, the tile (global memory) and reach back to the left
+    // edge of the readable text, so no state outside D has to be known anywhere: no exit-set scans, no dense
+    // fallback.  Chosen by the compiler when runs of dominated states die by themselves (no broad-class
+    // loop inside D) and the verification walk is short or has a skip state; RRX_COMPILE_NO_DONLY forbids it.
+    uint32_t donly;
+    uint32_t pad2[3];
 };
 constexpr uint32_t RRX_MAX_GROUPS = 4;
 

@@ -53,7 +53,12 @@ constexpr int ROW_PITCH = 132;
 // error bits reported by the kernel
 // ERR_START_LOST: a lazy start walk died without finding a start and without reaching the left edge (only
 // possible when the entry set handed to the scan was not the exact one)
-enum : uint32_t { ERR_PENDING_OVERFLOW = 2u, ERR_STAGING_OVERFLOW = 4u, ERR_START_LOST = 8u };
+// ERR_VERIFY_EDGE (soft): in the thread-owned scan a verification walk reached the left edge of the readable
+// text still alive; the scan treated it as "nothing before the text".  Right for a whole text or its first shard;
+// a caller that knows there IS text further left (sharded scans) must widen the halo or rescan without DONLY.
+// ERR_VERIFY_BUDGET (hard): a verification walk exceeded its step budget; the scan gave up (results invalid),
+// the host rescans with the row-bounded candidate scan.
+enum : uint32_t { ERR_PENDING_OVERFLOW = 2u, ERR_STAGING_OVERFLOW = 4u, ERR_START_LOST = 8u, ERR_VERIFY_EDGE = 16u, ERR_VERIFY_BUDGET = 32u };
 
 // Kinds of chunk transfer functions S_out = A*S_in | b:
 //   K_CLOSED  A = 0: the exit does not depend on the entry
@@ -235,6 +240,7 @@ RRX_DEV void follow_terms(const uint32_t* terms, uint32_t n_terms, const uint32_
 // shared copy of the program; the run-time specialised policy (rrx_jit.cu) overrides these with
 // immediates.
 template <int NW> struct SparseFromSmem {
+    RRX_DEV bool donly(const ProgView& pv) const { return pv.h().donly != 0u; }
     RRX_DEV uint32_t sp_cand(const ProgView& pv) const { return pv.h().cand_byte; }
     RRX_DEV uint32_t sp_ngroups(const ProgView& pv) const { return pv.h().n_groups; }
     RRX_DEV uint32_t sp_D(const ProgView& pv, int w) const { return pv.sm[pv.h().off_sparse + w]; }
@@ -406,7 +412,8 @@ struct ScanParams {
     // Staging slots.  A tile with at most seg_stride matches writes them at slot tile*seg_stride (no
     // atomic, no waiting); a fuller tile takes a segment of the overflow area [ovf_base, out_cap) with one
     // atomicAdd on total[0].  seg_stride == 0: every tile allocates.  The ordering pass compacts.
-    uint32_t seg_stride, pad2_;
+    uint32_t seg_stride;
+    uint32_t donly;             // 1: thread-owned candidate scan (program header `donly`; see phase_a_cand<.., true>)
     unsigned long long ovf_base;
     uint32_t* err;
     uint32_t* shard_comp;       // [1+3*NW] composite of the whole shard (relative to an unknown entry)
@@ -428,14 +435,14 @@ template <int NW> struct TileState {
     uint32_t* misc;       // see M_* below
     uint32_t* rq;         // replay queue: RQ_CAP items of {row<<5 | quad, state[NW]}
     uint16_t* list;       // hit list for the balanced start scans; aliases sum_b/sum_U/sum_P
-    uint16_t* kst;        // [2][32]    known lazy starts of up to two matches per row: (end-1)<<8 | start, row-relative
+    uint32_t* kst;        // [2][32]    known lazy starts of up to two matches per row: (end-1)<<16 | (start - row start + KS_BIAS)
     uint64_t row0;        // first row of the tile
     static constexpr int M_RQCNT = 0, M_ENTRY = 8;
     static constexpr int MISC_WORDS = 8 + NW;
     static constexpr int RQ_CAP = NW <= 2 ? 64 : 16;
     static constexpr int LIST_CAP = 3 * NW * ROWS * 2;
     static constexpr size_t bytes() {
-        return (size_t)ROWS * ROW_PITCH + sizeof(uint32_t) * ((size_t)3 * NW * ROWS + 7 * ROWS + MISC_WORDS + RQ_CAP * (1 + NW));
+        return (size_t)ROWS * ROW_PITCH + sizeof(uint32_t) * ((size_t)3 * NW * ROWS + 8 * ROWS + MISC_WORDS + RQ_CAP * (1 + NW));
     }
     RRX_DEV void carve(uint8_t* base) {
         text = base;
@@ -447,7 +454,7 @@ template <int NW> struct TileState {
         hits = p; p += 4 * ROWS;
         cnt = p; p += ROWS;
         misc = p; p += MISC_WORDS;
-        kst = reinterpret_cast<uint16_t*>(p); p += ROWS;
+        kst = p; p += 2 * ROWS;
         rq = p;
         list = reinterpret_cast<uint16_t*>(sum_b);
     }
@@ -468,6 +475,12 @@ RRX_DEV int row_nbytes(const ScanParams& sp, uint64_t row0, int t) {
     const uint64_t rem = sp.len - lo;
     return rem >= ROW_BYTES ? ROW_BYTES : (int)rem;
 }
+
+// Known lazy starts travel as 16-bit values: start offset relative to the row start, biased by KS_BIAS (a start
+// found by a verification walk may lie in an earlier row or tile); 0 = not known.
+constexpr uint32_t KST_NONE = 0xffffffffu;
+constexpr int KS_BIAS = 32768;
+constexpr int VERIFY_BUDGET = 1 << 16;      // steps one verification walk may take outside its row
 
 // ===== phase A: per-row scan from the empty set (+ openness analysis) ===============================
 template <int NW, class F>
@@ -615,7 +628,123 @@ RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
     ts.sum_kind[t] = kind;
 #pragma unroll
     for (int q = 0; q < 4; q++) ts.hits[q * ROWS + t] = hit[q];
-    ts.kst[2 * t] = ts.kst[2 * t + 1] = (uint16_t)0xffffu;      // no lazy start known in advance
+    ts.kst[2 * t] = ts.kst[2 * t + 1] = KST_NONE;      // no lazy start known in advance
+}
+
+// ===== backward walk over the reversed automaton =======================================================
+// From the set R (positions that may consume the byte at shard-local offset e1, then e1-1, ...) until a
+// first-position consumes a byte: that byte is the right-most (= lazy) start.  Used for the lazy start of a match
+// (R = accept, e1 = end-1: phase C) and for the verification of a candidate byte in the thread-owned scan
+// (R = predecessors of a cut group, e1 = candidate-1: "was a predecessor active, and since where?").
+// Inside the tile the walk reads the staged rows (32-bit tile-relative offsets), before it global memory, down to
+// the left edge of the readable text.  While R equals the program's skip state F the walk runs over the text
+// word-wise looking only for the bytes that matter.
+struct WalkResult {
+    int64_t j;          // found: offset of the start byte; pend: offset of the next byte to consume (left of the edge)
+    bool found, pend;   // neither: the walk died — no start exists
+    bool over;          // the step budget ran out (verification walks only)
+};
+template <int NW, class F>
+RRX_DEV WalkResult back_walk(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW>& ts, uint32_t* R,
+                             int64_t e1, int budget) {
+    uint32_t Bc[NW], x[NW];
+    const int64_t tile_lo = ts.lo(), left_edge = -(int64_t)sp.left_ctx;
+    WalkResult wr;
+    wr.found = wr.pend = wr.over = false;
+    bool dead = false;
+    // Skip state: while R equals F, bytes other than b0/b1 (and below 0x80) neither find a start nor
+    // change R, so the walk just runs over them.
+    const uint32_t rsn = fw.rs_n(pv), rsb = fw.rs_bytes(pv);
+    const uint32_t b0 = rsb & 0xffu, b1 = (rsb >> 8) & 0xffu;
+    // fast path: while the walk stays inside the tile (32-bit tile-relative offsets, shared memory)
+    int rel = (e1 - tile_lo) < 0 ? -1 : (int)(e1 - tile_lo);
+    for (; rel >= 0; rel--) {
+        uint32_t c = ts.rel_byte((uint32_t)rel);
+        if (rsn) {
+            uint32_t d = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) d |= R[w] ^ fw.rs_F(pv, w);
+            if (d == 0) {
+                // bytes down to a word boundary, then whole words (SWAR: does the word hold b0, b1 or a
+                // byte >= 0x80?), then the bytes of the word that does
+                while (c != b0 && c != b1 && c < 128u && rel > 0 && (rel & 3) != 0) { rel--; c = ts.rel_byte((uint32_t)rel); }
+                if (c != b0 && c != b1 && c < 128u && rel >= 4 && (rel & 3) == 0) {
+                    const uint32_t* t32 = reinterpret_cast<const uint32_t*>(ts.text);
+                    const uint32_t B0 = b0 * 0x01010101u, B1 = b1 * 0x01010101u;
+                    int wi = (rel >> 2) - 1;                 // last whole word before byte rel
+                    for (; wi >= 0; wi--) {
+                        const uint32_t w = t32[wi + (wi >> 5)];          // 33 words per staged row
+                        const uint32_t x0 = w ^ B0, x1 = w ^ B1;
+                        const uint32_t z = ((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | w;
+                        if (z & 0x80808080u) break;
+                    }
+                    rel = wi * 4 + 3;                        // last byte of the word that stopped the run (or -1)
+                    if (rel < 0) break;                      // ran to the tile start inside F
+                    c = ts.rel_byte((uint32_t)rel);
+                    while (c != b0 && c != b1 && c < 128u && rel > 0) { rel--; c = ts.rel_byte((uint32_t)rel); }
+                } else {
+                    while (c != b0 && c != b1 && c < 128u && rel > 0) { rel--; c = ts.rel_byte((uint32_t)rel); }
+                }
+                if (c != b0 && c != b1 && c < 128u) { rel = -1; break; }      // ran to the tile start inside F
+            }
+        }
+        load_B<NW>(pv, c, Bc);
+        uint32_t m = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) { x[w] = R[w] & Bc[w]; m |= x[w] & fw.first(pv, w); }
+        if (m) { wr.found = true; break; }
+        fw.rfollow(pv, x, R);
+        if (!any_w<NW>(R)) { dead = true; break; }
+    }
+    int64_t j = (e1 - tile_lo) < 0 ? e1 : tile_lo + rel;
+    if (!wr.found && !dead) {
+        // slow path: the walk left the tile; continue in global memory
+        for (;;) {
+            if (j < left_edge) { wr.pend = true; break; }
+            uint32_t c = (uint32_t)sp.text[j];
+            if (rsn) {
+                uint32_t d = 0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) d |= R[w] ^ fw.rs_F(pv, w);
+                if (d == 0) {
+                    // bytes down to a word boundary, whole words (the text pointer is 16-byte aligned), then bytes
+                    while (c != b0 && c != b1 && c < 128u && j > left_edge && (j & 3) != 0) { j--; c = (uint32_t)sp.text[j]; }
+                    if (c != b0 && c != b1 && c < 128u && (j & 3) == 0 && j - 4 >= left_edge) {
+                        const uint32_t B0 = b0 * 0x01010101u, B1 = b1 * 0x01010101u;
+                        int64_t wj = j - 4;
+                        for (; wj >= left_edge; wj -= 4) {
+                            const uint32_t w = *reinterpret_cast<const uint32_t*>(sp.text + wj);
+                            const uint32_t x0 = w ^ B0, x1 = w ^ B1;
+                            const uint32_t z = ((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | w;
+                            if (z & 0x80808080u) break;
+                            if (budget > 0 && --budget == 0) { wr.over = true; break; }
+                        }
+                        if (wr.over) break;
+                        if (wj < left_edge) {
+                            j = wj + 3;                  // bytes below the last whole word (if any), one by one
+                            if (j < left_edge) { j = left_edge - 1; wr.pend = true; break; }
+                        } else {
+                            j = wj + 3;
+                        }
+                        c = (uint32_t)sp.text[j];
+                    }
+                    while (c != b0 && c != b1 && c < 128u && j > left_edge) { j--; c = (uint32_t)sp.text[j]; }
+                    if (c != b0 && c != b1 && c < 128u) { j = left_edge - 1; wr.pend = true; break; }   // still in F at the edge
+                }
+            }
+            load_B<NW>(pv, c, Bc);
+            uint32_t m = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) { x[w] = R[w] & Bc[w]; m |= x[w] & fw.first(pv, w); }
+            if (m) { wr.found = true; break; }
+            fw.rfollow(pv, x, R);
+            j--;
+            if (!any_w<NW>(R)) break;
+            if (budget > 0 && --budget == 0) { wr.over = true; break; }
+        }
+    }
+    wr.j = j;
+    return wr;
 }
 
 // ===== phase A, candidate-driven ("sparse") variant =================================================
@@ -645,7 +774,6 @@ RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
 //   exhausted); the caller then runs phase_a/phase_a2 for the whole tile.
 constexpr int SPARSE_MAX_CAND = 16;
 constexpr int SPARSE_BUDGET = 96;
-constexpr uint32_t KST_NONE = 0xffffu;
 
 template <int NW, class F>
 RRX_DEV bool phase_a_exit(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t) {
@@ -679,16 +807,23 @@ RRX_DEV bool phase_a_exit(const ScanParams& sp, const ProgView& pv, const F& fw,
     return true;
 }
 
-// What phase_a_cand leaves in registers: up to four match ends of the row (kq: end+1 per byte, most
-// recent in the low byte) with their lazy starts (ks: start+1, or 0 = not known).
+// What phase_a_cand leaves in registers: up to four match ends of the row (kq: end+1 per byte, most recent in
+// the low byte), each tagged with the run it belongs to (ks: tag per byte, 0 = lazy start not known), and the
+// lazy starts of the last four tagged runs (rt: 16 bits each, most recent lowest: start - row start + KS_BIAS).
 struct SparseTail {
-    uint32_t kq, ks, nacc, drained;
+    uint32_t kq, ks, nacc, drained, nruns;
+    unsigned long long rt;
+    // lazy start (biased, see KS_BIAS) of the run with tag g, 0 if it is not on record any more
+    RRX_DEV uint32_t start_of(uint32_t g) const {
+        const uint32_t back = nruns - g;
+        return (g == 0u || back > 3u) ? 0u : (uint32_t)(rt >> (16u * back)) & 0xffffu;
+    }
     // every match of the row is in the queue and has a known start
     RRX_DEV bool simple() const {
         if (drained) return false;
-        const uint32_t m = nacc == 0 ? 0u : (0xffffffffu >> (32u - 8u * nacc));
-        const uint32_t v = ks | ~m;                              // bytes beyond the queue count as known
-        return (((v - 0x01010101u) & ~v) & 0x80808080u) == 0u;   // no zero byte
+        for (uint32_t i = 0; i < nacc; i++)
+            if (start_of((ks >> (8u * i)) & 0xffu) == 0u) return false;
+        return true;
     }
 };
 
@@ -699,11 +834,11 @@ RRX_DEV void phase_tail_fast(const ScanParams& sp, const TileState<NW>& ts, int 
     const long long row_lo = sp.base + ts.lo() + ((long long)t << ROW_SHIFT);
     for (uint32_t i = 0; i < tail.nacc; i++) {
         const uint32_t sh = 8u * (tail.nacc - 1u - i);
-        const uint32_t e1 = (tail.kq >> sh) & 0xffu, s1 = (tail.ks >> sh) & 0xffu;
+        const uint32_t e1 = (tail.kq >> sh) & 0xffu, s16 = tail.start_of((tail.ks >> sh) & 0xffu);
         const unsigned long long slot = slot0 + i;
         if (slot < sp.out_cap) {
             long long* o = sp.out + 2 * slot;
-            o[0] = row_lo + (long long)s1 - 1;
+            o[0] = row_lo + (long long)s16 - KS_BIAS;
             o[1] = row_lo + (long long)e1;            // e1 = (end offset - 1) + 1
         }
     }
@@ -711,29 +846,37 @@ RRX_DEV void phase_tail_fast(const ScanParams& sp, const TileState<NW>& ts, int 
 
 // Unpack the match-end queue of phase_a_cand into the row's hit mask (and its first two known starts).
 template <int NW>
-RRX_DEV void sparse_drain(TileState<NW>& ts, int t, uint32_t kq, uint32_t ks) {
+RRX_DEV void sparse_drain(TileState<NW>& ts, int t, const SparseTail& q) {
     constexpr int ROWS = TILE_ROWS;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const uint32_t e1 = (kq >> (8 * i)) & 0xffu, s1 = (ks >> (8 * i)) & 0xffu;
-        if (e1) {
-            const uint32_t q = e1 - 1;
-            ts.hits[(q >> 5) * ROWS + t] |= 1u << (q & 31);
-            if (s1) {
-                const uint16_t rec = (uint16_t)((q << 8) | (s1 - 1));
-                if (ts.kst[2 * t] == (uint16_t)KST_NONE) ts.kst[2 * t] = rec;
-                else if (ts.kst[2 * t + 1] == (uint16_t)KST_NONE) ts.kst[2 * t + 1] = rec;
+        const uint32_t e1 = (q.kq >> (8 * i)) & 0xffu;
+        if (e1 && (uint32_t)i < q.nacc) {
+            const uint32_t pos = e1 - 1, s16 = q.start_of((q.ks >> (8 * i)) & 0xffu);
+            ts.hits[(pos >> 5) * ROWS + t] |= 1u << (pos & 31);
+            if (s16) {
+                const uint32_t rec = (pos << 16) | s16;
+                if (ts.kst[2 * t] == KST_NONE) ts.kst[2 * t] = rec;
+                else if (ts.kst[2 * t + 1] == KST_NONE) ts.kst[2 * t + 1] = rec;
             }
         }
     }
 }
 
-template <int NW, class F>
+// DONLY = false: the row-bounded scan described above (a closed full row, scanned from the empty set).
+// DONLY = true:  the THREAD-OWNED scan.  The lane owns every activation thread that crosses the cut at a
+//   candidate byte of ITS row, wherever that thread began: the verification walk continues before the row start
+//   (earlier rows of the tile, then global memory, to the left edge of the readable text).  Only dominated
+//   states are ever carried, so nothing outside D has to be known at the row start: no exit-set scan, no
+//   dense fallback, no bail-outs.  The row may be partial (nb < 128 valid bytes; the staged bytes behind them are
+//   >= 0x80).  sum_b[t] receives the dominated states alive after the row's last byte that stem from the row's
+//   own candidates; carried states are phase B's business as before.
+template <int NW, class F, bool DONLY>
 RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t, SparseTail& tail) {
     constexpr int ROWS = TILE_ROWS;
-    const ProgHeader& h = pv.h();
     const uint32_t ngr = fw.sp_ngroups(pv), cand = fw.sp_cand(pv);
     const uint8_t* rp = ts.text + t * ROW_PITCH;
+    const uint32_t rowend = DONLY ? (uint32_t)row_nbytes(sp, ts.row0, t) : (uint32_t)ROW_BYTES;
 
     // (1) candidate mask: bit p of cm[q] <=> byte 32q+p == cand
     uint32_t cm[4];
@@ -762,16 +905,18 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
     //   inner, once per byte: the plain step of a live lane — follow, mask, accept test — a dozen
     //          instructions; a lane that meets a candidate byte inside a run parks until the outer
     //          loop has handled it.
-    // Match ends are pushed into a 4-entry byte queue (kq: end+1, ks: known start+1 or 0) and
+    // Match ends are pushed into a 4-entry byte queue (kq: end+1, ks: tag of the run or 0) and
     // unpacked after the loops.
     uint32_t H[NW], Bc[NW], f[NW], DA[NW];
 #pragma unroll
     for (int w = 0; w < NW; w++) { H[w] = 0; DA[w] = fw.sp_D(pv, w); }
-    int budget = SPARSE_BUDGET;         // backward verification steps this row may spend
+    int budget = SPARSE_BUDGET;         // backward verification steps this row may spend (row-bounded scan)
     uint32_t p = 0;
-    uint32_t rs1 = 0;                   // 1 + lazy start of every match of the current run, or 0: not known
-    uint32_t kq = 0, ks = 0, nacc = 0, drained = 0;
-    uint32_t bail = ncand > SPARSE_MAX_CAND ? 1u : 0u;
+    uint32_t rs1 = 0;                   // tag of the current run if the lazy start of its matches is known, else 0
+    SparseTail q;
+    q.kq = q.ks = q.nacc = q.drained = q.nruns = 0;
+    q.rt = 0ull;
+    uint32_t bail = (!DONLY && ncand > SPARSE_MAX_CAND) ? 1u : 0u;
     uint32_t live = 0;                  // OR of the words of H
     uint32_t work = bail ? 0u : (uint32_t)ncand;     // non-zero while the lane has something left to do
     const SmemBytes rb(rp);
@@ -780,14 +925,18 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
     const uint32_t* rw32 = reinterpret_cast<const uint32_t*>(rp);
     uint32_t fs_tried = 0;
 #pragma unroll
-    for (int q = 0; q < 4; q++) ts.hits[q * ROWS + t] = 0;
-    ts.kst[2 * t] = ts.kst[2 * t + 1] = (uint16_t)KST_NONE;
+    for (int qd = 0; qd < 4; qd++) ts.hits[qd * ROWS + t] = 0;
+    ts.kst[2 * t] = ts.kst[2 * t + 1] = KST_NONE;
+    if (DONLY) {
+        // a verification walk somewhere ran out of budget: the scan is void, let the grid drain quickly
+        if (*reinterpret_cast<volatile uint32_t*>(sp.err) & ERR_VERIFY_BUDGET) work = 0u;
+    }
     while (RRX_WARP_ANY(work != 0)) {
         // ---- outer: the queue is full, or the lane is at a candidate byte (or jumps to its next one) ----
-        if (work != 0 && nacc >= 4) {
-            sparse_drain<NW>(ts, t, kq, ks);
-            kq = ks = nacc = 0;
-            drained = 1u;
+        if (work != 0 && q.nacc >= 4) {
+            sparse_drain<NW>(ts, t, q);
+            q.kq = q.ks = q.nacc = 0;
+            q.drained = 1u;
         } else if (work != 0) {
             const uint32_t fresh = live == 0 ? 1u : 0u;
             if (fresh) {
@@ -817,15 +966,33 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
                     uint32_t R[NW], Bq[NW], x[NW];
 #pragma unroll
                     for (int w = 0; w < NW; w++) R[w] = fw.sp_gpred(pv, g, w);
-                    for (int q = (int)p - 1; q >= 0; q--) {
-                        load_B<NW>(pv, rb.at((uint32_t)q), Bq);
-                        uint32_t m = 0;
+                    int qb = (int)p - 1;
+                    bool alive = true;
+                    if (!(DONLY && fw.rs_n(pv) != 0u)) {       // (with a skip state the general walker below is the faster one)
+                        for (; qb >= 0; qb--) {
+                            load_B<NW>(pv, rb.at((uint32_t)qb), Bq);
+                            uint32_t m = 0;
 #pragma unroll
-                        for (int w = 0; w < NW; w++) { x[w] = R[w] & Bq[w]; m |= x[w] & fw.first(pv, w); }
-                        if (m) { inj = true; s = q; break; }
-                        fw.rfollow(pv, x, R);
-                        if (!any_w<NW>(R)) break;
-                        if (--budget < 0) { bail = 1u; break; }
+                            for (int w = 0; w < NW; w++) { x[w] = R[w] & Bq[w]; m |= x[w] & fw.first(pv, w); }
+                            if (m) { inj = true; s = qb; break; }
+                            fw.rfollow(pv, x, R);
+                            if (!any_w<NW>(R)) { alive = false; break; }
+                            if (!DONLY && --budget < 0) { bail = 1u; break; }
+                        }
+                    }
+                    if (DONLY && !inj && alive) {
+                        // the walk goes on before the row start: earlier rows of the tile, then global memory
+                        const int64_t row_lo = ts.lo() + ((int64_t)t << ROW_SHIFT);
+                        const WalkResult wr = back_walk<NW>(sp, pv, fw, ts, R, row_lo + qb, VERIFY_BUDGET);
+                        if (wr.found) {
+                            inj = true;
+                            const int64_t d = wr.j - row_lo;
+                            s = d < -(int64_t)(KS_BIAS - 1) ? -KS_BIAS : (int)d;      // -KS_BIAS: too far back to record
+                        } else if (wr.over) {
+                            atomicOr(sp.err, ERR_VERIFY_BUDGET);
+                        } else if (wr.pend) {
+                            atomicOr(sp.err, ERR_VERIFY_EDGE);      // soft: "nothing before the readable text"
+                        }
                     }
                 }
                 if (inj) {
@@ -835,7 +1002,13 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
                     for (int w = 0; w < NW; w++) nx[w] |= fw.sp_gk(pv, g, w);
                 }
             }
-            rs1 = (fresh && n_inj == 1) ? (uint32_t)(s_inj + 1) : 0u;       // a candidate inside a run: ambiguous from here on
+            // a run fed by one injection: its matches share the start found.  A candidate inside a run: ambiguous from here on.
+            rs1 = 0u;
+            if (fresh && n_inj == 1 && s_inj > -KS_BIAS) {
+                q.rt = (q.rt << 16) | (unsigned long long)(uint32_t)(s_inj + KS_BIAS);
+                q.nruns++;
+                rs1 = q.nruns & 0xffu;
+            }
             uint32_t a = 0;
             live = 0;
 #pragma unroll
@@ -845,18 +1018,19 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
                 a |= H[w] & fw.accept(pv, w);
             }
             p++;
-            if (a) { kq = (kq << 8) | p; ks = (ks << 8) | rs1; nacc++; }
-            if (p == (uint32_t)ROW_BYTES || bail) { live = 0; ncand = 0; }
+            if (a) { q.kq = (q.kq << 8) | p; q.ks = (q.ks << 8) | rs1; q.nacc++; }
+            if (!DONLY && (p == (uint32_t)ROW_BYTES || bail)) { live = 0; ncand = 0; }
             work = live | (uint32_t)ncand;
         }
         // ---- inner: plain steps while the run lives and no candidate byte comes up ----
         // (branch-free: every lane computes the step, lanes that are not in a run or stand on a
         // candidate byte just do not commit it)
-        // Two steps per vote: the second one is harmless for lanes that have stopped.  There is no
-        // end-of-row test: the 4 pad bytes behind every staged row hold 0xff (set once per warp by the
+        // Two steps per vote: the second one is harmless for lanes that have stopped.  Row-bounded scan: there is no
+        // end-of-row test — the 4 pad bytes behind every staged row hold 0xff (set once per warp by the
         // kernel; the emulator's fill pattern is >= 0x80 too), a byte no position accepts, so a run that
-        // reaches the row end dies there — and every candidate has been consumed by then.
-        uint32_t go = nacc < 4 ? live : 0u;
+        // reaches the row end dies there, and every candidate has been consumed by then.  Thread-owned scan: a run
+        // that reaches the row end stops THERE with its state intact (the row's exit).
+        uint32_t go = (q.nacc < 4 && (!DONLY || p < rowend)) ? live : 0u;
 #define RRX_SPARSE_STEP()                                                                       \
         {                                                                                           \
             const uint32_t c = rb.at(p);                /* p == 128: the row's pad, a byte >= 0x80 */ \
@@ -872,11 +1046,11 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
             }                                                                                       \
             p += step ? 1u : 0u;                                                                    \
             const bool take = step && a != 0;                                                       \
-            kq = take ? ((kq << 8) | p) : kq;                                                       \
-            ks = take ? ((ks << 8) | rs1) : ks;                                                     \
-            nacc += take ? 1u : 0u;                                                                 \
+            q.kq = take ? ((q.kq << 8) | p) : q.kq;                                                 \
+            q.ks = take ? ((q.ks << 8) | rs1) : q.ks;                                               \
+            q.nacc += take ? 1u : 0u;                                                               \
             live = step ? lv : live;                    /* dies on the pad at the latest */          \
-            go = (step && nacc < 4) ? live : 0u;        /* queue full: parked until drained */     \
+            go = (step && q.nacc < 4 && (!DONLY || p < rowend)) ? live : 0u;   /* queue full: parked until drained */ \
         }
         while (RRX_WARP_ANY(go != 0)) {
             // skip: a run in the forward skip state G advances four bytes at a time while they all lie
@@ -898,22 +1072,96 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
                     }
                 }
                 if (dG != 0) fs_tried = 0u;
+                if (DONLY && p >= rowend) go = 0u;
             }
             RRX_SPARSE_STEP()
             RRX_SPARSE_STEP()
         }
 #undef RRX_SPARSE_STEP
-        work = live | (uint32_t)ncand;
+        if (DONLY && p >= rowend) {         // the row is done; H (if the run still lives) is the row's exit
+            ncand = 0;
+            work = 0u;
+        } else {
+            work = live | (uint32_t)ncand;
+        }
     }
     if (bail) return false;
+    if (DONLY) {
+        // exit of the row: the run alive after the last byte (a run that ended earlier left H empty)
+#pragma unroll
+        for (int w = 0; w < NW; w++) ts.sum_b[w * ROWS + t] = (p >= rowend && rowend != 0u) ? H[w] : 0u;
+    }
     // The queue is handed to the caller: a tile whose rows all kept their matches in the queue, with
     // known starts, and whose rows receive no carried state writes them straight from registers
     // (phase_tail_fast); otherwise the caller drains it into the hit masks (sparse_drain).
-    tail.kq = kq;
-    tail.ks = ks;
-    tail.nacc = nacc;
-    tail.drained = drained;
+    tail = q;
     return true;
+}
+
+// ===== thread-owned scan: what a row does to CARRIED dominated states =================================
+// Row kind for the composites: K_IDENT (no bytes), K_CLOSED (no carried state survives the row — decided by
+// walking back from the row end with the dominated positions that can still lie on a surviving path; on
+// ordinary text that set is empty after a byte or two), else the survivor analysis of phase A restricted to D:
+// K_RANK1 with sum_U / sum_P, or K_HARD.
+template <int NW, class F>
+RRX_DEV uint32_t phase_d_kind(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t) {
+    constexpr int ROWS = TILE_ROWS;
+    const int nb = row_nbytes(sp, ts.row0, t);
+    if (nb == 0) { ts.sum_kind[t] = K_IDENT; return K_IDENT; }
+    const SmemBytes rb(ts.text + t * ROW_PITCH);
+    uint32_t A[NW], x[NW], Bc[NW], f[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) A[w] = fw.sp_D(pv, w);
+    bool open = true;
+    for (int q = nb - 1; q >= 0; q--) {
+        load_B<NW>(pv, rb.at((uint32_t)q), Bc);
+#pragma unroll
+        for (int w = 0; w < NW; w++) x[w] = A[w] & Bc[w];
+        if (!any_w<NW>(x)) { open = false; break; }
+        fw.rfollow(pv, x, A);
+#pragma unroll
+        for (int w = 0; w < NW; w++) A[w] &= fw.sp_D(pv, w);
+        if (!any_w<NW>(A)) { open = false; break; }
+    }
+    if (!open) { ts.sum_kind[t] = K_CLOSED; return K_CLOSED; }
+    // open: survivors of ALL dominated states, no injection
+    uint32_t U[NW], J[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) { U[w] = fw.sp_D(pv, w); J[w] = 0; }
+    int pc = -1;
+    for (int p = 0; p < nb; p++) {
+        load_B<NW>(pv, rb.at((uint32_t)p), Bc);
+        fw.follow(pv, U, f);
+#pragma unroll
+        for (int w = 0; w < NW; w++) U[w] = f[w] & Bc[w] & fw.sp_D(pv, w);
+        if (!any_w<NW>(U)) { ts.sum_kind[t] = K_CLOSED; return K_CLOSED; }       // (cannot happen: the walk above said open)
+        if (pc < 0 && popc_w<NW>(U) == 1) {
+            pc = p + 1;
+#pragma unroll
+            for (int w = 0; w < NW; w++) J[w] = U[w];
+        }
+    }
+    const uint32_t kind = pc < 0 ? K_HARD : K_RANK1;
+    uint32_t R[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) R[w] = J[w];
+    if (pc >= 0) {
+        for (int q = pc - 1; q >= 0; q--) {           // entry states that lead to the lone survivor
+            load_B<NW>(pv, rb.at((uint32_t)q), Bc);
+#pragma unroll
+            for (int w = 0; w < NW; w++) x[w] = R[w] & Bc[w];
+            fw.rfollow(pv, x, R);
+#pragma unroll
+            for (int w = 0; w < NW; w++) R[w] &= fw.sp_D(pv, w);
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        ts.sum_U[w * ROWS + t] = U[w];
+        ts.sum_P[w * ROWS + t] = R[w];
+    }
+    ts.sum_kind[t] = kind;
+    return kind;
 }
 
 // ===== phase A2: the warp replays the queued 4-byte words, one per lane ==============================
@@ -995,12 +1243,13 @@ template <int NW, class F>
 RRX_DEV void row_replay_exit(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW>& ts, int t,
                              uint32_t* X) {
     const int nb = row_nbytes(sp, ts.row0, t);
+    const bool dn = fw.donly(pv);          // thread-owned scan: only dominated states are carried
     uint32_t Bc[NW], f[NW];
     for (int p = 0; p < nb && any_w<NW>(X); p++) {
         load_B<NW>(pv, ts.row_byte(t, p), Bc);
         fw.follow(pv, X, f);
 #pragma unroll
-        for (int w = 0; w < NW; w++) X[w] = f[w] & Bc[w];
+        for (int w = 0; w < NW; w++) X[w] = f[w] & Bc[w] & (dn ? fw.sp_D(pv, w) : 0xffffffffu);
     }
 }
 
@@ -1130,16 +1379,28 @@ RRX_DEV uint32_t phase_b(const ScanParams& sp, const ProgView& pv, const F& fw, 
     }
     uint32_t hit[4] = {0, 0, 0, 0};
     bool touched = false;
+    const bool dn = fw.donly(pv);          // thread-owned scan: only dominated states are carried
     for (int p = 0; p < nb && any_w<NW>(X); p++) {
         load_B<NW>(pv, ts.row_byte(t, p), Bc);
         fw.follow(pv, X, f);
         uint32_t a2 = 0;
 #pragma unroll
         for (int w = 0; w < NW; w++) {
-            X[w] = f[w] & Bc[w];
+            X[w] = f[w] & Bc[w] & (dn ? fw.sp_D(pv, w) : 0xffffffffu);
             a2 |= X[w] & fw.accept(pv, w);
         }
         if (a2) { hit[p >> 5] |= 1u << (p & 31); touched = true; }
+    }
+    if (dn && touched) {
+        // A match end the carried state reaches as well: the start the row's own scan recorded for it (which may
+        // lie before the row) need not be the lazy one any more — let the backward walk decide.
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const uint32_t k = ts.kst[2 * t + i];
+            const uint32_t pos = k >> 16, wd = pos >> 5;
+            const uint32_t hw = wd == 0u ? hit[0] : wd == 1u ? hit[1] : wd == 2u ? hit[2] : hit[3];
+            if (k != KST_NONE && ((hw >> (pos & 31u)) & 1u)) ts.kst[2 * t + i] = KST_NONE;
+        }
     }
     uint32_t c = 0;
 #pragma unroll
@@ -1152,97 +1413,27 @@ RRX_DEV uint32_t phase_b(const ScanParams& sp, const ProgView& pv, const F& fw, 
 }
 
 // ===== phase C: resolve the lazy start of every match and write (start,end) ========================
-// Backward walk over the reversed automaton from the accepting positions, starting with the byte
-// at shard-local offset e-1; stops at the first (= right-most) start that works: lazy.
+// Backward walk from the accepting positions, starting with the byte at shard-local offset e-1; stops at the
+// first (= right-most) start that works: lazy.
 template <int NW, class F>
 RRX_DEV void resolve_and_write(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW>& ts,
                                int64_t e, unsigned long long slot, uint32_t rank_in_tile) {
-    uint32_t R[NW], Bc[NW], x[NW];
+    uint32_t R[NW];
 #pragma unroll
     for (int w = 0; w < NW; w++) R[w] = fw.accept(pv, w);
-    const int64_t tile_lo = ts.lo(), left_edge = -(int64_t)sp.left_ctx;
-    bool pend = false, found = false, dead = false;
-    // Skip state: while R equals F, bytes other than b0/b1 (and below 0x80) neither find a start nor
-    // change R, so the walk just runs over them.
-    const uint32_t rsn = fw.rs_n(pv), rsb = fw.rs_bytes(pv);
-    const uint32_t b0 = rsb & 0xffu, b1 = (rsb >> 8) & 0xffu;
-    // fast path: while the walk stays inside the tile (32-bit tile-relative offsets, shared memory)
-    int rel = (int)(e - 1 - tile_lo);
-    for (; rel >= 0; rel--) {
-        uint32_t c = ts.rel_byte((uint32_t)rel);
-        if (rsn) {
-            uint32_t d = 0;
-#pragma unroll
-            for (int w = 0; w < NW; w++) d |= R[w] ^ fw.rs_F(pv, w);
-            if (d == 0) {
-                // bytes down to a word boundary, then whole words (SWAR: does the word hold b0, b1 or a
-                // byte >= 0x80?), then the bytes of the word that does
-                while (c != b0 && c != b1 && c < 128u && rel > 0 && (rel & 3) != 0) { rel--; c = ts.rel_byte((uint32_t)rel); }
-                if (c != b0 && c != b1 && c < 128u && rel >= 4 && (rel & 3) == 0) {
-                    const uint32_t* t32 = reinterpret_cast<const uint32_t*>(ts.text);
-                    const uint32_t B0 = b0 * 0x01010101u, B1 = b1 * 0x01010101u;
-                    int wi = (rel >> 2) - 1;                 // last whole word before byte rel
-                    for (; wi >= 0; wi--) {
-                        const uint32_t w = t32[wi + (wi >> 5)];          // 33 words per staged row
-                        const uint32_t x0 = w ^ B0, x1 = w ^ B1;
-                        const uint32_t z = ((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | w;
-                        if (z & 0x80808080u) break;
-                    }
-                    rel = wi * 4 + 3;                        // last byte of the word that stopped the run (or -1)
-                    if (rel < 0) break;                      // ran to the tile start inside F
-                    c = ts.rel_byte((uint32_t)rel);
-                    while (c != b0 && c != b1 && c < 128u && rel > 0) { rel--; c = ts.rel_byte((uint32_t)rel); }
-                } else {
-                    while (c != b0 && c != b1 && c < 128u && rel > 0) { rel--; c = ts.rel_byte((uint32_t)rel); }
-                }
-                if (c != b0 && c != b1 && c < 128u) { rel = -1; break; }      // ran to the tile start inside F
-            }
-        }
-        load_B<NW>(pv, c, Bc);
-        uint32_t m = 0;
-#pragma unroll
-        for (int w = 0; w < NW; w++) { x[w] = R[w] & Bc[w]; m |= x[w] & fw.first(pv, w); }
-        if (m) { found = true; break; }
-        fw.rfollow(pv, x, R);
-        if (!any_w<NW>(R)) { dead = true; break; }     // only possible when the match began in the entry set
-    }
-    int64_t j = tile_lo + rel;
-    if (!found && !dead) {
-        // slow path: the walk left the tile; continue in global memory
-        for (;;) {
-            if (j < left_edge) { pend = true; break; }
-            uint32_t c = (uint32_t)sp.text[j];
-            if (rsn) {
-                uint32_t d = 0;
-#pragma unroll
-                for (int w = 0; w < NW; w++) d |= R[w] ^ fw.rs_F(pv, w);
-                if (d == 0) {
-                    while (c != b0 && c != b1 && c < 128u && j > left_edge) { j--; c = (uint32_t)sp.text[j]; }
-                    if (c != b0 && c != b1 && c < 128u) { j = left_edge - 1; pend = true; break; }   // still in F at the edge
-                }
-            }
-            load_B<NW>(pv, c, Bc);
-            uint32_t m = 0;
-#pragma unroll
-            for (int w = 0; w < NW; w++) { x[w] = R[w] & Bc[w]; m |= x[w] & fw.first(pv, w); }
-            if (m) { found = true; break; }
-            fw.rfollow(pv, x, R);
-            j--;
-            if (!any_w<NW>(R)) break;
-        }
-    }
+    const WalkResult wr = back_walk<NW>(sp, pv, fw, ts, R, e - 1, 0);
     if (slot < sp.out_cap) {
         long long* o = sp.out + 2 * slot;
-        o[0] = found ? sp.base + j : -1;        // -1: the start lies left of the available text
+        o[0] = wr.found ? sp.base + wr.j : -1;        // -1: the start lies left of the available text
         o[1] = sp.base + e;
     }
-    if (!found && !pend) atomicOr(sp.err, ERR_START_LOST);
-    if (pend) {
+    if (!wr.found && !wr.pend) atomicOr(sp.err, ERR_START_LOST);
+    if (wr.pend) {
         const unsigned long long k = atomicAdd(sp.total + 1, 1ull);
         if (k < sp.pending_cap) {
             PendingStart& ps = sp.pending[k];
             ps.match_index = ((uint64_t)(ts.row0 / TILE_ROWS) << 32) | rank_in_tile;
-            ps.next_offset = j;
+            ps.next_offset = wr.j;
 #pragma unroll
             for (int w = 0; w < NW; w++) ps.R[w] = R[w];
         } else {
@@ -1257,13 +1448,13 @@ RRX_DEV bool write_known(const ScanParams& sp, const TileState<NW>& ts, uint32_t
     const uint32_t row = rel >> ROW_SHIFT, p = rel & (ROW_BYTES - 1);
     const uint32_t k0 = ts.kst[2 * row], k1 = ts.kst[2 * row + 1];
     uint32_t s;
-    if ((k0 >> 8) == p) s = k0 & 0xffu;
-    else if ((k1 >> 8) == p) s = k1 & 0xffu;
+    if ((k0 >> 16) == p) s = k0 & 0xffffu;
+    else if ((k1 >> 16) == p) s = k1 & 0xffffu;
     else return false;
     if (slot < sp.out_cap) {
         long long* o = sp.out + 2 * slot;
         const long long row_lo = sp.base + ts.lo() + ((long long)row << ROW_SHIFT);
-        o[0] = row_lo + s;
+        o[0] = row_lo + (long long)s - KS_BIAS;
         o[1] = row_lo + p + 1;
     }
     return true;

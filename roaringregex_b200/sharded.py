@@ -24,7 +24,9 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from . import Scanner, RRegex, lib, _check
+from . import Scanner, RRegex, lib, _check, SOFT_VERIFY_EDGE
+
+ERR_VERIFY_EDGE, ERR_VERIFY_BUDGET = 16, 32      # rrx_tile.cuh
 
 PREFIX_WINDOW = 1 << 20          # bytes of a shard rescanned with the exact entry before giving up
 PENDING_RECORD = 8 + 8 + 4 * 32  # sizeof(PendingStart)
@@ -38,6 +40,7 @@ class ShardScan:
     summary: np.ndarray         # composite of the scanned range [kind, b, U, P]
     pending: list = field(default_factory=list)   # [(match_index, global_next_offset, R words)]
     handle: object = None       # backend-specific (device list)
+    want_fallback: bool = False  # thread-owned scan (rrx_info.donly) not valid for this shard: everybody rescans without it
 
 
 class DeviceBackend:
@@ -53,21 +56,24 @@ class DeviceBackend:
         self.prefix_scanner = None
         self.words = regex.info["words"]
 
-    def scan(self, length: int, entry, fetch: bool, prefix: bool = False, scanner=None) -> ShardScan:
+    def scan(self, length: int, entry, fetch: bool, prefix: bool = False, scanner=None, no_donly: bool = False) -> ShardScan:
         sc = scanner or self.scanner
         if prefix:
             if self.prefix_scanner is None:
                 self.prefix_scanner = Scanner(self.regex, min(self.len, PREFIX_WINDOW), min(self.len, PREFIX_WINDOW) + 16, jit=False)
             sc = self.prefix_scanner
-        sc.scan(self.ptr, length, self.base, self.halo, entry, self.stream)
+        sc.scan(self.ptr, length, self.base, self.halo, entry, self.stream, no_donly=no_donly)
         r = sc.result(self.stream)
         if r["error_bits"]:
             raise RuntimeError(f"scan kernel error bits {r['error_bits']}")
         if r["n_matches"] > r["capacity"]:
             raise RuntimeError("match buffer too small for this shard")
         pend = self._fetch_pending(sc, r["n_pending"])
+        # the thread-owned scan assumed "nothing left of the readable text" (soft bit) although there is, or fell
+        # back by itself (budget): its composite is not comparable with the other ranks' — all redo without it
+        want = (not no_donly) and (bool(r["soft_bits"] & SOFT_VERIFY_EDGE and self.base - self.halo > 0) or sc.used_fallback)
         return ShardScan(n=r["n_matches"], matches=sc.matches(self.stream) if fetch else None,
-                         summary=sc.shard_summary(self.stream), pending=pend, handle=sc)
+                         summary=sc.shard_summary(self.stream), pending=pend, handle=sc, want_fallback=want)
 
     def _fetch_pending(self, sc, n_pending: int) -> list:
         pend = []
@@ -112,14 +118,19 @@ class DeviceBackend:
         mine = g[comm.dist.get_rank()]
         ctr = mine[1 + 3 * W:]
         err, n_matches, n_pending = int(ctr[1]), int(ctr[6]) | (int(ctr[7]) << 32), int(ctr[4]) | (int(ctr[5]) << 32)
-        if err:
+        if err & ~(ERR_VERIFY_EDGE | ERR_VERIFY_BUDGET):
             raise RuntimeError(f"scan kernel error bits {err}")
         if n_matches > self.capacity:
             raise RuntimeError("match buffer too small for this shard")
         pend = self._fetch_pending(sc, n_pending)               # rare; no collective involved
-        spec = ShardScan(n=n_matches, matches=sc.matches(self.stream) if fetch else None,
-                         summary=mine[:1 + 3 * W].copy(), pending=pend, handle=sc)
-        msgs = np.concatenate([g[:, :1 + 3 * W], np.minimum(g[:, 1 + 3 * W + 4:1 + 3 * W + 5], 0xffffffff)], axis=1).astype(np.uint32)
+        # every rank derives every rank's "redo without the thread-owned scan" flag from the gathered error words
+        errs = g[:, 1 + 3 * W + 1].astype(np.int64)
+        left_text = np.array([r > 0 for r in range(g.shape[0])])         # ranks with text left of their halo
+        flags = ((errs & ERR_VERIFY_BUDGET) != 0) | (((errs & ERR_VERIFY_EDGE) != 0) & left_text)
+        spec = ShardScan(n=n_matches, matches=sc.matches(self.stream) if fetch and not flags.any() else None,
+                         summary=mine[:1 + 3 * W].copy(), pending=pend, handle=sc, want_fallback=bool(flags[comm.dist.get_rank()]))
+        msgs = np.concatenate([g[:, :1 + 3 * W], np.minimum(g[:, 1 + 3 * W + 4:1 + 3 * W + 5], 0xffffffff),
+                               flags[:, None].astype(np.uint32)], axis=1).astype(np.uint32)
         return spec, msgs
 
     def head(self, scan: ShardScan, k: int) -> np.ndarray:
@@ -208,32 +219,48 @@ def scan_sharded_finish(regex: RRegex, backend, comm, rank: int, world: int, tok
 
 
 def scan_sharded(regex: RRegex, backend, comm, rank: int, world: int, fetch: bool = False, _token=None) -> ShardResult:
+    """The per-rank procedure (see _scan_sharded).  A program with the thread-owned candidate scan (rrx_info.donly) runs
+    it first; if any rank reports that it does not hold for its shard — a verification walk reached the left edge of
+    the rank's readable text although there is text further left, or ran out of budget — every rank sees that in the
+    gathered messages and all of them redo the step with the row-bounded scan (rare: needs a verification walk
+    longer than the halo)."""
+    res = _scan_sharded(regex, backend, comm, rank, world, fetch, _token, False)
+    if res is None:
+        res = _scan_sharded(regex, backend, comm, rank, world, fetch, None, True)
+    return res
+
+
+def _scan_sharded(regex: RRegex, backend, comm, rank: int, world: int, fetch: bool, _token, no_donly: bool):
     """The per-rank procedure.  `comm.allgather(np.ndarray) -> (world, ...) ndarray` is the only
     collective on the data path: ONE message of 1+3W+1 words per rank (the shard summary and the
     number of unfinished start scans).  Everything else each rank derives locally from the gathered
     summaries (every rank can fold every other rank's entry), so in the common case — no entry set
     survives into any shard, no start scan crosses a halo — a step has exactly one collective.
     `comm.allgather_obj(obj)` (pickled, tiny) serves the rare hand-over of unfinished start scans."""
-    if _token is None:
+    kw = {"no_donly": True} if no_donly else {}
+    if _token is None and not no_donly:
         _token = scan_sharded_begin(regex, backend, comm)
     if _token is not None:
         spec, first_gather = backend.scan_gather_end(comm, _token, fetch)    # scan + exchange already enqueued, one sync
     else:
-        spec, first_gather = backend.scan(backend.len, None, fetch), None     # speculative: empty entry
+        spec, first_gather = backend.scan(backend.len, None, fetch, **kw), None     # speculative: empty entry
     advertised, result, last_entry = spec, None, None
     for _round in range(max(world, 1)):
         if _round == 0 and first_gather is not None:
             gathered = first_gather
         else:
-            msg = np.concatenate([advertised.summary.astype(np.uint32), np.array([len(spec.pending)], dtype=np.uint32)])
+            msg = np.concatenate([advertised.summary.astype(np.uint32),
+                                  np.array([len(spec.pending), int(spec.want_fallback)], dtype=np.uint32)])
             gathered = comm.allgather(msg)
-        summaries, spec_pending = gathered[:, :-1], gathered[:, -1]
+        summaries, spec_pending, fallback = gathered[:, :-2], gathered[:, -2], gathered[:, -1]
+        if fallback.any() and not no_donly:
+            return None                                           # same data on every rank: everybody redoes the step
         folds = fold_entries(regex, summaries)
         entry, _ = folds[rank]
         if result is None or not np.array_equal(entry, last_entry):
             last_entry = entry
             if entry.any():
-                result = _repair(regex, backend, spec, entry, fetch)
+                result = _repair(regex, backend, spec, entry, fetch, kw)
                 if result.rescans == 2:
                     advertised = result.tail                      # now computed with the exact entry
             else:
@@ -247,12 +274,12 @@ def scan_sharded(regex: RRegex, backend, comm, rank: int, world: int, fetch: boo
     return result
 
 
-def _repair(regex, backend, spec: ShardScan, entry: np.ndarray, fetch: bool) -> ShardResult:
+def _repair(regex, backend, spec: ShardScan, entry: np.ndarray, fetch: bool, kw: dict) -> ShardResult:
     window = min(backend.len, PREFIX_WINDOW)
     if window < backend.len:
         window -= window % 4096
-    a = backend.scan(window, None, True, prefix=True)             # speculative state after the window
-    b = backend.scan(window, entry, True, prefix=True)            # exact state after the window
+    a = backend.scan(window, None, True, prefix=True, **kw)       # speculative state after the window
+    b = backend.scan(window, entry, True, prefix=True, **kw)      # exact state after the window
     sa = apply_summary(regex, a.summary, np.zeros_like(entry))
     sb = apply_summary(regex, b.summary, entry)
     if np.array_equal(sa, sb) or window == backend.len:
@@ -261,8 +288,10 @@ def _repair(regex, backend, spec: ShardScan, entry: np.ndarray, fetch: bool) -> 
         return ShardResult(len(b.matches) + spec.n - skip, b.matches, skip, spec, 1, pend)
     # the entry's influence never died: rescan — into the buffers of the speculative scan it replaces
     # (with pipelined steps the other scanner may already hold the next step)
-    kw = {"scanner": spec.handle} if isinstance(backend, DeviceBackend) and spec.handle is not None else {}
-    full = backend.scan(backend.len, entry, fetch, **kw)
+    kw2 = dict(kw)
+    if isinstance(backend, DeviceBackend) and spec.handle is not None:
+        kw2["scanner"] = spec.handle
+    full = backend.scan(backend.len, entry, fetch, **kw2)
     return ShardResult(full.n, np.zeros((0, 2), np.int64), 0, full, 2, [("tail", i, nxt, R) for i, nxt, R in full.pending])
 
 

@@ -53,6 +53,7 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
     sp.num_tiles = num_tiles;
     sp.static_closed = (h.static_depth != 0xffffffffu && h.static_depth + 1 <= (uint32_t)ROW_BYTES) ? 1u : 0u;
     sp.sparse = h.sparse_ok && g_sparse_mode ? 1u : 0u;
+    sp.donly = h.donly;
     sp.ticket = &ticket;
     sp.out = reinterpret_cast<long long*>(out);
     sp.out_cap = cap;
@@ -89,10 +90,28 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
         bool dense = true;
         bool sp_ok[ROWS];
         uint32_t sp_hits[ROWS][4], sp_b[ROWS][NW];
-        uint16_t sp_kst[ROWS][2];
+        uint32_t sp_kst[ROWS][2];
         SparseTail tails[ROWS];
-        for (int t = 0; t < ROWS; t++) { tails[t].kq = tails[t].ks = tails[t].nacc = 0; tails[t].drained = 1; }
-        if (h.sparse_ok && g_sparse_mode) {
+        for (int t = 0; t < ROWS; t++) { tails[t].kq = tails[t].ks = tails[t].nacc = tails[t].nruns = 0; tails[t].rt = 0; tails[t].drained = 1; }
+        bool published = false;
+        if (h.donly && g_sparse_mode) {
+            // thread-owned candidate scan, as the kernel: every row, no dense fallback
+            for (int t = 0; t < ROWS; t++) {
+                ProgView pv = view(t);
+                Prog<NW, NT, NB> fw;
+                fw.init(pv);
+                phase_a_cand<NW, Prog<NW, NT, NB>, true>(sp, pv, fw, ts, t, tails[t]);
+            }
+            published = true;
+            for (int t = 0; t < ROWS; t++) {
+                ProgView pv = view(t);
+                Prog<NW, NT, NB> fw;
+                fw.init(pv);
+                if (phase_d_kind<NW>(sp, pv, fw, ts, t) != K_CLOSED) published = false;
+            }
+            dense = false;
+            g_sparse_rows += ROWS;
+        } else if (h.sparse_ok && g_sparse_mode) {
             // as the kernel: exit sets first; candidates only if every row of the tile is closed
             bool all_closed = true;
             for (int t = 0; t < ROWS; t++) {
@@ -103,15 +122,16 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
                 all_closed = all_closed && sp_ok[t];
             }
             dense = !all_closed;
+            published = all_closed;
             if (all_closed) {
                 for (int t = 0; t < ROWS; t++) {
                     ProgView pv = view(t);
                     Prog<NW, NT, NB> fw;
                     fw.init(pv);
-                    sp_ok[t] = phase_a_cand<NW>(sp, pv, fw, ts, t, tails[t]);
+                    sp_ok[t] = phase_a_cand<NW, Prog<NW, NT, NB>, false>(sp, pv, fw, ts, t, tails[t]);
                     if (!sp_ok[t]) dense = true;
                     else if (g_sparse_mode == 2) {
-                        sparse_drain<NW>(ts, t, tails[t].kq, tails[t].ks);      // materialise for the comparison
+                        sparse_drain<NW>(ts, t, tails[t]);      // materialise for the comparison
                         if (ts.sum_kind[t] != K_CLOSED) *err |= 0x80u;
                         for (int q = 0; q < 4; q++) sp_hits[t][q] = ts.hits[q * ROWS + t];
                         for (int w = 0; w < NW; w++) sp_b[t][w] = ts.sum_b[w * ROWS + t];
@@ -165,14 +185,14 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
         }
         uint32_t cnt[ROWS], off[ROWS], total_t = 0;
         // fast tail, as in the kernel: every row simple and without carried state
-        bool fast = !dense;
+        bool fast = !dense && published;
         if (!dense) {
             for (int t = 0; t < ROWS; t++) {
                 uint32_t carried = 0;
                 for (int w = 0; w < NW; w++) carried |= t == 0 ? ts.misc[TS::M_ENTRY + w] : ts.sum_b[w * ROWS + t - 1];
                 if (!tails[t].simple() || carried) fast = false;
             }
-            if (!fast) for (int t = 0; t < ROWS; t++) sparse_drain<NW>(ts, t, tails[t].kq, tails[t].ks);
+            if (!fast) for (int t = 0; t < ROWS; t++) sparse_drain<NW>(ts, t, tails[t]);
         }
         tile_base[tile] = matches_so_far;
         if (fast) {
@@ -229,21 +249,22 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
 extern "C" {
 
 // text_with_ctx points at the first byte of the left context; the shard starts left_ctx bytes in.
+// reduce: bit 0 = merge equivalent positions, bit 1 = forbid the thread-owned candidate scan (rrx_prog.h donly).
 // fast != 0: use the register-resident forward program when the automaton allows it (as the GPU does).
 // Returns 0, or <0 on a parse error.  counts[0] = matches, counts[1] = pending start scans.
 int emu_scan(const char* pattern, int reduce, int fast, const uint8_t* text_with_ctx, uint64_t left_ctx, uint64_t len,
              int64_t base, const uint32_t* entry, int64_t* out, uint64_t cap, uint64_t* counts, uint32_t* err,
-             uint32_t* shard_comp, uint32_t* info /* NW, P, n_terms, n_bicl, use_rows, static_depth */,
+             uint32_t* shard_comp, uint32_t* info /* NW, P, n_terms, n_bicl, use_rows, static_depth, sparse_ok, cand_byte, donly */,
              void* pending, uint32_t pending_cap) {
     Program prog;
     try {
         Automaton a = compile_ere(pattern);
-        prog = build_program(a, pattern, reduce != 0);
+        prog = build_program(a, pattern, (reduce & 1) != 0, (reduce & 2) == 0);
     } catch (const std::runtime_error&) {
         return -1;
     }
     const ProgHeader& h = prog.hdr();
-    if (info) { info[0] = h.NW; info[1] = h.P; info[2] = h.n_terms; info[3] = h.n_bicl; info[4] = h.use_rows; info[5] = h.static_depth; info[6] = h.sparse_ok; info[7] = h.cand_byte; }
+    if (info) { info[0] = h.NW; info[1] = h.P; info[2] = h.n_terms; info[3] = h.n_bicl; info[4] = h.use_rows; info[5] = h.static_depth; info[6] = h.sparse_ok; info[7] = h.cand_byte; info[8] = h.donly; }
     const uint8_t* text = text_with_ctx + left_ctx;
     PendingStart* pend = reinterpret_cast<PendingStart*>(pending);
 #define GO(NW_, NT_, NB_) return run<NW_, NT_, NB_>(prog, text, left_ctx, len, base, entry, out, cap, counts, err, shard_comp, pend, pending_cap)

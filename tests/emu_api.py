@@ -52,7 +52,7 @@ def sparse_stats(reset=True):
 last_fast_tiles = 0
 
 
-def scan(pattern: str, text, reduce=True, fast=True, left_ctx=0, base=0, entry=None, cap=None):
+def scan(pattern: str, text, reduce=True, fast=True, left_ctx=0, base=0, entry=None, cap=None, donly=True):
     """Returns dict(matches (M,2) int64, n, pending, err, shard_comp, info)."""
     buf = np.frombuffer(bytes(text), dtype=np.uint8) if not isinstance(text, np.ndarray) else np.ascontiguousarray(text)
     # keep 16 spare bytes around so that &buf[0] is valid for empty inputs
@@ -63,19 +63,19 @@ def scan(pattern: str, text, reduce=True, fast=True, left_ctx=0, base=0, entry=N
     counts = np.zeros(2, dtype=np.uint64)
     err = np.zeros(1, dtype=np.uint32)
     comp = np.zeros(1 + 3 * 32, dtype=np.uint32)
-    info = np.zeros(8, dtype=np.uint32)
+    info = np.zeros(12, dtype=np.uint32)
     ent = None
     if entry is not None:
         ent = np.zeros(32, dtype=np.uint32)
         ent[:len(entry)] = entry
     psz = _lib().emu_pending_size()
     pend = np.zeros(64 * psz, dtype=np.uint8)
-    rc = _lib().emu_scan(pattern.encode("latin-1"), int(reduce), int(fast), padded.ctypes.data, left_ctx, n, base,
+    rc = _lib().emu_scan(pattern.encode("latin-1"), int(bool(reduce)) | (0 if donly else 2), int(fast), padded.ctypes.data, left_ctx, n, base,
                          ent.ctypes.data if ent is not None else None, out.ctypes.data, cap, counts.ctypes.data,
                          err.ctypes.data, comp.ctypes.data, info.ctypes.data, pend.ctypes.data, 64)
     if rc:
         raise ValueError(f"emu_scan rc={rc}")
     m = int(counts[0])
-    return dict(matches=out[:min(m, cap)].copy(), n=m, pending=int(counts[1]), err=int(err[0]), shard_comp=comp,
+    return dict(matches=out[:min(m, cap)].copy(), n=m, pending=int(counts[1]), err=int(err[0]) & ~16, soft=int(err[0]) & 16, shard_comp=comp,
                 info=dict(NW=int(info[0]), P=int(info[1]), n_terms=int(info[2]), n_bicl=int(info[3]),
-                          use_rows=int(info[4]), static_depth=int(info[5]), sparse_ok=int(info[6]), cand_byte=int(info[7])), pend_raw=pend, pend_size=psz)
+                          use_rows=int(info[4]), static_depth=int(info[5]), sparse_ok=int(info[6]), cand_byte=int(info[7]), donly=int(info[8])), pend_raw=pend, pend_size=psz)

@@ -14,12 +14,12 @@ from roaringregex_b200.configs import CONFIGS
 def _check(oracle_api, pat, text, **kw):
     want = oracle_api.Oracle(pat).lazy_matches(text) if not isinstance(pat, tuple) else pat[1].lazy_matches(text)
     p = pat if not isinstance(pat, tuple) else pat[0]
-    for reduce in (True, False):
-        for fast in (True, False):
-            r = emu_api.scan(p, text, reduce=reduce, fast=fast, **kw)
-            assert r["err"] == 0
-            assert r["n"] == len(want), (p, reduce, fast, r["n"], len(want))
-            assert np.array_equal(r["matches"], want), (p, reduce, fast)
+    for reduce, fast, donly in ((True, True, True), (True, True, False), (False, False, True), (True, False, False), (False, True, False)):
+        # donly: let the compiler pick the thread-owned candidate scan where it applies / forbid it
+        r = emu_api.scan(p, text, reduce=reduce, fast=fast, donly=donly, **kw)
+        assert r["err"] == 0
+        assert r["n"] == len(want), (p, reduce, fast, donly, r["n"], len(want))
+        assert np.array_equal(r["matches"], want), (p, reduce, fast, donly)
 
 
 @pytest.mark.parametrize("cfg_id", [1, 2, 3, 4, 5])

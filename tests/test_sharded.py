@@ -18,25 +18,29 @@ from tests_support import apply_follow, decode_blob
 
 class EmuBackend:
     """TEST INFRASTRUCTURE: per-shard scans by the host-side kernel emulator."""
+    DONLY = True          # let the compiler choose the thread-owned candidate scan (the `mode` fixture flips it)
 
     def __init__(self, rrx, pattern, text, lo, hi, halo):
-        self.regex = rrx.RRegex(pattern)
+        self.regex = rrx.RRegex(pattern, 0 if self.DONLY else rrx.COMPILE_NO_DONLY)
         self.pattern, self.text = pattern, text
         self.base, self.len = lo, hi - lo
         self.halo = min(halo, lo)
         self.prog = decode_blob(self.regex.blob())
 
-    def scan(self, length, entry, fetch, prefix=False):
+    def scan(self, length, entry, fetch, prefix=False, no_donly=False):
         buf = self.text[self.base - self.halo:self.base + length]
-        r = emu_api.scan(self.pattern, buf, left_ctx=self.halo, base=self.base, entry=entry)
-        assert r["err"] == 0
+        donly = self.DONLY and not no_donly
+        r = emu_api.scan(self.pattern, buf, left_ctx=self.halo, base=self.base, entry=entry, donly=donly)
+        want_fb = donly and bool((r["err"] & 32) or (r["soft"] and self.base - self.halo > 0))
+        assert r["err"] & ~32 == 0
         W = r["info"]["NW"]
         pend = []
         for i in range(r["pending"]):
             rec = r["pend_raw"][i * r["pend_size"]:(i + 1) * r["pend_size"]]
             mi, nxt = np.frombuffer(rec[:16].tobytes(), dtype=np.int64)
             pend.append((int(mi), self.base + int(nxt), np.frombuffer(rec[16:].tobytes(), dtype=np.uint32).copy()))
-        return sharded.ShardScan(n=r["n"], matches=r["matches"], summary=r["shard_comp"][:1 + 3 * W].copy(), pending=pend)
+        return sharded.ShardScan(n=r["n"], matches=r["matches"], summary=r["shard_comp"][:1 + 3 * W].copy(), pending=pend,
+                                 want_fallback=want_fb)
 
     def head(self, scan, k):
         return scan.matches[:k]
@@ -89,6 +93,15 @@ class ThreadComm:
                 comm.bar.wait()
                 return out
         return V()
+
+
+@pytest.fixture(autouse=True, params=["thread-owned", "row-bounded"])
+def mode(request):
+    """Every test of this module runs with the compiler free to choose the thread-owned candidate scan, and with
+    it forbidden (RRX_COMPILE_NO_DONLY)."""
+    EmuBackend.DONLY = request.param == "thread-owned"
+    yield request.param
+    EmuBackend.DONLY = True
 
 
 def run_world(rrx, pattern, text, world, halo, cuts=None):

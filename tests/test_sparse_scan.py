@@ -23,22 +23,23 @@ def _both_modes(oracle_api, pat, text, o=None):
     o = o or oracle_api.Oracle(pat)
     want = o.lazy_matches(text)
     info = None
-    for mode in (2, 1):
+    # (thread-owned scan, -) / (row-bounded scan, checked row by row against the dense scan) / (row-bounded scan)
+    for donly, mode in ((True, 1), (False, 2), (False, 1)):
         emu_api.set_sparse(mode)
         for reduce in (True, False):
-            r = emu_api.scan(pat, text, reduce=reduce, fast=True)
-            assert r["err"] == 0, (pat, mode, reduce, hex(r["err"]))
-            assert r["n"] == len(want), (pat, mode, reduce, r["n"], len(want))
-            assert np.array_equal(r["matches"], want), (pat, mode, reduce)
+            r = emu_api.scan(pat, text, reduce=reduce, fast=True, donly=donly)
+            assert r["err"] == 0, (pat, mode, reduce, donly, hex(r["err"]))
+            assert r["n"] == len(want), (pat, mode, reduce, donly, r["n"], len(want))
+            assert np.array_equal(r["matches"], want), (pat, mode, reduce, donly)
             info = r["info"]
     return info
 
 
 def test_cuts_of_the_configs(rrx):
-    want = {1: "e", 2: "@", 3: "b", 4: "c"}
+    want = {1: "e", 2: "@", 3: "b", 4: "c", 5: "q"}
     for cid, byte in want.items():
         i = rrx.RRegex(CONFIGS[cid].pattern).info
-        assert i["sparse_ok"] == 1 and chr(i["cand_byte"]) == byte, (cid, i)
+        assert i["sparse_ok"] == 1 and chr(i["cand_byte"]) == byte and i["donly"] == 1, (cid, i)
     # no single byte lies on every path: dense scan only
     for pat in ("[a-z]+", "(a|b)c|d", "[ab]x"):
         i = rrx.RRegex(pat).info
@@ -56,10 +57,11 @@ def test_config_corpora_sparse_equals_dense(oracle_api, cfg_id):
     emu_api.sparse_stats()
     emu_api.scan(cfg.pattern, text)
     sparse_rows, dense_rows = emu_api.sparse_stats()
-    if cfg_id != 5:          # config 5's rows are open ('.' matches everything): always dense
+    assert dense_rows == 0, (sparse_rows, dense_rows)           # thread-owned scan: no dense fallback at all
+    emu_api.scan(cfg.pattern, text, donly=False)
+    sparse_rows, dense_rows = emu_api.sparse_stats()
+    if cfg_id != 5:          # config 5 without the thread-owned scan: walks back to the last z rarely fit the row
         assert sparse_rows > 10 * dense_rows, (sparse_rows, dense_rows)
-    else:
-        assert sparse_rows == 0
 
 
 def test_known_starts_and_ambiguous_runs(oracle_api):

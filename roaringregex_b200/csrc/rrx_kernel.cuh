@@ -369,18 +369,39 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             // fallback.  The rows' exits (dominated states only) are known once the candidates have been followed;
             // what a row does to carried states is decided by phase_d_kind.  All rows closed: the tile's aggregate
             // is the last row's exit.
-            phase_a_cand<NW, F, true>(sp, pv, fw, ts, lane, tail);
-            const uint32_t kind = phase_d_kind<NW>(sp, pv, fw, ts, lane);
+            // Usually the last row's exit is provably empty before any candidate has been followed (no candidate byte
+            // behind the point where nothing carried survives): the tile then publishes FIRST, and its successors find
+            // its aggregate ready when they look back.
+            uint32_t cm[4];
+            int qfree;
+            phase_a_mask<NW>(ts, lane, fw.sp_cand(pv), cm);
+            const uint32_t kind = phase_d_kind<NW>(sp, pv, fw, ts, lane, &qfree);
+            const uint32_t behind = qfree >= ROW_BYTES ? 0u : ((qfree >> 5) == 0 ? (cm[0] >> (qfree & 31)) | cm[1] | cm[2] | cm[3]
+                                                             : (qfree >> 5) == 1 ? (cm[1] >> (qfree & 31)) | cm[2] | cm[3]
+                                                             : (qfree >> 5) == 2 ? (cm[2] >> (qfree & 31)) | cm[3] : (cm[3] >> (qfree & 31)));
+            const bool all_closed = __all_sync(FULL, kind == K_CLOSED) != 0;
+            const bool early = all_closed && __shfl_sync(FULL, behind, TILE_ROWS - 1) == 0u;
+            uint32_t arrived = 0;
             dense = false;
+            if (early) {
+                uint32_t bl[NW];
+#pragma unroll
+                for (int w = 0; w < NW; w++) bl[w] = 0u;
+                comp_closed(agg, bl, 0);
+                arrived = lookback_publish_issue<NW>(sp, tile, agg, lane);
+                published = true;
+            }
+            phase_a_cand<NW, F, true>(sp, pv, fw, ts, lane, cm, tail);
             __syncwarp();
-            if (__all_sync(FULL, kind == K_CLOSED)) {
+            if (early) {
+                lookback_publish_fold<NW>(sp, tile, arrived, lane);       // the arrival count has long come back
+            } else if (all_closed) {
                 uint32_t bl[NW];
 #pragma unroll
                 for (int w = 0; w < NW; w++) bl[w] = ts.sum_b[w * TILE_ROWS + (TILE_ROWS - 1)];
                 comp_closed(agg, bl, 0);
-                const uint32_t arrived = lookback_publish_issue<NW>(sp, tile, agg, lane);
+                lookback_publish<NW>(sp, tile, agg, lane);
                 published = true;
-                lookback_publish_fold<NW>(sp, tile, arrived, lane);
             }
         } else if (sp.sparse) {
             if (dense_left == 0) {
@@ -397,7 +418,9 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
                         if (lane == 0) next_raw = atom_add_u32(sp.ticket, 1u);
                         have_next = true;
                     }
-                    const bool ok = phase_a_cand<NW, F, false>(sp, pv, fw, ts, lane, tail);
+                    uint32_t cm[4];
+                    phase_a_mask<NW>(ts, lane, fw.sp_cand(pv), cm);
+                    const bool ok = phase_a_cand<NW, F, false>(sp, pv, fw, ts, lane, cm, tail);
                     lookback_publish_fold<NW>(sp, tile, arrived, lane);       // the arrival count has long come back
                     dense = __any_sync(FULL, !ok) != 0;
                 }

@@ -871,31 +871,32 @@ RRX_DEV void sparse_drain(TileState<NW>& ts, int t, const SparseTail& q) {
 //   dense fallback, no bail-outs.  The row may be partial (nb < 128 valid bytes; the staged bytes behind them are
 //   >= 0x80).  sum_b[t] receives the dominated states alive after the row's last byte that stem from the row's
 //   own candidates; carried states are phase B's business as before.
+// (1) candidate mask of row t: bit p of cm[q] <=> byte 32q+p == cand
+template <int NW>
+RRX_DEV void phase_a_mask(const TileState<NW>& ts, int t, uint32_t cand, uint32_t* cm) {
+    const uint32_t C4 = cand * 0x01010101u;
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(ts.text + t * ROW_PITCH);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int j = 7; j >= 0; j--) {
+            const uint32_t x = rw[q * 8 + j] ^ C4;
+            const uint32_t y = (x | 0x80808080u) - 0x01010101u;     // no borrow between bytes
+            const uint32_t f = ~(y | x) & 0x80808080u;              // 0x80 where the byte equals cand
+            acc = fshl(f * 0x00204081u, acc, 4);                    // the 4 flags land in the top nibble
+        }
+        cm[q] = acc;
+    }
+}
+
 template <int NW, class F, bool DONLY>
-RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t, SparseTail& tail) {
+RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t, const uint32_t* cm,
+                          SparseTail& tail) {
     constexpr int ROWS = TILE_ROWS;
     const uint32_t ngr = fw.sp_ngroups(pv), cand = fw.sp_cand(pv);
     const uint8_t* rp = ts.text + t * ROW_PITCH;
     const uint32_t rowend = DONLY ? (uint32_t)row_nbytes(sp, ts.row0, t) : (uint32_t)ROW_BYTES;
-
-    // (1) candidate mask: bit p of cm[q] <=> byte 32q+p == cand
-    uint32_t cm[4];
-    {
-        const uint32_t C4 = cand * 0x01010101u;
-        const uint32_t* rw = reinterpret_cast<const uint32_t*>(rp);
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            uint32_t acc = 0;
-#pragma unroll
-            for (int j = 7; j >= 0; j--) {
-                const uint32_t x = rw[q * 8 + j] ^ C4;
-                const uint32_t y = (x | 0x80808080u) - 0x01010101u;     // no borrow between bytes
-                const uint32_t f = ~(y | x) & 0x80808080u;              // 0x80 where the byte equals cand
-                acc = fshl(f * 0x00204081u, acc, 4);                    // the 4 flags land in the top nibble
-            }
-            cm[q] = acc;
-        }
-    }
     int ncand = popc32(cm[0]) + popc32(cm[1]) + popc32(cm[2]) + popc32(cm[3]);
 
     // (2) runs of dominated states.  Two nested warp-uniform loops (every lane iterates until all
@@ -1103,10 +1104,13 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
 // walking back from the row end with the dominated positions that can still lie on a surviving path; on
 // ordinary text that set is empty after a byte or two), else the survivor analysis of phase A restricted to D:
 // K_RANK1 with sum_U / sum_P, or K_HARD.
+// *qfree: a closed row's exit (sum_b, known only after the candidates have been followed) is certainly empty if the row
+// has no candidate byte at or after this position — what lets a tile publish its aggregate before it scans.
 template <int NW, class F>
-RRX_DEV uint32_t phase_d_kind(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t) {
+RRX_DEV uint32_t phase_d_kind(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t, int* qfree) {
     constexpr int ROWS = TILE_ROWS;
     const int nb = row_nbytes(sp, ts.row0, t);
+    *qfree = 0;
     if (nb == 0) { ts.sum_kind[t] = K_IDENT; return K_IDENT; }
     const SmemBytes rb(ts.text + t * ROW_PITCH);
     uint32_t A[NW], x[NW], Bc[NW], f[NW];
@@ -1117,11 +1121,11 @@ RRX_DEV uint32_t phase_d_kind(const ScanParams& sp, const ProgView& pv, const F&
         load_B<NW>(pv, rb.at((uint32_t)q), Bc);
 #pragma unroll
         for (int w = 0; w < NW; w++) x[w] = A[w] & Bc[w];
-        if (!any_w<NW>(x)) { open = false; break; }
+        if (!any_w<NW>(x)) { open = false; *qfree = q + 1; break; }     // nothing alive after byte q survives
         fw.rfollow(pv, x, A);
 #pragma unroll
         for (int w = 0; w < NW; w++) A[w] &= fw.sp_D(pv, w);
-        if (!any_w<NW>(A)) { open = false; break; }
+        if (!any_w<NW>(A)) { open = false; *qfree = q; break; }         // only a thread injected AT byte q could
     }
     if (!open) { ts.sum_kind[t] = K_CLOSED; return K_CLOSED; }
     // open: survivors of ALL dominated states, no injection

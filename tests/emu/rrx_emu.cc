@@ -93,22 +93,26 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
         uint32_t sp_kst[ROWS][2];
         SparseTail tails[ROWS];
         for (int t = 0; t < ROWS; t++) { tails[t].kq = tails[t].ks = tails[t].nacc = tails[t].nruns = 0; tails[t].rt = 0; tails[t].drained = 1; }
-        bool published = false;
+        bool published = false, all_closed_d = true;
         if (h.donly && g_sparse_mode) {
             // thread-owned candidate scan, as the kernel: every row, no dense fallback
             for (int t = 0; t < ROWS; t++) {
                 ProgView pv = view(t);
                 Prog<NW, NT, NB> fw;
                 fw.init(pv);
-                phase_a_cand<NW, Prog<NW, NT, NB>, true>(sp, pv, fw, ts, t, tails[t]);
+                uint32_t cm[4];
+                int qfree;
+                phase_a_mask<NW>(ts, t, fw.sp_cand(pv), cm);
+                const uint32_t kind = phase_d_kind<NW>(sp, pv, fw, ts, t, &qfree);
+                phase_a_cand<NW, Prog<NW, NT, NB>, true>(sp, pv, fw, ts, t, cm, tails[t]);
+                if (kind != K_CLOSED) all_closed_d = false;
+                // the kernel's early-publish rule: no candidate at or behind qfree => the row's exit must be empty
+                bool behind = false;
+                for (int p = qfree; p < ROW_BYTES; p++) behind = behind || ((cm[p >> 5] >> (p & 31)) & 1u);
+                if (kind == K_CLOSED && !behind)
+                    for (int w = 0; w < NW; w++) if (ts.sum_b[w * ROWS + t]) *err |= 0x40u;
             }
-            published = true;
-            for (int t = 0; t < ROWS; t++) {
-                ProgView pv = view(t);
-                Prog<NW, NT, NB> fw;
-                fw.init(pv);
-                if (phase_d_kind<NW>(sp, pv, fw, ts, t) != K_CLOSED) published = false;
-            }
+            published = all_closed_d;
             dense = false;
             g_sparse_rows += ROWS;
         } else if (h.sparse_ok && g_sparse_mode) {
@@ -128,7 +132,9 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
                     ProgView pv = view(t);
                     Prog<NW, NT, NB> fw;
                     fw.init(pv);
-                    sp_ok[t] = phase_a_cand<NW, Prog<NW, NT, NB>, false>(sp, pv, fw, ts, t, tails[t]);
+                    uint32_t cm[4];
+                    phase_a_mask<NW>(ts, t, fw.sp_cand(pv), cm);
+                    sp_ok[t] = phase_a_cand<NW, Prog<NW, NT, NB>, false>(sp, pv, fw, ts, t, cm, tails[t]);
                     if (!sp_ok[t]) dense = true;
                     else if (g_sparse_mode == 2) {
                         sparse_drain<NW>(ts, t, tails[t]);      // materialise for the comparison

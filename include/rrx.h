@@ -155,7 +155,7 @@ int rrx_scanner_enable_timing(rrx_scanner* s, int on);
 int rrx_scanner_kernel_ms(rrx_scanner* s, float* ms);
 
 /* The same composite followed by the scan's counters, left in DEVICE memory (asynchronous): words32
- * [kind, b[W], U[W], P[W], ticket, error_bits, allocator lo, hi, n_pending lo, hi, n_matches lo, hi].  This is the
+ * [kind, b[W], U[W], P[W], 0, error_bits, allocator lo, hi, n_pending lo, hi, n_matches lo, hi].  This is the
  * message a rank contributes to the all-gather of a sharded scan: the collective can be enqueued on
  * the same stream right behind the scan, and ONE device-to-host copy of the gathered messages gives
  * every rank its own counters and everybody's composite (one synchronisation per step). */

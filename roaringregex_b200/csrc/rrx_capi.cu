@@ -27,11 +27,12 @@ int cuda_err(cudaError_t e, const char* what) {
 #define RRX_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_err(e_, #call); } while (0)
 
 // Control block of a scan over T tiles (B = ceil(T/32) blocks); everything in it is zeroed before
-// the scan: [ticket,err,total[2],pad | f_a0[T] f_i0[T] f_a1[B] f_i1[B] st_arrive[B]].
+// the scan: [-,err,total[2],n_matches | pad | ticket (its own 128-byte line: every tile of the grid adds to it, nothing
+// else should wait behind those atomics) | f_a0[T] f_i0[T] f_a1[B] f_i1[B] st_arrive[B]].
 // Returns the size; fills the five offsets.
 size_t ctrl_layout(size_t T, size_t* off) {
     const size_t B = (T + 31) / 32;
-    size_t o = 32, tmp[8];
+    size_t o = 256, tmp[8];
     size_t* f = off ? off : tmp;
     f[0] = o; o += 4 * T;
     f[1] = o; o += 4 * T;
@@ -406,7 +407,7 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     size_t off[10];
     const size_t used = ctrl_layout(sp.num_tiles, off);
     const size_t T = sp.num_tiles, B = (T + 31) / 32, PW = 1 + 3 * (size_t)h.NW;
-    sp.ticket = reinterpret_cast<uint32_t*>(c);
+    sp.ticket = reinterpret_cast<uint32_t*>(c + 128);
     sp.err = reinterpret_cast<uint32_t*>(c + 4);
     sp.total = reinterpret_cast<unsigned long long*>(c + 8);
     sp.f_a0 = reinterpret_cast<volatile uint32_t*>(c + off[0]);

@@ -928,10 +928,6 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
 #pragma unroll
     for (int qd = 0; qd < 4; qd++) ts.hits[qd * ROWS + t] = 0;
     ts.kst[2 * t] = ts.kst[2 * t + 1] = KST_NONE;
-    if (DONLY) {
-        // a verification walk somewhere ran out of budget: the scan is void, let the grid drain quickly
-        if (*reinterpret_cast<volatile uint32_t*>(sp.err) & ERR_VERIFY_BUDGET) work = 0u;
-    }
     while (RRX_WARP_ANY(work != 0)) {
         // ---- outer: the queue is full, or the lane is at a candidate byte (or jumps to its next one) ----
         if (work != 0 && q.nacc >= 4) {
@@ -983,8 +979,10 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
                     }
                     if (DONLY && !inj && alive) {
                         // the walk goes on before the row start: earlier rows of the tile, then global memory
+                        // (once a walk somewhere has run out of budget the scan is void: let the grid drain quickly)
                         const int64_t row_lo = ts.lo() + ((int64_t)t << ROW_SHIFT);
-                        const WalkResult wr = back_walk<NW>(sp, pv, fw, ts, R, row_lo + qb, VERIFY_BUDGET);
+                        const bool over = (*reinterpret_cast<volatile uint32_t*>(sp.err) & ERR_VERIFY_BUDGET) != 0u;
+                        const WalkResult wr = back_walk<NW>(sp, pv, fw, ts, R, row_lo + qb, over ? 1 : VERIFY_BUDGET);
                         if (wr.found) {
                             inj = true;
                             const int64_t d = wr.j - row_lo;

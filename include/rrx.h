@@ -50,6 +50,7 @@ typedef struct rrx_info {
     uint32_t cand_byte;      /* that byte */
     uint32_t donly;          /* thread-owned candidate scan: only the states dominated by the cut are carried between rows,
                               * tiles and shards; candidates are verified by backward walks (DESIGN.md "Thread-owned scan") */
+    uint32_t carried_words;  /* 32-bit words that hold every carried set (dominated positions are numbered first) */
 } rrx_info;
 
 /* ---- compile: replaces RRegex::RRegex(const char*) (regex.h:224, Parser.cpp:161-170) ---------- */

@@ -45,7 +45,7 @@ class InvalidExpression(RrxError):
 
 class _Info(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("n_raw", "ref_width_class", "n_flat", "n_device", "words", "nullable",
-                                          "n_terms", "n_bicliques", "uses_rows", "static_closed", "sparse_ok", "cand_byte", "donly")]
+                                          "n_terms", "n_bicliques", "uses_rows", "static_closed", "sparse_ok", "cand_byte", "donly", "carried_words")]
 
 
 class _Opts(C.Structure):

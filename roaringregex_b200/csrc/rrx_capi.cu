@@ -187,6 +187,7 @@ void rrx_program_info(const rrx_program* p, rrx_info* o) {
     o->sparse_ok = h.sparse_ok;
     o->cand_byte = h.cand_byte;
     o->donly = h.donly;
+    o->carried_words = h.donly ? h.CW : h.NW;
 }
 
 int64_t rrx_program_flat_table(const rrx_program* p, int which, uint32_t* out, uint64_t cap) {
@@ -406,7 +407,10 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     uint8_t* c = s->d_ctrl;
     size_t off[10];
     const size_t used = ctrl_layout(sp.num_tiles, off);
-    const size_t T = sp.num_tiles, B = (T + 31) / 32, PW = 1 + 3 * (size_t)h.NW;
+    // look-back payload entries: 1+3*CW words, CW = the kernel's carried width (rrx_prog.h; the pre-compiled
+    // kernels carry NW words); CW == 1: one 16-byte word per entry with the ready bit inside
+    const size_t cw = (s->jit && h.donly) ? h.CW : h.NW;
+    const size_t T = sp.num_tiles, B = (T + 31) / 32, PW = cw == 1 ? 4 : 1 + 3 * cw;
     sp.ticket = reinterpret_cast<uint32_t*>(c + 128);
     sp.err = reinterpret_cast<uint32_t*>(c + 4);
     sp.total = reinterpret_cast<unsigned long long*>(c + 8);
@@ -440,7 +444,7 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     s->last_base = (int64_t)base_offset;
     s->h_shard_valid = false;
     RRX_CUDA(cudaMemsetAsync(s->d_ctrl, 0, used, st));
-    if (h.NW == 1)      // one-word automata keep the ready bit inside the 16-byte composite words
+    if (cw == 1)        // one-word composites keep the ready bit inside their 16-byte words
         RRX_CUDA(cudaMemsetAsync(s->d_tpay, 0, (2 * T + 2 * B) * PW * 4, st));
     if (sp.num_tiles == 0) {
         // empty text: identity transfer function, no matches

@@ -801,6 +801,31 @@ Program build_program(const Automaton& a, const std::string& pattern, bool reduc
     // supported state-set widths: 1,2,4,8,16,32 words of 32 bits
     uint32_t NW = 1;
     while (NW * 32 < P) NW *= 2;
+    if (allow_donly && NW > 1) {
+        // Multi-word automaton: number the positions a cut dominates FIRST (stable otherwise), so that everything
+        // the thread-owned scan carries fits the first CW words (rrx_prog.h).  Renumbering changes no language.
+        Bits first0(P), accept0(P);
+        std::vector<Bits> fol0(P, Bits(P)), rfol0(P, Bits(P));
+        for (uint32_t k = 0; k < P; k++) { if (pos[k].first) first0.add(k); if (pos[k].accept) accept0.add(k); }
+        for (uint32_t k = 0; k < P; k++)
+            for (uint32_t t : pos[k].follow.list())
+                if (!first0.has(t)) { fol0[k].add(t); rfol0[t].add(k); }
+        const Cut c0 = find_cut(pos, fol0, rfol0, first0, accept0);
+        if (c0.ok && !c0.run_broad && c0.D.count() < P) {
+            std::vector<uint32_t> order, newid(P);
+            for (uint32_t k = 0; k < P; k++) if (c0.D.has(k)) order.push_back(k);
+            for (uint32_t k = 0; k < P; k++) if (!c0.D.has(k)) order.push_back(k);
+            for (uint32_t i = 0; i < P; i++) newid[order[i]] = i;
+            std::vector<Pos> np(P);
+            for (uint32_t i = 0; i < P; i++) {
+                np[i] = pos[order[i]];
+                Bits nf(P);
+                for (uint32_t t : pos[order[i]].follow.list()) nf.add(newid[t]);
+                np[i].follow = nf;
+            }
+            pos.swap(np);
+        }
+    }
 
     Bits first(P), accept(P), all(P);
     for (uint32_t k = 0; k < P; k++) {
@@ -867,6 +892,14 @@ Program build_program(const Automaton& a, const std::string& pattern, bool reduc
     // thread-owned candidate scan (rrx_prog.h `donly`): runs of dominated states must die by themselves, and the
     // verification walk must be short or have a skip state to run on
     h.donly = (allow_donly && cut.ok && !cut.run_broad && (!cut.ver_broad || rskip.n >= 1)) ? 1u : 0u;
+    h.CW = NW;
+    if (h.donly) {
+        uint32_t top = 0;
+        for (uint32_t k : cut.D.list()) top = k;
+        uint32_t cw = 1;
+        while (cw * 32 <= top) cw *= 2;
+        h.CW = cw < NW ? cw : NW;
+    }
     const FSkip fskip = find_forward_skip(pos, fol, cut, accept);
     h.off_fskip = take(NW);
     h.fskip_n = fskip.n; h.fskip_lo = fskip.lo; h.fskip_hi = fskip.hi;

@@ -22,11 +22,11 @@
 namespace rrx {
 
 // shared-memory geometry of a CTA of WARPS warps
-template <int NW, int WARPS_> struct KCfg {
+template <int NW, int CW, int WARPS_> struct KCfg {
     static constexpr int WARPS = WARPS_;
     static constexpr int THREADS = WARPS * 32;
     static constexpr uint32_t BT_BYTES = (NW == 1 ? 256u * 128u : 256u * (uint32_t)NW * 4u);
-    static constexpr size_t REGION = (TileState<NW>::bytes() + 15) & ~(size_t)15;
+    static constexpr size_t REGION = (TileState<NW, CW>::bytes() + 15) & ~(size_t)15;
     // small program part: header + 3 sets + 2 decompositions
     static constexpr size_t SMALL = sizeof(ProgHeader) + 4u * (3 * NW + 2 * (RRX_MAX_TERMS * (1 + NW) + RRX_MAX_BICL * 2 * NW + NW) + NW + RRX_MAX_GROUPS * (2 * NW + 1) + 2 * NW);
     static constexpr size_t SMEM = BT_BYTES + (size_t)WARPS * REGION + SMALL + 64;
@@ -227,10 +227,12 @@ __device__ __forceinline__ unsigned long long reserve_segment(const ScanParams& 
 #define RRX_T(i)
 #endif
 
-template <int NW, class F, int WARPS>
+// NW: words of a state set.  CW: words of a carried set (composites, row exits, look-back payloads); NW unless the
+// kernel is specialised for a thread-owned program with fewer dominated words (rrx_prog.h CW).
+template <int NW, int CW, class F, int WARPS>
 __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
-    using K = KCfg<NW, WARPS>;
-    using TS = TileState<NW>;
+    using K = KCfg<NW, CW, WARPS>;
+    using TS = TileState<NW, CW>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -359,7 +361,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         // tile needs the dense scan the whole tile takes it (the lanes run in lock-step anyway), and
         // the next few tiles of this warp do not try again.
         bool dense = true, published = false;
-        Comp<NW> agg, acc, inc;
+        Comp<CW> agg, acc, inc;
         SparseTail tail;
         tail.kq = tail.ks = tail.nacc = tail.nruns = 0;
         tail.rt = 0ull;
@@ -384,23 +386,23 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             uint32_t arrived = 0;
             dense = false;
             if (early) {
-                uint32_t bl[NW];
+                uint32_t bl[CW];
 #pragma unroll
-                for (int w = 0; w < NW; w++) bl[w] = 0u;
+                for (int w = 0; w < CW; w++) bl[w] = 0u;
                 comp_closed(agg, bl, 0);
-                arrived = lookback_publish_issue<NW>(sp, tile, agg, lane);
+                arrived = lookback_publish_issue<CW>(sp, tile, agg, lane);
                 published = true;
             }
             phase_a_cand<NW, F, true>(sp, pv, fw, ts, lane, cm, tail);
             __syncwarp();
             if (early) {
-                lookback_publish_fold<NW>(sp, tile, arrived, lane);       // the arrival count has long come back
+                lookback_publish_fold<CW>(sp, tile, arrived, lane);       // the arrival count has long come back
             } else if (all_closed) {
-                uint32_t bl[NW];
+                uint32_t bl[CW];
 #pragma unroll
-                for (int w = 0; w < NW; w++) bl[w] = ts.sum_b[w * TILE_ROWS + (TILE_ROWS - 1)];
+                for (int w = 0; w < CW; w++) bl[w] = ts.sum_b[w * TILE_ROWS + (TILE_ROWS - 1)];
                 comp_closed(agg, bl, 0);
-                lookback_publish<NW>(sp, tile, agg, lane);
+                lookback_publish<CW>(sp, tile, agg, lane);
                 published = true;
             }
         } else if (sp.sparse) {
@@ -408,11 +410,11 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
                 const bool closed = phase_a_exit<NW>(sp, pv, fw, ts, lane);
                 if (__all_sync(FULL, closed)) {
                     __syncwarp();
-                    uint32_t bl[NW];
+                    uint32_t bl[CW];
 #pragma unroll
-                    for (int w = 0; w < NW; w++) bl[w] = ts.sum_b[w * TILE_ROWS + (TILE_ROWS - 1)];
+                    for (int w = 0; w < CW; w++) bl[w] = ts.sum_b[w * TILE_ROWS + (TILE_ROWS - 1)];
                     comp_closed(agg, bl, 0);
-                    const uint32_t arrived = lookback_publish_issue<NW>(sp, tile, agg, lane);
+                    const uint32_t arrived = lookback_publish_issue<CW>(sp, tile, agg, lane);
                     published = true;
                     if (sp.ticket_ahead == 1) {
                         if (lane == 0) next_raw = atom_add_u32(sp.ticket, 1u);
@@ -421,7 +423,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
                     uint32_t cm[4];
                     phase_a_mask<NW>(ts, lane, fw.sp_cand(pv), cm);
                     const bool ok = phase_a_cand<NW, F, false>(sp, pv, fw, ts, lane, cm, tail);
-                    lookback_publish_fold<NW>(sp, tile, arrived, lane);       // the arrival count has long come back
+                    lookback_publish_fold<CW>(sp, tile, arrived, lane);       // the arrival count has long come back
                     dense = __any_sync(FULL, !ok) != 0;
                 }
                 if (dense) dense_left = 4;
@@ -447,17 +449,17 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         // closed map absorbs whatever precedes it) is the last row's exit, and row t's entry is row
         // t-1's exit — phases S1/S2 have nothing to compute beyond the tile's entry set.
         bool any_open = false;
-        SLocal<NW> L;
+        SLocal<CW> L;
         if (!published) {
             const uint32_t my_kind = ts.sum_kind[lane];
             any_open = __any_sync(FULL, my_kind == K_RANK1 || my_kind == K_HARD) != 0;
             __syncwarp();
             if (lane == 0) { phase_s1<NW>(sp, pv, fw, ts, any_open, L); agg = L.run; } else { comp_ident(agg); }
             bcast_comp(agg, 0);
-            lookback_publish<NW>(sp, tile, agg, lane);
+            lookback_publish<CW>(sp, tile, agg, lane);
         }
         RRX_T(2)
-        lookback_wait<NW>(sp, tile, lane, acc);
+        lookback_wait<CW>(sp, tile, lane, acc);
         if (((sp.ticket_ahead == 4) || (sp.ticket_ahead == 5 && published && !dense)) && !have_next) {       // the tile's tail is short: take the next ticket now
             if (lane == 0) next_raw = atom_add_u32(sp.ticket, 1u);
             have_next = true;
@@ -466,18 +468,18 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         RRX_T(3)
         if (lane == 0) {
             if (published) {
-                uint32_t E[NW];
-                comp_apply<NW>(acc, sp.entry, E);
+                uint32_t E[CW];
+                comp_apply<CW>(acc, sp.entry, E);
 #pragma unroll
-                for (int w = 0; w < NW; w++) ts.misc[TS::M_ENTRY + w] = E[w];
+                for (int w = 0; w < CW; w++) ts.misc[TS::M_ENTRY + w] = E[w];
                 inc = agg;
             } else {
                 phase_s2<NW>(sp, pv, fw, ts, L, acc, inc);
             }
-            publish_comp<NW>(sp.st_i0, sp.f_i0, tile, inc);
+            publish_comp<CW>(sp.st_i0, sp.f_i0, tile, inc);
             const uint32_t rest = sp.num_tiles - (tile & ~31u);
-            if ((tile & 31u) == (rest < 32u ? rest : 32u) - 1u) publish_comp<NW>(sp.st_i1, sp.f_i1, tile >> 5, inc);
-            if (tile + 1 == sp.num_tiles) store_comp_global<NW>(sp.shard_comp, inc);
+            if ((tile & 31u) == (rest < 32u ? rest : 32u) - 1u) publish_comp<CW>(sp.st_i1, sp.f_i1, tile >> 5, inc);
+            if (tile + 1 == sp.num_tiles) store_comp_external<NW, CW>(sp.shard_comp, inc);
         }
         __syncwarp();
         RRX_T(4)
@@ -488,7 +490,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         if (!dense) {
             uint32_t carried = 0;
 #pragma unroll
-            for (int w = 0; w < NW; w++) carried |= lane == 0 ? ts.misc[TS::M_ENTRY + w] : ts.sum_b[w * TILE_ROWS + lane - 1];
+            for (int w = 0; w < CW; w++) carried |= lane == 0 ? ts.misc[TS::M_ENTRY + w] : ts.sum_b[w * TILE_ROWS + lane - 1];
             // (only tiles that published early still have the rows' exits in sum_b: phase S1 rewrites them otherwise)
             fast = published && __all_sync(FULL, tail.simple() && carried == 0) != 0;
             if (!fast) sparse_drain<NW>(ts, lane, tail);

@@ -59,7 +59,12 @@ struct ProgHeader {
     // fallback.  Chosen by the compiler when runs of dominated states die by themselves (no broad-class
     // loop inside D) and the verification walk is short or has a skip state; RRX_COMPILE_NO_DONLY forbids it.
     uint32_t donly;
-    uint32_t pad2[3];
+    // Carried width: with `donly` only subsets of D travel between rows, tiles and shards.  The compiler numbers the
+    // dominated positions first, so those sets fit the first CW words (CW a power of two <= NW); a kernel specialised
+    // for the program keeps its composites, row summaries and look-back payloads CW words wide.  Generic kernels
+    // use NW.  (Everything that leaves the scanner — shard summaries, entry sets — stays NW words wide.)
+    uint32_t CW;
+    uint32_t pad2[2];
 };
 constexpr uint32_t RRX_MAX_GROUPS = 4;
 

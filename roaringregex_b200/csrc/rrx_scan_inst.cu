@@ -17,12 +17,12 @@ template <int NW, int NT> struct Warps { static constexpr int N = (NW == 1 && NT
 
 template <int NW, int NT, int NB>
 __global__ void __launch_bounds__(Warps<NW, NT>::N * 32, 1) rrx_scan_kernel(const __grid_constant__ ScanParams sp) {
-    rrx_scan_body<NW, Prog<NW, NT, NB>, Warps<NW, NT>::N>(sp);
+    rrx_scan_body<NW, NW, Prog<NW, NT, NB>, Warps<NW, NT>::N>(sp);
 }
 
 template <int NW, int NT, int NB>
 cudaError_t launch_one(const ScanParams& sp, int sm_count, cudaStream_t st, int* grid_out) {
-    using K = KCfg<NW, Warps<NW, NT>::N>;
+    using K = KCfg<NW, NW, Warps<NW, NT>::N>;
     auto kern = rrx_scan_kernel<NW, NT, NB>;
     const size_t smem = K::SMEM;
     // per instantiation AND per device: the shared-memory opt-in and the occupancy belong to the device

@@ -423,12 +423,19 @@ struct ScanParams {
 };
 
 // ---- shared-memory state of one tile (= one warp) ----------------------------------------------------
-template <int NW> struct TileState {
+// size of TileState<NW, CW> (also evaluated on the host for run-time compiled kernels)
+RRX_HD constexpr size_t tile_state_bytes(int NW, int CW) {
+    return (size_t)TILE_ROWS * ROW_PITCH +
+           sizeof(uint32_t) * ((size_t)3 * CW * TILE_ROWS + 8 * TILE_ROWS + (8 + CW) + (NW <= 2 ? 64 : NW <= 4 ? 32 : 16) * (1 + NW));
+}
+// NW: words of a state set; CW: words of a CARRIED set (row exits, composites, entry) — CW == NW unless the kernel is
+// specialised for a thread-owned program whose dominated positions fit fewer words (rrx_prog.h CW).
+template <int NW, int CW = NW> struct TileState {
     static constexpr int ROWS = TILE_ROWS;
     uint8_t* text;        // 32 rows of 128 B, ROW_PITCH bytes apart
-    uint32_t* sum_b;      // [NW][32]   exit of the row scanned from the empty set
-    uint32_t* sum_U;      // [NW][32]   (open rows) survivors at the row end / prefix composite U
-    uint32_t* sum_P;      // [NW][32]   (open rows) entry states that feed the survivor
+    uint32_t* sum_b;      // [CW][32]   exit of the row scanned from the empty set
+    uint32_t* sum_U;      // [CW][32]   (open rows) survivors at the row end / prefix composite U
+    uint32_t* sum_P;      // [CW][32]   (open rows) entry states that feed the survivor
     uint32_t* sum_kind;   // [32]
     uint32_t* hits;       // [4][32]    one bit per byte of the row: a match ends after that byte
     uint32_t* cnt;        // [32]       matches per row -> exclusive offsets
@@ -438,18 +445,16 @@ template <int NW> struct TileState {
     uint32_t* kst;        // [2][32]    known lazy starts of up to two matches per row: (end-1)<<16 | (start - row start + KS_BIAS)
     uint64_t row0;        // first row of the tile
     static constexpr int M_RQCNT = 0, M_ENTRY = 8;
-    static constexpr int MISC_WORDS = 8 + NW;
-    static constexpr int RQ_CAP = NW <= 2 ? 64 : 16;
-    static constexpr int LIST_CAP = 3 * NW * ROWS * 2;
-    static constexpr size_t bytes() {
-        return (size_t)ROWS * ROW_PITCH + sizeof(uint32_t) * ((size_t)3 * NW * ROWS + 8 * ROWS + MISC_WORDS + RQ_CAP * (1 + NW));
-    }
+    static constexpr int MISC_WORDS = 8 + CW;
+    static constexpr int RQ_CAP = NW <= 2 ? 64 : NW <= 4 ? 32 : 16;         // (>= 512 bytes: the stop-byte masks alias it)
+    static constexpr int LIST_CAP = 3 * CW * ROWS * 2;
+    static constexpr size_t bytes() { return tile_state_bytes(NW, CW); }
     RRX_DEV void carve(uint8_t* base) {
         text = base;
         uint32_t* p = reinterpret_cast<uint32_t*>(base + (size_t)ROWS * ROW_PITCH);
-        sum_b = p; p += NW * ROWS;
-        sum_U = p; p += NW * ROWS;
-        sum_P = p; p += NW * ROWS;
+        sum_b = p; p += CW * ROWS;
+        sum_U = p; p += CW * ROWS;
+        sum_P = p; p += CW * ROWS;
         sum_kind = p; p += ROWS;
         hits = p; p += 4 * ROWS;
         cnt = p; p += ROWS;
@@ -483,10 +488,10 @@ constexpr int KS_BIAS = 32768;
 constexpr int VERIFY_BUDGET = 1 << 16;      // steps one verification walk may take outside its row
 
 // ===== phase A: per-row scan from the empty set (+ openness analysis) ===============================
-template <int NW, class F>
-RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t) {
+template <int NW, class F, int CW>
+RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, CW>& ts, int t) {
     constexpr int ROWS = TILE_ROWS;
-    using TS = TileState<NW>;
+    using TS = TileState<NW, CW>;
     const int nb = row_nbytes(sp, ts.row0, t);
     uint32_t kind = nb ? K_CLOSED : K_IDENT;
     uint32_t Bc[NW], f[NW];
@@ -534,8 +539,10 @@ RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
             }
 #pragma unroll
             for (int w = 0; w < NW; w++) {
-                ts.sum_U[w * ROWS + t] = U[w];
-                ts.sum_P[w * ROWS + t] = R[w];
+                if (w < CW) {
+                    ts.sum_U[w * ROWS + t] = U[w];
+                    ts.sum_P[w * ROWS + t] = R[w];
+                }
             }
         }
     }
@@ -624,7 +631,7 @@ RRX_DEV void phase_a(const ScanParams& sp, const ProgView& pv, const F& fw, Tile
         }
     }
 #pragma unroll
-    for (int w = 0; w < NW; w++) ts.sum_b[w * ROWS + t] = S[w];
+    for (int w = 0; w < NW; w++) if (w < CW) ts.sum_b[w * ROWS + t] = S[w];
     ts.sum_kind[t] = kind;
 #pragma unroll
     for (int q = 0; q < 4; q++) ts.hits[q * ROWS + t] = hit[q];
@@ -644,8 +651,8 @@ struct WalkResult {
     bool found, pend;   // neither: the walk died — no start exists
     bool over;          // the step budget ran out (verification walks only)
 };
-template <int NW, class F>
-RRX_DEV WalkResult back_walk(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW>& ts, uint32_t* R,
+template <int NW, class F, int CW>
+RRX_DEV WalkResult back_walk(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW, CW>& ts, uint32_t* R,
                              int64_t e1, int budget) {
     uint32_t Bc[NW], x[NW];
     const int64_t tile_lo = ts.lo(), left_edge = -(int64_t)sp.left_ctx;
@@ -775,8 +782,8 @@ RRX_DEV WalkResult back_walk(const ScanParams& sp, const ProgView& pv, const F& 
 constexpr int SPARSE_MAX_CAND = 16;
 constexpr int SPARSE_BUDGET = 96;
 
-template <int NW, class F>
-RRX_DEV bool phase_a_exit(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t) {
+template <int NW, class F, int CW>
+RRX_DEV bool phase_a_exit(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, CW>& ts, int t) {
     constexpr int ROWS = TILE_ROWS;
     if (row_nbytes(sp, ts.row0, t) != ROW_BYTES) return false;
     const uint8_t* rp = ts.text + t * ROW_PITCH;
@@ -802,7 +809,7 @@ RRX_DEV bool phase_a_exit(const ScanParams& sp, const ProgView& pv, const F& fw,
         for (int w = 0; w < NW; w++) S[w] = (f[w] | fw.first(pv, w)) & Bc[w];
     }
 #pragma unroll
-    for (int w = 0; w < NW; w++) ts.sum_b[w * ROWS + t] = S[w];
+    for (int w = 0; w < NW; w++) if (w < CW) ts.sum_b[w * ROWS + t] = S[w];
     ts.sum_kind[t] = K_CLOSED;
     return true;
 }
@@ -829,8 +836,8 @@ struct SparseTail {
 
 // Fast tail of a tile: the row's matches go from the queue straight to the output list, in text order
 // (oldest queue entry first), at slots slot0, slot0+1, ...
-template <int NW>
-RRX_DEV void phase_tail_fast(const ScanParams& sp, const TileState<NW>& ts, int t, const SparseTail& tail, unsigned long long slot0) {
+template <int NW, int CW>
+RRX_DEV void phase_tail_fast(const ScanParams& sp, const TileState<NW, CW>& ts, int t, const SparseTail& tail, unsigned long long slot0) {
     const long long row_lo = sp.base + ts.lo() + ((long long)t << ROW_SHIFT);
     for (uint32_t i = 0; i < tail.nacc; i++) {
         const uint32_t sh = 8u * (tail.nacc - 1u - i);
@@ -845,8 +852,8 @@ RRX_DEV void phase_tail_fast(const ScanParams& sp, const TileState<NW>& ts, int 
 }
 
 // Unpack the match-end queue of phase_a_cand into the row's hit mask (and its first two known starts).
-template <int NW>
-RRX_DEV void sparse_drain(TileState<NW>& ts, int t, const SparseTail& q) {
+template <int NW, int CW>
+RRX_DEV void sparse_drain(TileState<NW, CW>& ts, int t, const SparseTail& q) {
     constexpr int ROWS = TILE_ROWS;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -872,8 +879,8 @@ RRX_DEV void sparse_drain(TileState<NW>& ts, int t, const SparseTail& q) {
 //   >= 0x80).  sum_b[t] receives the dominated states alive after the row's last byte that stem from the row's
 //   own candidates; carried states are phase B's business as before.
 // (1) candidate mask of row t: bit p of cm[q] <=> byte 32q+p == cand
-template <int NW>
-RRX_DEV void phase_a_mask(const TileState<NW>& ts, int t, uint32_t cand, uint32_t* cm) {
+template <int NW, int CW>
+RRX_DEV void phase_a_mask(const TileState<NW, CW>& ts, int t, uint32_t cand, uint32_t* cm) {
     const uint32_t C4 = cand * 0x01010101u;
     const uint32_t* rw = reinterpret_cast<const uint32_t*>(ts.text + t * ROW_PITCH);
 #pragma unroll
@@ -890,8 +897,8 @@ RRX_DEV void phase_a_mask(const TileState<NW>& ts, int t, uint32_t cand, uint32_
     }
 }
 
-template <int NW, class F, bool DONLY>
-RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t, const uint32_t* cm,
+template <int NW, class F, bool DONLY, int CW>
+RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, CW>& ts, int t, const uint32_t* cm,
                           SparseTail& tail) {
     constexpr int ROWS = TILE_ROWS;
     const uint32_t ngr = fw.sp_ngroups(pv), cand = fw.sp_cand(pv);
@@ -1088,7 +1095,7 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
     if (DONLY) {
         // exit of the row: the run alive after the last byte (a run that ended earlier left H empty)
 #pragma unroll
-        for (int w = 0; w < NW; w++) ts.sum_b[w * ROWS + t] = (p >= rowend && rowend != 0u) ? H[w] : 0u;
+        for (int w = 0; w < NW; w++) if (w < CW) ts.sum_b[w * ROWS + t] = (p >= rowend && rowend != 0u) ? H[w] : 0u;
     }
     // The queue is handed to the caller: a tile whose rows all kept their matches in the queue, with
     // known starts, and whose rows receive no carried state writes them straight from registers
@@ -1104,8 +1111,8 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
 // K_RANK1 with sum_U / sum_P, or K_HARD.
 // *qfree: a closed row's exit (sum_b, known only after the candidates have been followed) is certainly empty if the row
 // has no candidate byte at or after this position — what lets a tile publish its aggregate before it scans.
-template <int NW, class F>
-RRX_DEV uint32_t phase_d_kind(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t, int* qfree) {
+template <int NW, class F, int CW>
+RRX_DEV uint32_t phase_d_kind(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, CW>& ts, int t, int* qfree) {
     constexpr int ROWS = TILE_ROWS;
     const int nb = row_nbytes(sp, ts.row0, t);
     *qfree = 0;
@@ -1159,8 +1166,10 @@ RRX_DEV uint32_t phase_d_kind(const ScanParams& sp, const ProgView& pv, const F&
     }
 #pragma unroll
     for (int w = 0; w < NW; w++) {
-        ts.sum_U[w * ROWS + t] = U[w];
-        ts.sum_P[w * ROWS + t] = R[w];
+        if (w < CW) {
+            ts.sum_U[w * ROWS + t] = U[w];
+            ts.sum_P[w * ROWS + t] = R[w];
+        }
     }
     ts.sum_kind[t] = kind;
     return kind;
@@ -1168,10 +1177,10 @@ RRX_DEV uint32_t phase_d_kind(const ScanParams& sp, const ProgView& pv, const F&
 
 // ===== phase A2: the warp replays the queued 4-byte words, one per lane ==============================
 // (after all lanes have finished phase A and stored their hit words)
-template <int NW, class F>
-RRX_DEV void phase_a2(const ProgView& pv, const F& fw, TileState<NW>& ts, int lane) {
+template <int NW, class F, int CW>
+RRX_DEV void phase_a2(const ProgView& pv, const F& fw, TileState<NW, CW>& ts, int lane) {
     constexpr int ROWS = TILE_ROWS;
-    using TS = TileState<NW>;
+    using TS = TileState<NW, CW>;
     uint32_t n = ts.misc[TS::M_RQCNT];
     if (n > (uint32_t)TS::RQ_CAP) n = TS::RQ_CAP;
     for (uint32_t i = (uint32_t)lane; i < n; i += ROWS) {
@@ -1197,21 +1206,21 @@ RRX_DEV void phase_a2(const ProgView& pv, const F& fw, TileState<NW>& ts, int la
     }
 }
 
-template <int NW> RRX_DEV void load_row_comp(const TileState<NW>& ts, int t, Comp<NW>& c) {
+template <int NW, int CW> RRX_DEV void load_row_comp(const TileState<NW, CW>& ts, int t, Comp<CW>& c) {
     constexpr int ROWS = TILE_ROWS;
     c.kind = ts.sum_kind[t];
 #pragma unroll
-    for (int w = 0; w < NW; w++) {
+    for (int w = 0; w < CW; w++) {
         c.b[w] = ts.sum_b[w * ROWS + t];
         c.U[w] = (c.kind & K_TYPE) == K_RANK1 ? ts.sum_U[w * ROWS + t] : 0u;
         c.P[w] = (c.kind & K_TYPE) == K_RANK1 ? ts.sum_P[w * ROWS + t] : 0u;
     }
 }
-template <int NW> RRX_DEV void store_row_comp(TileState<NW>& ts, int t, const Comp<NW>& c) {
+template <int NW, int CW> RRX_DEV void store_row_comp(TileState<NW, CW>& ts, int t, const Comp<CW>& c) {
     constexpr int ROWS = TILE_ROWS;
     ts.sum_kind[t] = c.kind;
 #pragma unroll
-    for (int w = 0; w < NW; w++) {
+    for (int w = 0; w < CW; w++) {
         ts.sum_b[w * ROWS + t] = c.b[w];
         ts.sum_U[w * ROWS + t] = c.U[w];
         ts.sum_P[w * ROWS + t] = c.P[w];
@@ -1228,6 +1237,16 @@ template <int NW> RRX_DEV void load_comp_global(const uint32_t* src, Comp<NW>& c
 #pragma unroll
     for (int w = 0; w < NW; w++) { c.b[w] = v[1 + w]; c.U[w] = v[1 + NW + w]; c.P[w] = v[1 + 2 * NW + w]; }
 }
+// The shard composite as it leaves the scanner: always NW words per set (rrx.h), whatever the kernel's carried width.
+template <int NW, int CW> RRX_DEV void store_comp_external(uint32_t* dst, const Comp<CW>& c) {
+    dst[0] = c.kind;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        dst[1 + w] = w < CW ? c.b[w < CW ? w : 0] : 0u;
+        dst[1 + NW + w] = w < CW ? c.U[w < CW ? w : 0] : 0u;
+        dst[1 + 2 * NW + w] = w < CW ? c.P[w < CW ? w : 0] : 0u;
+    }
+}
 
 RRX_DEV void rrx_fence() {
 #if defined(__CUDA_ARCH__) && !defined(RRX_HOST_EMU)
@@ -1241,8 +1260,8 @@ RRX_DEV void rrx_backoff() {
 }
 
 // Exit of the no-injection replay of row t from the exact entry set X (in place).
-template <int NW, class F>
-RRX_DEV void row_replay_exit(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW>& ts, int t,
+template <int NW, class F, int CW>
+RRX_DEV void row_replay_exit(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW, CW>& ts, int t,
                              uint32_t* X) {
     const int nb = row_nbytes(sp, ts.row0, t);
     const bool dn = fw.donly(pv);          // thread-owned scan: only dominated states are carried
@@ -1261,18 +1280,24 @@ RRX_DEV void row_replay_exit(const ScanParams& sp, const ProgView& pv, const F& 
 // S2: tile entry, blocked segment, inclusive composite.
 // After S2 sum_* of row t hold the composite of rows [0,t) of the tile (what turns the tile entry
 // into row t's entry) and misc[M_ENTRY..] holds the tile's exact entry set.
-template <int NW> struct SLocal {
-    Comp<NW> run;          // tile aggregate (kind K_WAIT if it cannot be summarised)
-    Comp<NW> pre_block;    // composite of the rows before the blocked segment
+template <int CW> struct SLocal {
+    Comp<CW> run;          // tile aggregate (kind K_WAIT if it cannot be summarised)
+    Comp<CW> pre_block;    // composite of the rows before the blocked segment
     int blocked_from, resume_at;
     bool wait_agg;
 };
 
-template <int NW, class F>
-RRX_DEV void phase_s1(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, bool any_open,
-                      SLocal<NW>& L) {
+// widen a carried set (CW words) to a full state set (NW words) and back
+template <int NW, int CW> RRX_DEV void widen(const uint32_t* c, uint32_t* full) {
+#pragma unroll
+    for (int w = 0; w < NW; w++) full[w] = w < CW ? c[w < CW ? w : 0] : 0u;
+}
+
+template <int NW, class F, int CW>
+RRX_DEV void phase_s1(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, CW>& ts, bool any_open,
+                      SLocal<CW>& L) {
     constexpr int ROWS = TILE_ROWS;
-    Comp<NW> rowc, nxt;
+    Comp<CW> rowc, nxt;
     comp_ident(L.run);
     comp_ident(L.pre_block);
     comp_ident(nxt);
@@ -1292,20 +1317,19 @@ RRX_DEV void phase_s1(const ScanParams& sp, const ProgView& pv, const F& fw, Til
                 for (int u = t + 1; u < ROWS; u++) if ((ts.sum_kind[u] & K_TYPE) == K_CLOSED) { c = u; break; }
                 if (c < 0) { L.wait_agg = true; L.resume_at = ROWS; break; }
                 L.resume_at = c + 1;
-                uint32_t bc[NW];
+                uint32_t bc[CW];
 #pragma unroll
-                for (int w = 0; w < NW; w++) bc[w] = ts.sum_b[w * ROWS + c];
+                for (int w = 0; w < CW; w++) bc[w] = ts.sum_b[w * ROWS + c];
                 comp_closed(L.run, bc, 0);
                 continue;
             }
             store_row_comp(ts, t, L.run);
             if ((rowc.kind & K_TYPE) == K_HARD) {                  // exact state: replay the row
                 uint32_t X[NW];
-#pragma unroll
-                for (int w = 0; w < NW; w++) X[w] = L.run.b[w];
+                widen<NW, CW>(L.run.b, X);
                 row_replay_exit<NW>(sp, pv, fw, ts, t, X);
 #pragma unroll
-                for (int w = 0; w < NW; w++) X[w] |= rowc.b[w];
+                for (int w = 0; w < CW; w++) X[w] |= rowc.b[w];
                 comp_closed(L.run, X, L.run.kind & K_OPAQUE);
             } else {
                 comp_compose(L.run, rowc, nxt);
@@ -1323,34 +1347,34 @@ RRX_DEV void phase_s1(const ScanParams& sp, const ProgView& pv, const F& fw, Til
 }
 
 // `acc` = composite of the whole shard before this tile.  Returns the tile's inclusive composite.
-template <int NW, class F>
-RRX_DEV void phase_s2(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, const SLocal<NW>& L,
-                      const Comp<NW>& acc, Comp<NW>& inc) {
-    using TS = TileState<NW>;
-    uint32_t E[NW];
-    comp_apply<NW>(acc, sp.entry, E);
+template <int NW, class F, int CW>
+RRX_DEV void phase_s2(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, CW>& ts, const SLocal<CW>& L,
+                      const Comp<CW>& acc, Comp<CW>& inc) {
+    using TS = TileState<NW, CW>;
+    uint32_t E[CW];
+    comp_apply<CW>(acc, sp.entry, E);
 #pragma unroll
-    for (int w = 0; w < NW; w++) ts.misc[TS::M_ENTRY + w] = E[w];
+    for (int w = 0; w < CW; w++) ts.misc[TS::M_ENTRY + w] = E[w];
     if (L.blocked_from >= 0) {
         // second stage: walk the blocked segment with exact states
-        uint32_t X[NW], Y[NW];
-        comp_apply<NW>(L.pre_block, E, X);
-        Comp<NW> ex, rowc;
+        uint32_t X[CW], Y[NW];
+        comp_apply<CW>(L.pre_block, E, X);
+        Comp<CW> ex, rowc;
         for (int t = L.blocked_from; t < L.resume_at; t++) {
             load_row_comp(ts, t, rowc);
             comp_closed(ex, X, 0);
             store_row_comp(ts, t, ex);
             const uint32_t rt = rowc.kind & K_TYPE;
             if (rt == K_HARD) {
-#pragma unroll
-                for (int w = 0; w < NW; w++) Y[w] = X[w];
+                widen<NW, CW>(X, Y);
                 row_replay_exit<NW>(sp, pv, fw, ts, t, Y);
 #pragma unroll
-                for (int w = 0; w < NW; w++) X[w] = Y[w] | rowc.b[w];
+                for (int w = 0; w < CW; w++) X[w] = Y[w] | rowc.b[w];
             } else {
-                comp_apply<NW>(rowc, X, Y);
+                uint32_t Z[CW];
+                comp_apply<CW>(rowc, X, Z);
 #pragma unroll
-                for (int w = 0; w < NW; w++) X[w] = Y[w];
+                for (int w = 0; w < CW; w++) X[w] = Z[w];
             }
         }
         if (L.wait_agg) { comp_closed(inc, X, K_OPAQUE); return; }
@@ -1360,25 +1384,26 @@ RRX_DEV void phase_s2(const ScanParams& sp, const ProgView& pv, const F& fw, Til
 
 // ===== phase B: replay each row's prefix from its exact entry set (no injection) ====================
 // Returns the number of matches of the row.
-template <int NW, class F>
-RRX_DEV uint32_t phase_b(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW>& ts, int t,
+template <int NW, class F, int CW>
+RRX_DEV uint32_t phase_b(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, CW>& ts, int t,
                          bool any_open) {
     constexpr int ROWS = TILE_ROWS;
-    using TS = TileState<NW>;
+    using TS = TileState<NW, CW>;
     const int nb = row_nbytes(sp, ts.row0, t);
-    uint32_t X[NW], Bc[NW], f[NW];
+    uint32_t X[NW], Bc[NW], f[NW], Xc[CW];
     const uint32_t* E = ts.misc + TS::M_ENTRY;
     if (any_open) {
-        Comp<NW> pre;
+        Comp<CW> pre;
         load_row_comp(ts, t, pre);
-        comp_apply<NW>(pre, E, X);
+        comp_apply<CW>(pre, E, Xc);
     } else if (t == 0) {
 #pragma unroll
-        for (int w = 0; w < NW; w++) X[w] = E[w];
+        for (int w = 0; w < CW; w++) Xc[w] = E[w];
     } else {
 #pragma unroll
-        for (int w = 0; w < NW; w++) X[w] = ts.sum_b[w * ROWS + (t - 1)];
+        for (int w = 0; w < CW; w++) Xc[w] = ts.sum_b[w * ROWS + (t - 1)];
     }
+    widen<NW, CW>(Xc, X);
     uint32_t hit[4] = {0, 0, 0, 0};
     bool touched = false;
     const bool dn = fw.donly(pv);          // thread-owned scan: only dominated states are carried
@@ -1417,8 +1442,8 @@ RRX_DEV uint32_t phase_b(const ScanParams& sp, const ProgView& pv, const F& fw, 
 // ===== phase C: resolve the lazy start of every match and write (start,end) ========================
 // Backward walk from the accepting positions, starting with the byte at shard-local offset e-1; stops at the
 // first (= right-most) start that works: lazy.
-template <int NW, class F>
-RRX_DEV void resolve_and_write(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW>& ts,
+template <int NW, class F, int CW>
+RRX_DEV void resolve_and_write(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW, CW>& ts,
                                int64_t e, unsigned long long slot, uint32_t rank_in_tile) {
     uint32_t R[NW];
 #pragma unroll
@@ -1445,8 +1470,8 @@ RRX_DEV void resolve_and_write(const ScanParams& sp, const ProgView& pv, const F
 }
 
 // The match ending after tile-relative byte `rel`: if phase A already knows its lazy start, write it.
-template <int NW>
-RRX_DEV bool write_known(const ScanParams& sp, const TileState<NW>& ts, uint32_t rel, unsigned long long slot) {
+template <int NW, int CW>
+RRX_DEV bool write_known(const ScanParams& sp, const TileState<NW, CW>& ts, uint32_t rel, unsigned long long slot) {
     const uint32_t row = rel >> ROW_SHIFT, p = rel & (ROW_BYTES - 1);
     const uint32_t k0 = ts.kst[2 * row], k1 = ts.kst[2 * row + 1];
     uint32_t s;
@@ -1464,7 +1489,7 @@ RRX_DEV bool write_known(const ScanParams& sp, const TileState<NW>& ts, uint32_t
 
 // C1 (per lane): append the row's match ends to the tile's hit list (tile-relative end-1).
 // cnt[t] must hold the row's exclusive offset.  Only when the tile total fits the list.
-template <int NW> RRX_DEV void phase_c1_list(TileState<NW>& ts, int t, uint32_t offset, const uint32_t* hit) {
+template <int NW, int CW> RRX_DEV void phase_c1_list(TileState<NW, CW>& ts, int t, uint32_t offset, const uint32_t* hit) {
     uint32_t k = offset;
     for (int q = 0; q < 4; q++) {
         uint32_t v = hit[q];
@@ -1476,8 +1501,8 @@ template <int NW> RRX_DEV void phase_c1_list(TileState<NW>& ts, int t, uint32_t 
     }
 }
 // C2 (per lane): balanced — lane handles list entries lane, lane+32, ...
-template <int NW, class F>
-RRX_DEV void phase_c2_balanced(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW>& ts, int lane,
+template <int NW, class F, int CW>
+RRX_DEV void phase_c2_balanced(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW, CW>& ts, int lane,
                                uint32_t total, unsigned long long base) {
     for (uint32_t i = (uint32_t)lane; i < total; i += TILE_ROWS) {
         const uint32_t rel = ts.list[i];
@@ -1486,8 +1511,8 @@ RRX_DEV void phase_c2_balanced(const ScanParams& sp, const ProgView& pv, const F
     }
 }
 // C2 fallback (per lane): every row resolves its own matches (tiles with more hits than the list holds).
-template <int NW, class F>
-RRX_DEV void phase_c2_rows(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW>& ts, int t,
+template <int NW, class F, int CW>
+RRX_DEV void phase_c2_rows(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW, CW>& ts, int t,
                            uint32_t offset, const uint32_t* hit, unsigned long long base) {
     unsigned long long slot = base + offset;
     const int64_t row_lo = ts.lo() + ((int64_t)t << ROW_SHIFT);

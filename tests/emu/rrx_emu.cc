@@ -24,19 +24,23 @@ namespace {
 int g_sparse_mode = 1;
 unsigned long long g_sparse_rows = 0, g_dense_rows = 0, g_fast_tiles = 0;
 
-template <int NW, int NT, int NB>
+// test-only policy: the generic shared-memory program with a narrower carried width, standing in for the run-time
+// specialised kernels of thread-owned programs (rrx_prog.h CW)
+template <int NW, int CW_> struct ProgNarrow : Prog<NW, -1, 0> {};
+
+template <int NW, int CW, class PROG>
 int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t len, int64_t base,
         const uint32_t* entry, int64_t* out, uint64_t cap, uint64_t* counts, uint32_t* err, uint32_t* shard_comp,
         PendingStart* pending, uint32_t pending_cap) {
     constexpr int ROWS = TILE_ROWS;
-    using TS = TileState<NW>;
+    using TS = TileState<NW, CW>;
     const ProgHeader& h = prog.hdr();
     const uint32_t num_tiles = (uint32_t)((len + TILE_BYTES - 1) / TILE_BYTES);
 
     std::vector<uint8_t> smem(TS::bytes() + 64, 0xAA);
     std::vector<uint32_t> btab(NW == 1 ? 256 * 32 : 256 * NW);
     for (uint32_t i = 0; i < btab.size(); i++) btab[i] = prog.blob[h.off_B + (NW == 1 ? (i >> 5) : i)];
-    std::vector<uint32_t> incl((size_t)(num_tiles + 1) * (1 + 3 * NW), 0);   // inclusive composite per tile
+    std::vector<uint32_t> incl((size_t)(num_tiles + 1) * (1 + 3 * CW), 0);   // inclusive composite per tile
     unsigned long long matches_so_far = 0;
     std::vector<unsigned long long> tile_base(num_tiles + 1, 0);
     unsigned long long total[2] = {0, 0};
@@ -98,19 +102,19 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
             // thread-owned candidate scan, as the kernel: every row, no dense fallback
             for (int t = 0; t < ROWS; t++) {
                 ProgView pv = view(t);
-                Prog<NW, NT, NB> fw;
+                PROG fw;
                 fw.init(pv);
                 uint32_t cm[4];
                 int qfree;
                 phase_a_mask<NW>(ts, t, fw.sp_cand(pv), cm);
                 const uint32_t kind = phase_d_kind<NW>(sp, pv, fw, ts, t, &qfree);
-                phase_a_cand<NW, Prog<NW, NT, NB>, true>(sp, pv, fw, ts, t, cm, tails[t]);
+                phase_a_cand<NW, PROG, true>(sp, pv, fw, ts, t, cm, tails[t]);
                 if (kind != K_CLOSED) all_closed_d = false;
                 // the kernel's early-publish rule: no candidate at or behind qfree => the row's exit must be empty
                 bool behind = false;
                 for (int p = qfree; p < ROW_BYTES; p++) behind = behind || ((cm[p >> 5] >> (p & 31)) & 1u);
                 if (kind == K_CLOSED && !behind)
-                    for (int w = 0; w < NW; w++) if (ts.sum_b[w * ROWS + t]) *err |= 0x40u;
+                    for (int w = 0; w < CW; w++) if (ts.sum_b[w * ROWS + t]) *err |= 0x40u;
             }
             published = all_closed_d;
             dense = false;
@@ -120,7 +124,7 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
             bool all_closed = true;
             for (int t = 0; t < ROWS; t++) {
                 ProgView pv = view(t);
-                Prog<NW, NT, NB> fw;
+                PROG fw;
                 fw.init(pv);
                 sp_ok[t] = phase_a_exit<NW>(sp, pv, fw, ts, t);
                 all_closed = all_closed && sp_ok[t];
@@ -130,17 +134,17 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
             if (all_closed) {
                 for (int t = 0; t < ROWS; t++) {
                     ProgView pv = view(t);
-                    Prog<NW, NT, NB> fw;
+                    PROG fw;
                     fw.init(pv);
                     uint32_t cm[4];
                     phase_a_mask<NW>(ts, t, fw.sp_cand(pv), cm);
-                    sp_ok[t] = phase_a_cand<NW, Prog<NW, NT, NB>, false>(sp, pv, fw, ts, t, cm, tails[t]);
+                    sp_ok[t] = phase_a_cand<NW, PROG, false>(sp, pv, fw, ts, t, cm, tails[t]);
                     if (!sp_ok[t]) dense = true;
                     else if (g_sparse_mode == 2) {
                         sparse_drain<NW>(ts, t, tails[t]);      // materialise for the comparison
                         if (ts.sum_kind[t] != K_CLOSED) *err |= 0x80u;
                         for (int q = 0; q < 4; q++) sp_hits[t][q] = ts.hits[q * ROWS + t];
-                        for (int w = 0; w < NW; w++) sp_b[t][w] = ts.sum_b[w * ROWS + t];
+                        for (int w = 0; w < CW; w++) sp_b[t][w] = ts.sum_b[w * ROWS + t];
                         sp_kst[t][0] = ts.kst[2 * t]; sp_kst[t][1] = ts.kst[2 * t + 1];
                     }
                 }
@@ -153,13 +157,13 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
         if (dense) {
             for (int t = 0; t < ROWS; t++) {
                 ProgView pv = view(t);
-                Prog<NW, NT, NB> fw;
+                PROG fw;
                 fw.init(pv);
                 phase_a<NW>(sp, pv, fw, ts, t);
             }
             for (int t = 0; t < ROWS; t++) {
                 ProgView pv = view(t);
-                Prog<NW, NT, NB> fw;
+                PROG fw;
                 fw.init(pv);
                 phase_a2<NW>(pv, fw, ts, t);
             }
@@ -168,7 +172,7 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
                     if (!sp_ok[t]) continue;
                     if (ts.sum_kind[t] != K_CLOSED) *err |= 0x80u;
                     for (int q = 0; q < 4; q++) if (sp_hits[t][q] != ts.hits[q * ROWS + t]) *err |= 0x80u;
-                    for (int w = 0; w < NW; w++) if (sp_b[t][w] != ts.sum_b[w * ROWS + t]) *err |= 0x80u;
+                    for (int w = 0; w < CW; w++) if (sp_b[t][w] != ts.sum_b[w * ROWS + t]) *err |= 0x80u;
                     ts.kst[2 * t] = sp_kst[t][0]; ts.kst[2 * t + 1] = sp_kst[t][1];   // let phase C use them
                 }
             }
@@ -176,18 +180,18 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
         for (int t = 0; t < ROWS; t++) any_open = any_open || ts.sum_kind[t] == K_RANK1 || ts.sum_kind[t] == K_HARD;
         {
             ProgView pv = view(0);
-            Prog<NW, NT, NB> fw;
+            PROG fw;
             fw.init(pv);
             // The emulator runs the tiles in order, so "look-back" is just the previous tile's
             // inclusive composite; the two-level GPU look-back (rrx_scan.cu) is exercised by -m gpu.
-            SLocal<NW> L;
-            Comp<NW> acc, inc;
+            SLocal<CW> L;
+            Comp<CW> acc, inc;
             phase_s1<NW>(sp, pv, fw, ts, any_open, L);
             if (tile == 0) comp_ident(acc);
-            else load_comp_global<NW>(incl.data() + (size_t)(tile - 1) * (1 + 3 * NW), acc);
+            else load_comp_global<CW>(incl.data() + (size_t)(tile - 1) * (1 + 3 * CW), acc);
             phase_s2<NW>(sp, pv, fw, ts, L, acc, inc);
-            store_comp_global<NW>(incl.data() + (size_t)tile * (1 + 3 * NW), inc);
-            if (tile + 1 == num_tiles) store_comp_global<NW>(sp.shard_comp, inc);
+            store_comp_global<CW>(incl.data() + (size_t)tile * (1 + 3 * CW), inc);
+            if (tile + 1 == num_tiles) store_comp_external<NW, CW>(sp.shard_comp, inc);
         }
         uint32_t cnt[ROWS], off[ROWS], total_t = 0;
         // fast tail, as in the kernel: every row simple and without carried state
@@ -195,7 +199,7 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
         if (!dense) {
             for (int t = 0; t < ROWS; t++) {
                 uint32_t carried = 0;
-                for (int w = 0; w < NW; w++) carried |= t == 0 ? ts.misc[TS::M_ENTRY + w] : ts.sum_b[w * ROWS + t - 1];
+                for (int w = 0; w < CW; w++) carried |= t == 0 ? ts.misc[TS::M_ENTRY + w] : ts.sum_b[w * ROWS + t - 1];
                 if (!tails[t].simple() || carried) fast = false;
             }
             if (!fast) for (int t = 0; t < ROWS; t++) sparse_drain<NW>(ts, t, tails[t]);
@@ -211,7 +215,7 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
         }
         for (int t = 0; t < ROWS; t++) {
             ProgView pv = view(t);
-            Prog<NW, NT, NB> fw;
+            PROG fw;
             fw.init(pv);
             cnt[t] = phase_b<NW>(sp, pv, fw, ts, t, any_open);
         }
@@ -226,14 +230,14 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
                 for (int t = 0; t < ROWS; t++) phase_c1_list<NW>(ts, t, off[t], hit[t]);
                 for (int t = 0; t < ROWS; t++) {
                     ProgView pv = view(t);
-                    Prog<NW, NT, NB> fw;
+                    PROG fw;
                     fw.init(pv);
                     phase_c2_balanced<NW>(sp, pv, fw, ts, t, total_t, b0);
                 }
             } else {
                 for (int t = 0; t < ROWS; t++) {
                     ProgView pv = view(t);
-                    Prog<NW, NT, NB> fw;
+                    PROG fw;
                     fw.init(pv);
                     phase_c2_rows<NW>(sp, pv, fw, ts, t, off[t], hit[t], b0);
                 }
@@ -270,10 +274,11 @@ int emu_scan(const char* pattern, int reduce, int fast, const uint8_t* text_with
         return -1;
     }
     const ProgHeader& h = prog.hdr();
-    if (info) { info[0] = h.NW; info[1] = h.P; info[2] = h.n_terms; info[3] = h.n_bicl; info[4] = h.use_rows; info[5] = h.static_depth; info[6] = h.sparse_ok; info[7] = h.cand_byte; info[8] = h.donly; }
+    if (info) { info[0] = h.NW; info[1] = h.P; info[2] = h.n_terms; info[3] = h.n_bicl; info[4] = h.use_rows; info[5] = h.static_depth; info[6] = h.sparse_ok; info[7] = h.cand_byte; info[8] = h.donly; info[9] = h.CW; }
     const uint8_t* text = text_with_ctx + left_ctx;
     PendingStart* pend = reinterpret_cast<PendingStart*>(pending);
-#define GO(NW_, NT_, NB_) return run<NW_, NT_, NB_>(prog, text, left_ctx, len, base, entry, out, cap, counts, err, shard_comp, pend, pending_cap)
+#define GO(NW_, NT_, NB_) return run<NW_, NW_, Prog<NW_, NT_, NB_>>(prog, text, left_ctx, len, base, entry, out, cap, counts, err, shard_comp, pend, pending_cap)
+#define GON(NW_, CW_) return run<NW_, CW_, ProgNarrow<NW_, CW_>>(prog, text, left_ctx, len, base, entry, out, cap, counts, err, shard_comp, pend, pending_cap)
     if (h.NW == 1) {
         if (fast && !h.use_rows && !h.use_rrows) {
             const uint32_t nt = h.n_terms > h.n_rterms ? h.n_terms : h.n_rterms;
@@ -290,6 +295,12 @@ int emu_scan(const char* pattern, int reduce, int fast, const uint8_t* text_with
             if (nt <= 4 && nb <= 2) GO(1, 4, 2);
         }
         GO(1, -1, 0);
+    }
+    // `fast` on a thread-owned multi-word program: carry CW words only, as the run-time specialised kernels do
+    if (fast && h.donly && h.CW < h.NW) {
+        if (h.CW == 1) switch (h.NW) { case 2: GON(2, 1); case 4: GON(4, 1); case 8: GON(8, 1); case 16: GON(16, 1); case 32: GON(32, 1); }
+        if (h.CW == 2) switch (h.NW) { case 4: GON(4, 2); case 8: GON(8, 2); case 16: GON(16, 2); case 32: GON(32, 2); }
+        if (h.CW == 4) switch (h.NW) { case 8: GON(8, 4); case 16: GON(16, 4); case 32: GON(32, 4); }
     }
     switch (h.NW) {
         case 2: GO(2, -1, 0);

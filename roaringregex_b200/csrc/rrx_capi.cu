@@ -28,7 +28,7 @@ int cuda_err(cudaError_t e, const char* what) {
 
 // Control block of a scan over T tiles (B = ceil(T/32) blocks); everything in it is zeroed before
 // the scan: [-,err,total[2],n_matches | pad | ticket (its own 128-byte line: every tile of the grid adds to it, nothing
-// else should wait behind those atomics) | f_a0[T] f_i0[T] f_a1[B] f_i1[B] st_arrive[B]].
+// else should wait behind those atomics) | f_a0[T] f_i0[T] f_a1[B] f_i1[B] st_arrive[B] tile_stop[T]].
 // Returns the size; fills the five offsets.
 size_t ctrl_layout(size_t T, size_t* off) {
     const size_t B = (T + 31) / 32;
@@ -39,6 +39,7 @@ size_t ctrl_layout(size_t T, size_t* off) {
     f[2] = o; o += 4 * B;
     f[3] = o; o += 4 * B;
     f[4] = o; o += 4 * B;
+    f[5] = o; o += 4 * T;        // stop-byte table (ScanParams::tile_stop)
     return (o + 15) & ~(size_t)15;
 }
 // Non-overlapping view (RRX_MODE_NO_OVERLAP): filter a device match list of n pairs into a newly
@@ -419,6 +420,8 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     sp.f_a1 = reinterpret_cast<volatile uint32_t*>(c + off[2]);
     sp.f_i1 = reinterpret_cast<volatile uint32_t*>(c + off[3]);
     sp.st_arrive = reinterpret_cast<uint32_t*>(c + off[4]);
+    // (only kernels that WRITE the stop-byte table may wait on it: thread-owned programs with a reverse skip state)
+    sp.tile_stop = (h.donly && h.rskip_n) ? reinterpret_cast<volatile uint32_t*>(c + off[5]) : nullptr;
     sp.tile_seg = s->d_tile_seg;
     sp.tile_cnt = s->d_tile_cnt;
     sp.st_a0 = s->d_tpay;

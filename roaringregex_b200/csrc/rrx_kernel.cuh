@@ -261,6 +261,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
     ts.carve(regions + (size_t)warp * K::REGION);
     // pad bytes behind every staged row: a byte that no position accepts (see phase_a_cand)
     *reinterpret_cast<uint32_t*>(ts.text + lane * ROW_PITCH + ROW_BYTES) = 0xffffffffu;
+    if (lane == 0) ts.misc[TS::M_ZVALID] = 0u;
     const int64_t len = (int64_t)sp.len;
 #ifdef RRX_PHASE_TIMING
     long long tprev_ = clock64();
@@ -366,6 +367,24 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         tail.kq = tail.ks = tail.nacc = tail.nruns = 0;
         tail.rt = 0ull;
         tail.drained = 1;
+        if (fw.donly(pv) && fw.rs_n(pv) != 0u) {
+            // The program's backward walks have a skip state: note where its stop bytes are — per row in shared memory
+            // (walks inside the tile), and the tile's last one in the stop-byte table (walks that arrive from later tiles).
+            uint32_t zm[4];
+            phase_z_mask<NW>(ts, lane, fw.rs_bytes(pv), fw.rs_n(pv), zm);
+            const uint32_t rowhas = __ballot_sync(FULL, (zm[0] | zm[1] | zm[2] | zm[3]) != 0u);
+            if (lane == 0) { ts.misc[TS::M_ROWHAS] = rowhas; ts.misc[TS::M_ZVALID] = 1u; }
+            if (rowhas == 0u ? lane == 0 : lane == 31 - __clz((int)rowhas)) {
+                uint32_t v = 1u;
+                if (rowhas) {
+                    const int q = zm[3] ? 3 : zm[2] ? 2 : zm[1] ? 1 : 0;
+                    const uint32_t m = q == 3 ? zm[3] : q == 2 ? zm[2] : q == 1 ? zm[1] : zm[0];
+                    v = 2u + (uint32_t)lane * ROW_BYTES + (uint32_t)q * 32u + (31u - (uint32_t)__clz((int)m));
+                }
+                sp.tile_stop[tile] = v;
+            }
+            __syncwarp();
+        }
         if (fw.donly(pv)) {
             // Thread-owned candidate scan: every row — full, partial or empty — goes through it; there is no dense
             // fallback.  The rows' exits (dominated states only) are known once the candidates have been followed;

@@ -78,13 +78,26 @@ RRX_DEV uint32_t fshl(uint32_t lo, uint32_t hi, uint32_t r) { return __funnelshi
 RRX_DEV uint32_t fshr(uint32_t lo, uint32_t hi, uint32_t r) { return __funnelshift_r(lo, hi, r); }   // (hi:lo >> r) & 0xffffffff
 RRX_DEV int popc32(uint32_t x) { return __popc(x); }
 RRX_DEV int ctz32(uint32_t x) { return __ffs((int)x) - 1; }
+RRX_DEV int clz32(uint32_t x) { return __clz((int)x); }
 #else
 RRX_DEV uint32_t rotl32(uint32_t x, uint32_t r) { r &= 31; return r ? (x << r) | (x >> (32 - r)) : x; }
 RRX_DEV uint32_t fshl(uint32_t lo, uint32_t hi, uint32_t r) { r &= 31; return r ? (hi << r) | (lo >> (32 - r)) : hi; }
 RRX_DEV uint32_t fshr(uint32_t lo, uint32_t hi, uint32_t r) { r &= 31; return r ? (lo >> r) | (hi << (32 - r)) : lo; }
 RRX_DEV int popc32(uint32_t x) { return __builtin_popcount(x); }
 RRX_DEV int ctz32(uint32_t x) { return __builtin_ctz(x); }
+RRX_DEV int clz32(uint32_t x) { return __builtin_clz(x); }
 #endif
+
+RRX_DEV void rrx_fence() {
+#if defined(__CUDA_ARCH__) && !defined(RRX_HOST_EMU)
+    __threadfence();
+#endif
+}
+RRX_DEV void rrx_backoff() {
+#if defined(__CUDA_ARCH__) && !defined(RRX_HOST_EMU)
+    __nanosleep(100);
+#endif
+}
 
 // ---- small fixed-width set helpers ---------------------------------------------------------------
 template <int NW> RRX_DEV bool any_w(const uint32_t* a) {
@@ -414,6 +427,10 @@ struct ScanParams {
     // atomicAdd on total[0].  seg_stride == 0: every tile allocates.  The ordering pass compacts.
     uint32_t seg_stride;
     uint32_t donly;             // 1: thread-owned candidate scan (program header `donly`; see phase_a_cand<.., true>)
+    // Stop-byte table (programs with a reverse skip state, thread-owned scan): tile_stop[tile] = 0 not known yet,
+    // 1 the tile holds none of the skip state's stop bytes, else 2 + tile-relative offset of its LAST one.  A backward
+    // walk in the skip state that leaves its tile hops over whole tiles with it (see back_walk).  Zeroed per scan.
+    volatile uint32_t* tile_stop;
     unsigned long long ovf_base;
     uint32_t* err;
     uint32_t* shard_comp;       // [1+3*NW] composite of the whole shard (relative to an unknown entry)
@@ -441,10 +458,14 @@ template <int NW, int CW = NW> struct TileState {
     uint32_t* cnt;        // [32]       matches per row -> exclusive offsets
     uint32_t* misc;       // see M_* below
     uint32_t* rq;         // replay queue: RQ_CAP items of {row<<5 | quad, state[NW]}
+    uint32_t* zmask;      // [4][32], aliases rq
     uint16_t* list;       // hit list for the balanced start scans; aliases sum_b/sum_U/sum_P
     uint32_t* kst;        // [2][32]    known lazy starts of up to two matches per row: (end-1)<<16 | (start - row start + KS_BIAS)
     uint64_t row0;        // first row of the tile
-    static constexpr int M_RQCNT = 0, M_ENTRY = 8;
+    static constexpr int M_RQCNT = 0, M_ROWHAS = 1, M_ZVALID = 2, M_ENTRY = 8;
+    // Stop-byte masks of the staged tile (zmask[q*32 + t]: bit p <=> byte 32q+p of row t is one of the reverse skip
+    // state's stop bytes or >= 0x80), M_ROWHAS: rows that have any, M_ZVALID: masks valid for this tile.
+    // They alias the replay queue, which only the dense row scan uses.
     static constexpr int MISC_WORDS = 8 + CW;
     static constexpr int RQ_CAP = NW <= 2 ? 64 : NW <= 4 ? 32 : 16;         // (>= 512 bytes: the stop-byte masks alias it)
     static constexpr int LIST_CAP = 3 * CW * ROWS * 2;
@@ -461,6 +482,7 @@ template <int NW, int CW = NW> struct TileState {
         misc = p; p += MISC_WORDS;
         kst = p; p += 2 * ROWS;
         rq = p;
+        zmask = p;
         list = reinterpret_cast<uint16_t*>(sum_b);
     }
     RRX_DEV int64_t lo() const { return (int64_t)(row0 << ROW_SHIFT); }
@@ -671,7 +693,22 @@ RRX_DEV WalkResult back_walk(const ScanParams& sp, const ProgView& pv, const F& 
             uint32_t d = 0;
 #pragma unroll
             for (int w = 0; w < NW; w++) d |= R[w] ^ fw.rs_F(pv, w);
-            if (d == 0) {
+            if (d == 0 && ts.misc[TileState<NW, CW>::M_ZVALID]) {
+                // the tile's stop-byte masks answer "last stop byte at or before rel" in a few instructions
+                uint32_t row = (uint32_t)rel >> ROW_SHIFT, pos = (uint32_t)rel & (ROW_BYTES - 1), w = pos >> 5;
+                uint32_t m = ts.zmask[w * TILE_ROWS + row] & (0xffffffffu >> (31u - (pos & 31u)));
+                while (m == 0u && w > 0u) { w--; m = ts.zmask[w * TILE_ROWS + row]; }
+                if (m == 0u) {
+                    const uint32_t rh = ts.misc[TileState<NW, CW>::M_ROWHAS] & ((1u << row) - 1u);
+                    if (rh == 0u) { rel = -1; break; }              // ran to the tile start inside F
+                    row = 31u - (uint32_t)clz32(rh);
+                    w = 3u;
+                    m = ts.zmask[3 * TILE_ROWS + row];
+                    while (m == 0u) { w--; m = ts.zmask[w * TILE_ROWS + row]; }
+                }
+                rel = (int)(row * ROW_BYTES + w * 32u + (31u - (uint32_t)clz32(m)));
+                c = ts.rel_byte((uint32_t)rel);
+            } else if (d == 0) {
                 // bytes down to a word boundary, then whole words (SWAR: does the word hold b0, b1 or a
                 // byte >= 0x80?), then the bytes of the word that does
                 while (c != b0 && c != b1 && c < 128u && rel > 0 && (rel & 3) != 0) { rel--; c = ts.rel_byte((uint32_t)rel); }
@@ -708,11 +745,28 @@ RRX_DEV WalkResult back_walk(const ScanParams& sp, const ProgView& pv, const F& 
         // slow path: the walk left the tile; continue in global memory
         for (;;) {
             if (j < left_edge) { wr.pend = true; break; }
-            uint32_t c = (uint32_t)sp.text[j];
+            uint32_t d = 1;
             if (rsn) {
-                uint32_t d = 0;
+                d = 0;
 #pragma unroll
                 for (int w = 0; w < NW; w++) d |= R[w] ^ fw.rs_F(pv, w);
+                if (d == 0 && sp.tile_stop && j >= 0 && (j & (TILE_BYTES - 1)) == TILE_BYTES - 1) {
+                    // in the skip state on the last byte of an earlier tile of this shard: that tile's entry of the
+                    // stop-byte table (written by its warp right after staging; smaller tile index, so it is in
+                    // flight or done) says where its last stop byte is, or that it has none
+                    const int64_t tt = j >> 12;
+                    uint32_t v = sp.tile_stop[tt];
+                    while (v == 0u) { rrx_backoff(); v = sp.tile_stop[tt]; }
+                    if (v == 1u) {
+                        j -= TILE_BYTES;
+                        if (budget > 0 && --budget == 0) { wr.over = true; break; }
+                        continue;
+                    }
+                    j = (tt << 12) + (int64_t)(v - 2u);
+                }
+            }
+            uint32_t c = (uint32_t)sp.text[j];
+            if (rsn) {
                 if (d == 0) {
                     // bytes down to a word boundary, whole words (the text pointer is 16-byte aligned), then bytes
                     while (c != b0 && c != b1 && c < 128u && j > left_edge && (j & 3) != 0) { j--; c = (uint32_t)sp.text[j]; }
@@ -894,6 +948,32 @@ RRX_DEV void phase_a_mask(const TileState<NW, CW>& ts, int t, uint32_t cand, uin
             acc = fshl(f * 0x00204081u, acc, 4);                    // the 4 flags land in the top nibble
         }
         cm[q] = acc;
+    }
+}
+
+// Stop-byte mask of row t for the reverse skip state (stop bytes b0/b1 of rrx_prog.h rskip, and every byte >= 0x80):
+// bit p of zm[q] <=> byte 32q+p stops a backward walk that is in the skip state.  Also left in ts.zmask.
+template <int NW, int CW>
+RRX_DEV void phase_z_mask(TileState<NW, CW>& ts, int t, uint32_t rs_bytes, uint32_t rs_n, uint32_t* zm) {
+    const uint32_t B0 = (rs_bytes & 0xffu) * 0x01010101u, B1 = ((rs_bytes >> 8) & 0xffu) * 0x01010101u;
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(ts.text + t * ROW_PITCH);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int j = 7; j >= 0; j--) {
+            const uint32_t wv = rw[q * 8 + j];
+            const uint32_t x0 = wv ^ B0;
+            uint32_t f = ~(((x0 | 0x80808080u) - 0x01010101u) | x0);      // bit 7 of a byte set <=> the byte equals b0
+            if (rs_n > 1u) {
+                const uint32_t x1 = wv ^ B1;
+                f |= ~(((x1 | 0x80808080u) - 0x01010101u) | x1);
+            }
+            f = (f | wv) & 0x80808080u;                                    // ... or is >= 0x80
+            acc = fshl(f * 0x00204081u, acc, 4);
+        }
+        zm[q] = acc;
+        ts.zmask[q * TILE_ROWS + t] = acc;
     }
 }
 
@@ -1248,16 +1328,6 @@ template <int NW, int CW> RRX_DEV void store_comp_external(uint32_t* dst, const 
     }
 }
 
-RRX_DEV void rrx_fence() {
-#if defined(__CUDA_ARCH__) && !defined(RRX_HOST_EMU)
-    __threadfence();
-#endif
-}
-RRX_DEV void rrx_backoff() {
-#if defined(__CUDA_ARCH__) && !defined(RRX_HOST_EMU)
-    __nanosleep(100);
-#endif
-}
 
 // Exit of the no-injection replay of row t from the exact entry set X (in place).
 template <int NW, class F, int CW>

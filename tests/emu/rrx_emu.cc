@@ -43,6 +43,7 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
     std::vector<uint32_t> incl((size_t)(num_tiles + 1) * (1 + 3 * CW), 0);   // inclusive composite per tile
     unsigned long long matches_so_far = 0;
     std::vector<unsigned long long> tile_base(num_tiles + 1, 0);
+    std::vector<uint32_t> tile_stop(num_tiles + 1, 0);
     unsigned long long total[2] = {0, 0};
     uint32_t ticket = 0;
     *err = 0;
@@ -58,6 +59,7 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
     sp.static_closed = (h.static_depth != 0xffffffffu && h.static_depth + 1 <= (uint32_t)ROW_BYTES) ? 1u : 0u;
     sp.sparse = h.sparse_ok && g_sparse_mode ? 1u : 0u;
     sp.donly = h.donly;
+    sp.tile_stop = (h.donly && h.rskip_n && g_sparse_mode) ? tile_stop.data() : nullptr;
     sp.ticket = &ticket;
     sp.out = reinterpret_cast<long long*>(out);
     sp.out_cap = cap;
@@ -98,6 +100,23 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
         SparseTail tails[ROWS];
         for (int t = 0; t < ROWS; t++) { tails[t].kq = tails[t].ks = tails[t].nacc = tails[t].nruns = 0; tails[t].rt = 0; tails[t].drained = 1; }
         bool published = false, all_closed_d = true;
+        ts.misc[TS::M_ZVALID] = 0;
+        if (h.donly && g_sparse_mode && h.rskip_n) {
+            // stop-byte masks of the tile + its entry of the stop-byte table, as the kernel
+            uint32_t rowhas = 0, v = 1;
+            for (int t = 0; t < ROWS; t++) {
+                uint32_t zm[4];
+                phase_z_mask<NW>(ts, t, h.rskip_bytes, h.rskip_n, zm);
+                if (zm[0] | zm[1] | zm[2] | zm[3]) {
+                    rowhas |= 1u << t;
+                    const int q = zm[3] ? 3 : zm[2] ? 2 : zm[1] ? 1 : 0;
+                    v = 2u + (uint32_t)t * ROW_BYTES + (uint32_t)q * 32u + (31u - (uint32_t)__builtin_clz(zm[q]));
+                }
+            }
+            ts.misc[TS::M_ROWHAS] = rowhas;
+            ts.misc[TS::M_ZVALID] = 1;
+            tile_stop[tile] = v;
+        }
         if (h.donly && g_sparse_mode) {
             // thread-owned candidate scan, as the kernel: every row, no dense fallback
             for (int t = 0; t < ROWS; t++) {

@@ -25,8 +25,9 @@ namespace rrx {
 template <int NW, int CW, int WARPS_> struct KCfg {
     static constexpr int WARPS = WARPS_;
     static constexpr int THREADS = WARPS * 32;
-    static constexpr uint32_t BT_BYTES = (NW == 1 ? 256u * 128u : 256u * (uint32_t)NW * 4u);
-    static constexpr size_t REGION = (TileState<NW, CW>::bytes() + 15) & ~(size_t)15;
+    static constexpr uint32_t BT_BYTES = (NW == 1 ? 256u * (uint32_t)BT_COPIES * 4u : 256u * (uint32_t)NW * 4u);
+    // per-warp region: the tile state, then 16 bytes for the warp's mbarrier (bulk-copy staging)
+    static constexpr size_t REGION = (TileState<NW, CW>::bytes() + 16 + 15) & ~(size_t)15;
     // small program part: header + 3 sets + 2 decompositions
     static constexpr size_t SMALL = sizeof(ProgHeader) + 4u * (3 * NW + 2 * (RRX_MAX_TERMS * (1 + NW) + RRX_MAX_BICL * 2 * NW + NW) + NW + RRX_MAX_GROUPS * (2 * NW + 1) + 2 * NW);
     static constexpr size_t SMEM = BT_BYTES + (size_t)WARPS * REGION + SMALL + 64;
@@ -68,6 +69,35 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 constexpr unsigned long long CT_READY = 1ull << 63;
+
+#ifdef RRX_BULK
+// Tile staging with bulk asynchronous copies (the TMA engine's 1-D mode): each lane asks for ITS 128-byte row with one
+// cp.async.bulk, completion is counted in bytes on the warp's mbarrier — no registers, no per-word instructions.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+    } while (!done);
+}
+// Ask for the 32 rows of the tile at text offset g0 (whole tile inside the text).  Every lane has finished reading the
+// staging rows (the caller's __syncwarp); generic-proxy accesses are ordered before the async-proxy writes by the fence.
+__device__ __forceinline__ void bulk_stage_tile(const uint8_t* text, int64_t g0, uint32_t rows_smem, uint32_t mbar, int lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (lane == 0) mbar_expect_tx(mbar, (uint32_t)TILE_BYTES);
+    __syncwarp();
+    bulk_g2s(rows_smem + (uint32_t)lane * (uint32_t)ROW_PITCH, text + g0 + ((int64_t)lane << ROW_SHIFT), (uint32_t)ROW_BYTES, mbar);
+}
+#endif
 
 template <int NW> __device__ __forceinline__ void bcast_comp(Comp<NW>& c, int src) {
     c.kind = __shfl_sync(FULL, c.kind, src);
@@ -246,15 +276,24 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
     for (uint32_t i = tid; i < n_small; i += K::THREADS) progsm[i] = sp.prog[i];
     if (NW == 1) {
         // one private copy of the table per lane: entry (c, lane) lives in bank `lane`
-        for (uint32_t i = tid; i < K::BT_BYTES / 4; i += K::THREADS) Btab[i] = sp.prog[off_B + (i >> 5)];
+        for (uint32_t i = tid; i < K::BT_BYTES / 4; i += K::THREADS) Btab[i] = sp.prog[off_B + i / (uint32_t)BT_COPIES];
     } else {
         for (uint32_t i = tid; i < K::BT_BYTES / 4; i += K::THREADS) Btab[i] = sp.prog[off_B + i];
     }
+#ifdef RRX_BULK
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(regions + (size_t)warp * K::REGION + K::REGION - 16);
+    const uint32_t rows_smem = (uint32_t)__cvta_generic_to_shared(regions + (size_t)warp * K::REGION);
+    uint32_t mphase = 0;
+    if (lane == 0) {
+        mbar_init(mbar, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#endif
     __syncthreads();                      // the only block-level barrier of the kernel
     ProgView pv;
     pv.sm = progsm;
     pv.glob = sp.prog;
-    pv.Blane = reinterpret_cast<const uint8_t*>(Btab) + (NW == 1 ? lane * 4 : 0);
+    pv.Blane = reinterpret_cast<const uint8_t*>(Btab) + (NW == 1 ? (lane % BT_COPIES) * 4 : 0);
     F fw;
     fw.init(pv);
     TS ts;
@@ -324,9 +363,21 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         {
             const int64_t g0 = ts.lo();
             uint4 v[8];
+#ifdef RRX_BULK
+            if (!preloaded && g0 + TILE_BYTES <= len) {
+                __syncwarp();
+                bulk_stage_tile(sp.text, g0, rows_smem, mbar, lane);
+                preloaded = true;
+            }
+            if (preloaded) {                              // bulk copies in flight (started just now, or during the previous tile's tail)
+                mbar_wait(mbar, mphase);
+                mphase ^= 1u;
+            } else if (g0 + TILE_BYTES <= len) {
+#else
             if (preloaded) {                              // copies started during the previous tile's tail
                 asm volatile("cp.async.wait_all;" ::: "memory");
             } else if (g0 + TILE_BYTES <= len) {          // whole tile inside the text: no per-load checks
+#endif
                 const uint4* src = reinterpret_cast<const uint4*>(sp.text + g0) + lane;
 #pragma unroll
                 for (int k = 0; k < 8; k++) v[k] = __ldcs(src + k * 32);
@@ -349,7 +400,11 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     uint32_t* dst = ts.chunk_ptr(k * 32 + lane);
+#if RRX_ROW_PITCH % 16 == 0
+                    *reinterpret_cast<uint4*>(dst) = v[k];
+#else
                     dst[0] = v[k].x; dst[1] = v[k].y; dst[2] = v[k].z; dst[3] = v[k].w;
+#endif
                 }
             }
             preloaded = false;
@@ -541,12 +596,24 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
                 const uint32_t nt = __shfl_sync(FULL, next_raw, 0);
                 const int64_t n0 = ((int64_t)nt * TILE_ROWS) << ROW_SHIFT;
                 if (nt < sp.num_tiles && n0 + TILE_BYTES <= len) {
+#ifdef RRX_BULK
+                    __syncwarp();
+                    bulk_stage_tile(sp.text, n0, rows_smem, mbar, lane);
+#elif RRX_ROW_PITCH % 16 == 0
+                    // 16-byte aligned rows: chunk q = 32k + lane of the tile -> row q/8, bytes 16*(q%8).. (8 copies per lane)
+                    const uint8_t* src = sp.text + n0 + 16 * lane;
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ts.text) + (uint32_t)(lane >> 3) * (uint32_t)ROW_PITCH + 16u * (uint32_t)(lane & 7);
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 4u * (uint32_t)ROW_PITCH * k), "l"(src + 512 * k) : "memory");
+#else
                     // word j = 32k + lane of the tile -> staged row k, word `lane` (rows are 33 words apart)
                     const uint32_t* src = reinterpret_cast<const uint32_t*>(sp.text + n0) + lane;
                     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ts.text) + 4u * (uint32_t)lane;
 #pragma unroll
                     for (int k = 0; k < 32; k++)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 132u * k), "l"(src + 32 * k) : "memory");
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)ROW_PITCH * k), "l"(src + 32 * k) : "memory");
+#endif
                     preloaded = true;
                 }
             }

@@ -48,7 +48,20 @@ constexpr int TILE_BYTES = TILE_ROWS * ROW_BYTES;     // 4 KiB
 // Rows are staged in shared memory 132 bytes apart: lane t reading byte p of ITS row touches bank
 // (33t + p/4) mod 32 = (t + p/4) mod 32, so the 32 lanes of a warp stepping through their rows in
 // lock-step never collide, for byte, word or any other same-offset access.
-constexpr int ROW_PITCH = 132;
+// (Kernels that stage tiles with bulk copies — cp.async.bulk needs 16-byte aligned destinations — are compiled with
+// RRX_ROW_PITCH 144: 128-bit loads of the same 16-byte chunk of 8 consecutive rows are conflict-free, same-offset
+// 32-bit accesses of all 32 lanes 4-way.  The candidate scan reads rows with 128-bit loads and bytes at scattered
+// offsets, so it does not care; the dense row scan does, and keeps 132.)
+#ifndef RRX_ROW_PITCH
+#define RRX_ROW_PITCH 132
+#endif
+constexpr int ROW_PITCH = RRX_ROW_PITCH;
+constexpr int ROW_GAP = ROW_PITCH - ROW_BYTES;
+// NW == 1 byte table: RRX_BT_COPIES private copies, lane l uses copy l % RRX_BT_COPIES (32: conflict-free)
+#ifndef RRX_BT_COPIES
+#define RRX_BT_COPIES 32
+#endif
+constexpr int BT_COPIES = RRX_BT_COPIES;
 
 // error bits reported by the kernel
 // ERR_START_LOST: a lazy start walk died without finding a start and without reaching the left edge (only
@@ -145,7 +158,7 @@ template <int K> RRX_DEV uint32_t lds_u8(const uint8_t* p) {
 }
 RRX_DEV uint32_t lds_tab1(const uint8_t* blane, uint32_t c) {
     uint32_t a, v;
-    asm("mad.lo.u32 %0, %1, 128, %2;" : "=r"(a) : "r"(c), "r"((uint32_t)__cvta_generic_to_shared(blane)));
+    asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a) : "r"(c), "r"((uint32_t)__cvta_generic_to_shared(blane)), "n"(BT_COPIES * 4));
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
@@ -157,7 +170,7 @@ RRX_DEV uint32_t or_and(uint32_t a, uint32_t b, uint32_t c) {
 }
 #else
 template <int K> RRX_DEV uint32_t lds_u8(const uint8_t* p) { return p[K]; }
-RRX_DEV uint32_t lds_tab1(const uint8_t* blane, uint32_t c) { return *reinterpret_cast<const uint32_t*>(blane + c * 128u); }
+RRX_DEV uint32_t lds_tab1(const uint8_t* blane, uint32_t c) { return *reinterpret_cast<const uint32_t*>(blane + c * (uint32_t)(BT_COPIES * 4)); }
 RRX_DEV uint32_t or_and(uint32_t a, uint32_t b, uint32_t c) { return (a | b) & c; }
 #endif
 
@@ -441,8 +454,8 @@ struct ScanParams {
 
 // ---- shared-memory state of one tile (= one warp) ----------------------------------------------------
 // size of TileState<NW, CW> (also evaluated on the host for run-time compiled kernels)
-RRX_HD constexpr size_t tile_state_bytes(int NW, int CW) {
-    return (size_t)TILE_ROWS * ROW_PITCH +
+RRX_HD constexpr size_t tile_state_bytes(int NW, int CW, int pitch = ROW_PITCH) {
+    return (size_t)TILE_ROWS * pitch +
            sizeof(uint32_t) * ((size_t)3 * CW * TILE_ROWS + 8 * TILE_ROWS + (8 + CW) + (NW <= 2 ? 64 : NW <= 4 ? 32 : 16) * (1 + NW));
 }
 // NW: words of a state set; CW: words of a CARRIED set (row exits, composites, entry) — CW == NW unless the kernel is
@@ -487,7 +500,7 @@ template <int NW, int CW = NW> struct TileState {
     }
     RRX_DEV int64_t lo() const { return (int64_t)(row0 << ROW_SHIFT); }
     // byte at tile-relative offset rel (0 .. TILE_BYTES)
-    RRX_DEV uint32_t rel_byte(uint32_t rel) const { return text[rel + 4u * (rel >> ROW_SHIFT)]; }
+    RRX_DEV uint32_t rel_byte(uint32_t rel) const { return text[rel + (uint32_t)ROW_GAP * (rel >> ROW_SHIFT)]; }
     // where the q-th 16-byte chunk of the tile goes (4-byte aligned)
     RRX_DEV uint32_t* chunk_ptr(int q) const {
         return reinterpret_cast<uint32_t*>(text + (q >> 3) * ROW_PITCH + ((q & 7) << 4));
@@ -717,7 +730,7 @@ RRX_DEV WalkResult back_walk(const ScanParams& sp, const ProgView& pv, const F& 
                     const uint32_t B0 = b0 * 0x01010101u, B1 = b1 * 0x01010101u;
                     int wi = (rel >> 2) - 1;                 // last whole word before byte rel
                     for (; wi >= 0; wi--) {
-                        const uint32_t w = t32[wi + (wi >> 5)];          // 33 words per staged row
+                        const uint32_t w = t32[wi + (ROW_GAP / 4) * (wi >> 5)];          // ROW_PITCH / 4 words per staged row
                         const uint32_t x0 = w ^ B0, x1 = w ^ B1;
                         const uint32_t z = ((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | w;
                         if (z & 0x80808080u) break;
@@ -879,12 +892,15 @@ struct SparseTail {
         const uint32_t back = nruns - g;
         return (g == 0u || back > 3u) ? 0u : (uint32_t)(rt >> (16u * back)) & 0xffffu;
     }
-    // every match of the row is in the queue and has a known start
+    // every match of the row is in the queue and has a known start: no zero tag among the nacc entries, and the
+    // oldest entry's run (tags never decrease along the queue) is still among the four on record
     RRX_DEV bool simple() const {
         if (drained) return false;
-        for (uint32_t i = 0; i < nacc; i++)
-            if (start_of((ks >> (8u * i)) & 0xffu) == 0u) return false;
-        return true;
+        if (nacc == 0u) return true;
+        const uint32_t m = 0xffffffffu >> (32u - 8u * nacc);
+        const uint32_t v = ks | ~m;                              // bytes beyond the queue count as tagged
+        if ((((v - 0x01010101u) & ~v) & 0x80808080u) != 0u) return false;   // a zero byte
+        return nruns - ((ks >> (8u * (nacc - 1u))) & 0xffu) <= 3u;
     }
 };
 
@@ -933,16 +949,28 @@ RRX_DEV void sparse_drain(TileState<NW, CW>& ts, int t, const SparseTail& q) {
 //   >= 0x80).  sum_b[t] receives the dominated states alive after the row's last byte that stem from the row's
 //   own candidates; carried states are phase B's business as before.
 // (1) candidate mask of row t: bit p of cm[q] <=> byte 32q+p == cand
+// word j of a staged row (rows that are 16-byte aligned are read with 128-bit loads)
+RRX_DEV void row_words8(const uint32_t* rw, int q, uint32_t* w8) {
+#if RRX_ROW_PITCH % 16 == 0 && defined(__CUDA_ARCH__) && !defined(RRX_HOST_EMU)
+    const uint4 a = *reinterpret_cast<const uint4*>(rw + q * 8), b = *reinterpret_cast<const uint4*>(rw + q * 8 + 4);
+    w8[0] = a.x; w8[1] = a.y; w8[2] = a.z; w8[3] = a.w; w8[4] = b.x; w8[5] = b.y; w8[6] = b.z; w8[7] = b.w;
+#else
+#pragma unroll
+    for (int j = 0; j < 8; j++) w8[j] = rw[q * 8 + j];
+#endif
+}
+
 template <int NW, int CW>
 RRX_DEV void phase_a_mask(const TileState<NW, CW>& ts, int t, uint32_t cand, uint32_t* cm) {
     const uint32_t C4 = cand * 0x01010101u;
     const uint32_t* rw = reinterpret_cast<const uint32_t*>(ts.text + t * ROW_PITCH);
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        uint32_t acc = 0;
+        uint32_t acc = 0, w8[8];
+        row_words8(rw, q, w8);
 #pragma unroll
         for (int j = 7; j >= 0; j--) {
-            const uint32_t x = rw[q * 8 + j] ^ C4;
+            const uint32_t x = w8[j] ^ C4;
             const uint32_t y = (x | 0x80808080u) - 0x01010101u;     // no borrow between bytes
             const uint32_t f = ~(y | x) & 0x80808080u;              // 0x80 where the byte equals cand
             acc = fshl(f * 0x00204081u, acc, 4);                    // the 4 flags land in the top nibble
@@ -959,10 +987,11 @@ RRX_DEV void phase_z_mask(TileState<NW, CW>& ts, int t, uint32_t rs_bytes, uint3
     const uint32_t* rw = reinterpret_cast<const uint32_t*>(ts.text + t * ROW_PITCH);
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        uint32_t acc = 0;
+        uint32_t acc = 0, w8[8];
+        row_words8(rw, q, w8);
 #pragma unroll
         for (int j = 7; j >= 0; j--) {
-            const uint32_t wv = rw[q * 8 + j];
+            const uint32_t wv = w8[j];
             const uint32_t x0 = wv ^ B0;
             uint32_t f = ~(((x0 | 0x80808080u) - 0x01010101u) | x0);      // bit 7 of a byte set <=> the byte equals b0
             if (rs_n > 1u) {

@@ -416,7 +416,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         // closed the tile aggregate is the last row's exit and is published at once.  If any row of the
         // tile needs the dense scan the whole tile takes it (the lanes run in lock-step anyway), and
         // the next few tiles of this warp do not try again.
-        bool dense = true, published = false;
+        bool dense = true, published = false, agg_done = false;
         Comp<CW> agg, acc, inc;
         SparseTail tail;
         tail.kq = tail.ks = tail.nacc = tail.nruns = 0;
@@ -445,18 +445,22 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             // fallback.  The rows' exits (dominated states only) are known once the candidates have been followed;
             // what a row does to carried states is decided by phase_d_kind.  All rows closed: the tile's aggregate
             // is the last row's exit.
+            // What a row does to CARRIED states (phase_d_kind) matters for the last row (the tile's aggregate: a closed last
+            // row makes the tile closed, whatever precedes it), for row 0 (it may receive the tile's entry) and for rows that
+            // receive a state from the row before — known once the candidates have been followed, and rare.
             // Usually the last row's exit is provably empty before any candidate has been followed (no candidate byte
             // behind the point where nothing carried survives): the tile then publishes FIRST, and its successors find
             // its aggregate ready when they look back.
             uint32_t cm[4];
-            int qfree;
+            int qfree = 0;
             phase_a_mask<NW>(ts, lane, fw.sp_cand(pv), cm);
-            const uint32_t kind = phase_d_kind<NW>(sp, pv, fw, ts, lane, &qfree);
+            const bool edge = lane == 0 || lane == TILE_ROWS - 1;
+            uint32_t kind = K_CLOSED;
+            if (edge) kind = phase_d_kind<NW>(sp, pv, fw, ts, lane, &qfree);
             const uint32_t behind = qfree >= ROW_BYTES ? 0u : ((qfree >> 5) == 0 ? (cm[0] >> (qfree & 31)) | cm[1] | cm[2] | cm[3]
                                                              : (qfree >> 5) == 1 ? (cm[1] >> (qfree & 31)) | cm[2] | cm[3]
                                                              : (qfree >> 5) == 2 ? (cm[2] >> (qfree & 31)) | cm[3] : (cm[3] >> (qfree & 31)));
-            const bool all_closed = __all_sync(FULL, kind == K_CLOSED) != 0;
-            const bool early = all_closed && __shfl_sync(FULL, behind, TILE_ROWS - 1) == 0u;
+            const bool early = __all_sync(FULL, kind == K_CLOSED) != 0 && __shfl_sync(FULL, behind, TILE_ROWS - 1) == 0u;
             uint32_t arrived = 0;
             dense = false;
             if (early) {
@@ -465,19 +469,32 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
                 for (int w = 0; w < CW; w++) bl[w] = 0u;
                 comp_closed(agg, bl, 0);
                 arrived = lookback_publish_issue<CW>(sp, tile, agg, lane);
-                published = true;
             }
             phase_a_cand<NW, F, true>(sp, pv, fw, ts, lane, cm, tail);
             __syncwarp();
-            if (early) {
-                lookback_publish_fold<CW>(sp, tile, arrived, lane);       // the arrival count has long come back
-            } else if (all_closed) {
-                uint32_t bl[CW];
+            uint32_t carried_in = 0;
+            if (!edge) {
 #pragma unroll
-                for (int w = 0; w < CW; w++) bl[w] = ts.sum_b[w * TILE_ROWS + (TILE_ROWS - 1)];
-                comp_closed(agg, bl, 0);
-                lookback_publish<CW>(sp, tile, agg, lane);
+                for (int w = 0; w < CW; w++) carried_in |= ts.sum_b[w * TILE_ROWS + lane - 1];
+            }
+            if (__any_sync(FULL, carried_in != 0u) && carried_in != 0u) kind = phase_d_kind<NW>(sp, pv, fw, ts, lane, &qfree);
+            const bool rows_ok = __all_sync(FULL, kind == K_CLOSED) != 0;
+            if (early) lookback_publish_fold<CW>(sp, tile, arrived, lane);       // the arrival count has long come back
+            if (rows_ok) {
+                if (!early) {
+                    uint32_t bl[CW];
+#pragma unroll
+                    for (int w = 0; w < CW; w++) bl[w] = ts.sum_b[w * TILE_ROWS + (TILE_ROWS - 1)];
+                    comp_closed(agg, bl, 0);
+                    lookback_publish<CW>(sp, tile, agg, lane);
+                }
                 published = true;
+            } else {
+                // a row that matters is open, or the tile is partial: the general composition (phase S) wants every row's
+                // kind; an aggregate published early stands (it is what the composition will find)
+                if (!edge && carried_in == 0u) phase_d_kind<NW>(sp, pv, fw, ts, lane, &qfree);
+                agg_done = early;
+                __syncwarp();
             }
         } else if (sp.sparse) {
             if (dense_left == 0) {
@@ -530,7 +547,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             __syncwarp();
             if (lane == 0) { phase_s1<NW>(sp, pv, fw, ts, any_open, L); agg = L.run; } else { comp_ident(agg); }
             bcast_comp(agg, 0);
-            lookback_publish<CW>(sp, tile, agg, lane);
+            if (!agg_done) lookback_publish<CW>(sp, tile, agg, lane);
         }
         RRX_T(2)
         lookback_wait<CW>(sp, tile, lane, acc);

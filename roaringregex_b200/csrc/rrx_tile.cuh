@@ -930,7 +930,13 @@ RRX_DEV void sparse_drain(TileState<NW, CW>& ts, int t, const SparseTail& q) {
         const uint32_t e1 = (q.kq >> (8 * i)) & 0xffu;
         if (e1 && (uint32_t)i < q.nacc) {
             const uint32_t pos = e1 - 1, s16 = q.start_of((q.ks >> (8 * i)) & 0xffu);
-            ts.hits[(pos >> 5) * ROWS + t] |= 1u << (pos & 31);
+            if (pos >= (uint32_t)ROW_BYTES) {
+                // an end found while overrunning into the next row: it belongs to that row's hit mask (another lane's
+                // words: atomic); its start is left to the backward walk
+                atomicOr(ts.hits + ((pos - ROW_BYTES) >> 5) * ROWS + t + 1, 1u << (pos & 31));
+                continue;
+            }
+            atomicOr(ts.hits + (pos >> 5) * ROWS + t, 1u << (pos & 31));
             if (s16) {
                 const uint32_t rec = (pos << 16) | s16;
                 if (ts.kst[2 * t] == KST_NONE) ts.kst[2 * t] = rec;
@@ -1202,6 +1208,55 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
     }
     if (bail) return false;
     if (DONLY) {
+        // ---- overrun: a run that is alive at the end of its row is followed INTO THE NEXT ROW by the lane that owns it
+        // (rows t+1's staged bytes), as long as it meets no candidate byte there: its matches then still precede every
+        // match of lane t+1 (whose runs start at ITS candidates), so the lanes' queues stay in text order, row t hands
+        // no state to row t+1, and the tile keeps its fast tail.  If the run meets a candidate byte, outlives the queue or
+        // the next row, the overrun is undone and the run's state at the row end becomes the row's exit as before.
+        // (Not for the tile's last row: its exit travels through the look-back.)
+        const uint32_t over = (t < ROWS - 1 && rowend == (uint32_t)ROW_BYTES && p >= rowend && live != 0u && q.nacc < 4u) ? 1u : 0u;
+        if (RRX_WARP_ANY(over != 0u)) {
+            uint32_t Hx[NW];
+#pragma unroll
+            for (int w = 0; w < NW; w++) Hx[w] = H[w];
+            const uint32_t kq0 = q.kq, ks0 = q.ks, na0 = q.nacc;
+            const SmemBytes rb2(rp + ROW_PITCH);
+            uint32_t p2 = 0, ovf = 0, go = over ? live : 0u;
+            while (RRX_WARP_ANY(go != 0u)) {
+                const uint32_t c = rb2.at(p2);
+                load_B<NW>(pv, c, Bc);
+                fw.follow(pv, H, f);
+                const bool on = go != 0u;
+                const bool step = on && c != cand;
+                ovf |= (on && c == cand) ? 1u : 0u;                 // another cut crossing: not this lane's business
+                uint32_t a = 0, lv = 0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) {
+                    const uint32_t hn = f[w] & DA[w] & Bc[w];
+                    lv |= hn;
+                    a |= hn & fw.accept(pv, w);
+                    H[w] = step ? hn : H[w];
+                }
+                p2 += step ? 1u : 0u;
+                const bool take = step && a != 0u;
+                q.kq = take ? ((q.kq << 8) | (p2 + (uint32_t)ROW_BYTES)) : q.kq;
+                q.ks = take ? ((q.ks << 8) | rs1) : q.ks;
+                q.nacc += take ? 1u : 0u;
+                live = step ? lv : live;
+                ovf |= (step && lv != 0u && (q.nacc >= 4u || p2 >= (uint32_t)ROW_BYTES - 1u)) ? 1u : 0u;   // outlives the queue / the next row
+                go = (step && !ovf) ? live : 0u;
+            }
+            if (over) {
+                if (ovf) {                      // undo: the classic hand-over through the row's exit
+                    q.kq = kq0; q.ks = ks0; q.nacc = na0;
+#pragma unroll
+                    for (int w = 0; w < NW; w++) H[w] = Hx[w];
+                } else {                        // the run died in the next row: nothing is handed over
+#pragma unroll
+                    for (int w = 0; w < NW; w++) H[w] = 0u;
+                }
+            }
+        }
         // exit of the row: the run alive after the last byte (a run that ended earlier left H empty)
 #pragma unroll
         for (int w = 0; w < NW; w++) if (w < CW) ts.sum_b[w * ROWS + t] = (p >= rowend && rowend != 0u) ? H[w] : 0u;

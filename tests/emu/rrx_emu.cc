@@ -118,23 +118,48 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
             tile_stop[tile] = v;
         }
         if (h.donly && g_sparse_mode) {
-            // thread-owned candidate scan, as the kernel: every row, no dense fallback
+            // thread-owned candidate scan, as the kernel: every row, no dense fallback.  Row kinds lazily: the two edge rows
+            // first, rows that receive a carried state after the candidates have been followed, the rest only if the
+            // general composition is needed.
+            uint32_t kinds[ROWS];
+            bool have_kind[ROWS];
             for (int t = 0; t < ROWS; t++) {
                 ProgView pv = view(t);
                 PROG fw;
                 fw.init(pv);
                 uint32_t cm[4];
-                int qfree;
+                int qfree = 0;
                 phase_a_mask<NW>(ts, t, fw.sp_cand(pv), cm);
-                const uint32_t kind = phase_d_kind<NW>(sp, pv, fw, ts, t, &qfree);
+                have_kind[t] = t == 0 || t == ROWS - 1;
+                kinds[t] = have_kind[t] ? phase_d_kind<NW>(sp, pv, fw, ts, t, &qfree) : (uint32_t)K_CLOSED;
                 phase_a_cand<NW, PROG, true>(sp, pv, fw, ts, t, cm, tails[t]);
-                if (kind != K_CLOSED) all_closed_d = false;
                 // the kernel's early-publish rule: no candidate at or behind qfree => the row's exit must be empty
                 bool behind = false;
                 for (int p = qfree; p < ROW_BYTES; p++) behind = behind || ((cm[p >> 5] >> (p & 31)) & 1u);
-                if (kind == K_CLOSED && !behind)
+                if (have_kind[t] && kinds[t] == K_CLOSED && !behind)
                     for (int w = 0; w < CW; w++) if (ts.sum_b[w * ROWS + t]) *err |= 0x40u;
             }
+            for (int t = 1; t < ROWS - 1; t++) {
+                uint32_t carried_in = 0;
+                for (int w = 0; w < CW; w++) carried_in |= ts.sum_b[w * ROWS + t - 1];
+                if (carried_in) {
+                    ProgView pv = view(t);
+                    PROG fw;
+                    fw.init(pv);
+                    int qf;
+                    kinds[t] = phase_d_kind<NW>(sp, pv, fw, ts, t, &qf);
+                    have_kind[t] = true;
+                }
+            }
+            for (int t = 0; t < ROWS; t++) if (kinds[t] != K_CLOSED) all_closed_d = false;
+            if (!all_closed_d)
+                for (int t = 0; t < ROWS; t++) if (!have_kind[t]) {
+                    ProgView pv = view(t);
+                    PROG fw;
+                    fw.init(pv);
+                    int qf;
+                    phase_d_kind<NW>(sp, pv, fw, ts, t, &qf);
+                }
             published = all_closed_d;
             dense = false;
             g_sparse_rows += ROWS;

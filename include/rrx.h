@@ -130,6 +130,10 @@ enum { RRX_SCANNER_DEFAULT = 0, RRX_SCANNER_JIT = 1, RRX_SCANNER_NO_JIT = 2 };
 int rrx_scanner_create_ex(const rrx_program* p, uint64_t max_len, uint64_t match_capacity, uint32_t flags, rrx_scanner** out);
 /* 1 if the scanner runs a run-time specialised kernel, 0 if a pre-compiled one. */
 int rrx_scanner_is_jit(const rrx_scanner* s);
+/* Specialised kernel the NEXT scan will use: 0 lean, 1 straddle (matches straddling 128-byte rows are followed by
+ * their lane).  A scanner starts lean and switches by what each scan saw (rrx_scanner_result); RRX_JIT_VARIANT=0/1
+ * pins it. */
+int rrx_scanner_kernel_variant(const rrx_scanner* s);
 /* 1 if the last scan ran on the fallback (row-bounded) scanner of a thread-owned program. */
 int rrx_scanner_used_fallback(const rrx_scanner* s);
 /* CUDA source of the specialised follow functions for this program (for inspection); returns the

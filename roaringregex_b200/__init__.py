@@ -94,6 +94,7 @@ def lib() -> C.CDLL:
         "rrx_scanner_create_ex": (C.c_int, [vp, u64, u64, u32, C.POINTER(vp)]),
         "rrx_scanner_is_jit": (C.c_int, [vp]),
         "rrx_scanner_used_fallback": (C.c_int, [vp]),
+        "rrx_scanner_kernel_variant": (C.c_int, [vp]),
         "rrx_program_jit_source": (u64, [vp, vp, u64]),
         "rrx_program_jit_compile": (C.c_int, [vp, C.c_char_p]),
         "rrx_scanner_free": (None, [vp]),
@@ -352,6 +353,11 @@ class Scanner:
     @property
     def is_jit(self) -> bool:
         return bool(lib().rrx_scanner_is_jit(self._h))
+
+    @property
+    def kernel_variant(self) -> int:
+        """Specialised kernel the next scan uses: 0 lean, 1 straddle (rrx_scanner_kernel_variant)."""
+        return int(lib().rrx_scanner_kernel_variant(self._h))
 
     @property
     def used_fallback(self) -> bool:

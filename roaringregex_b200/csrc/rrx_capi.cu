@@ -126,6 +126,12 @@ struct rrx_scanner {
     struct { const uint8_t* text; uint64_t len, base, left_ctx; bool has_entry; uint32_t entry[RRX_NW_MAX]; void* stream; } last = {};
     bool owns_out = true;
     JitKernel* jit = nullptr;        // run-time specialised kernel (owned by the process-wide cache)
+    // Thread-owned programs have two specialised kernels (rrx_jit.h): lean and straddle.  A scanner starts lean; every
+    // rrx_scanner_result looks at how many tiles handed states from row to row (lean) / had a lane follow a run into the
+    // next row (straddle) and picks the kernel of the NEXT scan: above 1/8 of the tiles -> straddle, below 1/64 -> lean.
+    JitKernel* jit_v[2] = {nullptr, nullptr};
+    int variant = 0;
+    uint32_t last_tiles = 0;
     // pinned host mirror of [ticket, err, total0, total1] followed by the shard composite (1+3*NW words)
     uint64_t* h_ctr = nullptr;
     bool h_shard_valid = false;     // the composite in h_ctr belongs to the last scan
@@ -250,6 +256,7 @@ int rrx_scanner_create(const rrx_program* p, uint64_t max_len, uint64_t capacity
 }
 int rrx_scanner_is_jit(const rrx_scanner* s) { return s && s->jit ? 1 : 0; }
 int rrx_scanner_used_fallback(const rrx_scanner* s) { return s && s->use_alt ? 1 : 0; }
+int rrx_scanner_kernel_variant(const rrx_scanner* s) { return s ? s->variant : 0; }
 uint64_t rrx_program_jit_source(const rrx_program* p, char* buf, uint64_t cap) {
     const std::string src = jit_applicable(p->prog) ? jit_policy_source(p->prog) : std::string();
     if (buf && cap) { const size_t n = src.size() + 1 < cap ? src.size() + 1 : cap; std::memcpy(buf, src.c_str(), n); buf[n - 1] = 0; }
@@ -310,7 +317,14 @@ int rrx_scanner_create_ex(const rrx_program* p, uint64_t max_len, uint64_t capac
         if (const char* e = getenv("RRX_JIT")) want = e[0] == '1' && !(flags & RRX_SCANNER_NO_JIT);
         if (want && jit_applicable(p->prog)) {
             std::string err;
-            s->jit = jit_get(p->prog, &err);
+            s->jit = jit_get(p->prog, &err, 0);
+            s->jit_v[0] = s->jit;
+            if (const char* v = getenv("RRX_JIT_VARIANT")) {          // force a kernel variant (A/B measurements)
+                if (v[0] == '1' && s->jit && p->prog.hdr().donly) {
+                    JitKernel* k1 = jit_get(p->prog, &err, 1);
+                    if (k1) { s->jit = s->jit_v[1] = k1; s->variant = 1; }
+                }
+            }
             if (!s->jit) {
                 if (flags & RRX_SCANNER_JIT) return set_err(RRX_ERR_CUDA, "run-time specialisation failed: " + err);
                 // not fatal (the pre-compiled kernel gives the same results, slower), but never silent: one line on
@@ -421,6 +435,8 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     sp.f_i1 = reinterpret_cast<volatile uint32_t*>(c + off[3]);
     sp.st_arrive = reinterpret_cast<uint32_t*>(c + off[4]);
     // (only kernels that WRITE the stop-byte table may wait on it: thread-owned programs with a reverse skip state)
+    sp.straddle_tiles = reinterpret_cast<uint32_t*>(c);          // word 0 of the control block
+    s->last_tiles = sp.num_tiles;
     sp.tile_stop = (h.donly && h.rskip_n) ? reinterpret_cast<volatile uint32_t*>(c + off[5]) : nullptr;
     sp.tile_seg = s->d_tile_seg;
     sp.tile_cnt = s->d_tile_cnt;
@@ -477,6 +493,18 @@ int rrx_scanner_result(rrx_scanner* s, rrx_scan_result* out, void* stream) {
     RRX_CUDA(cudaStreamSynchronize(st));
     s->h_shard_valid = true;
     const uint32_t* w32 = reinterpret_cast<const uint32_t*>(s->h_ctr);
+    if (s->jit && s->p->prog.hdr().donly && s->last_tiles >= 64 && !getenv("RRX_JIT_VARIANT")) {
+        // pick the kernel of the next scan by what this one saw (see rrx_scanner::jit_v)
+        const uint64_t straddle = w32[0], tiles = s->last_tiles;
+        const int want = (s->variant == 0 && straddle * 8 > tiles) ? 1 : (s->variant == 1 && straddle * 64 < tiles) ? 0 : s->variant;
+        if (want != s->variant) {
+            if (!s->jit_v[want]) {
+                std::string err;
+                s->jit_v[want] = jit_get(s->p->prog, &err, want);
+            }
+            if (s->jit_v[want]) { s->jit = s->jit_v[want]; s->variant = want; }
+        }
+    }
     out->error_bits = w32[1] & ~(uint32_t)ERR_VERIFY_EDGE;
     out->soft_bits = w32[1] & (uint32_t)ERR_VERIFY_EDGE;
     out->reserved = 0;

@@ -419,7 +419,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         bool dense = true, published = false, agg_done = false;
         Comp<CW> agg, acc, inc;
         SparseTail tail;
-        tail.kq = tail.ks = tail.nacc = tail.nruns = 0;
+        tail.kq = tail.ks = tail.nacc = tail.nruns = tail.over = 0;
         tail.rt = 0ull;
         tail.drained = 1;
         if (fw.donly(pv) && fw.rs_n(pv) != 0u) {
@@ -584,6 +584,15 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             for (int w = 0; w < CW; w++) carried |= lane == 0 ? ts.misc[TS::M_ENTRY + w] : ts.sum_b[w * TILE_ROWS + lane - 1];
             // (only tiles that published early still have the rows' exits in sum_b: phase S1 rewrites them otherwise)
             fast = published && __all_sync(FULL, tail.simple() && carried == 0) != 0;
+            if (fw.donly(pv)) {
+                // what the scanner picks its next kernel by (ScanParams::straddle_tiles)
+#ifdef RRX_NO_OVERRUN
+                const bool straddle = __any_sync(FULL, lane != 0 && carried != 0u) != 0;
+#else
+                const bool straddle = __any_sync(FULL, tail.over != 0u) != 0;
+#endif
+                if (straddle && lane == 0 && sp.straddle_tiles) atom_add_u32(sp.straddle_tiles, 1u);
+            }
             if (!fast) sparse_drain<NW>(ts, lane, tail);
             __syncwarp();
         }

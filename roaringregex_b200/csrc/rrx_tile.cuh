@@ -24,11 +24,21 @@
 #if defined(__CUDACC__) && !defined(RRX_HOST_EMU)
 #define RRX_DEV __device__ __forceinline__
 #define RRX_HD __host__ __device__ __forceinline__
+// Cold paths (carried-state replay, start walks, open-row analysis, ...).  The per-tile code of 32 de-phased warps has
+// to fit the instruction cache: a 5 % larger kernel took sm__icc_request_hit_rate from 96 % to 84 % and cost config 2
+// 12 % (profiles/README.md), so cold code is kept to ONE inlined copy per function.  Calling it out of line
+// (RRX_NOINLINE_COLD, A/B) is worse still: the ABI forces the match queue and the tile state into local memory.
+#ifdef RRX_NOINLINE_COLD
+#define RRX_COLD __device__ __noinline__
+#else
+#define RRX_COLD __device__ __forceinline__
+#endif
 // warp-uniform loop control inside per-lane phase functions (all 32 lanes call them convergently)
 #define RRX_WARP_ANY(x) (__any_sync(0xffffffffu, (x)) != 0)
 #else
 #define RRX_DEV inline
 #define RRX_HD inline
+#define RRX_COLD inline
 #define RRX_WARP_ANY(x) (x)          // the emulator steps one lane at a time
 #endif
 
@@ -444,6 +454,9 @@ struct ScanParams {
     // 1 the tile holds none of the skip state's stop bytes, else 2 + tile-relative offset of its LAST one.  A backward
     // walk in the skip state that leaves its tile hops over whole tiles with it (see back_walk).  Zeroed per scan.
     volatile uint32_t* tile_stop;
+    // thread-owned scan: tiles that left the fast tail because a row handed a state to the next one (lean kernel) /
+    // tiles in which a lane followed a run into the next row (straddle kernel) — what the scanner picks its next kernel by
+    uint32_t* straddle_tiles;
     unsigned long long ovf_base;
     uint32_t* err;
     uint32_t* shard_comp;       // [1+3*NW] composite of the whole shard (relative to an unknown entry)
@@ -687,7 +700,7 @@ struct WalkResult {
     bool over;          // the step budget ran out (verification walks only)
 };
 template <int NW, class F, int CW>
-RRX_DEV WalkResult back_walk(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW, CW>& ts, uint32_t* R,
+RRX_COLD WalkResult back_walk(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW, CW>& ts, uint32_t* R,
                              int64_t e1, int budget) {
     uint32_t Bc[NW], x[NW];
     const int64_t tile_lo = ts.lo(), left_edge = -(int64_t)sp.left_ctx;
@@ -886,6 +899,7 @@ RRX_DEV bool phase_a_exit(const ScanParams& sp, const ProgView& pv, const F& fw,
 // lazy starts of the last four tagged runs (rt: 16 bits each, most recent lowest: start - row start + KS_BIAS).
 struct SparseTail {
     uint32_t kq, ks, nacc, drained, nruns;
+    uint32_t over;      // the lane followed a run into the next row
     unsigned long long rt;
     // lazy start (biased, see KS_BIAS) of the run with tag g, 0 if it is not on record any more
     RRX_DEV uint32_t start_of(uint32_t g) const {
@@ -923,7 +937,7 @@ RRX_DEV void phase_tail_fast(const ScanParams& sp, const TileState<NW, CW>& ts, 
 
 // Unpack the match-end queue of phase_a_cand into the row's hit mask (and its first two known starts).
 template <int NW, int CW>
-RRX_DEV void sparse_drain(TileState<NW, CW>& ts, int t, const SparseTail& q) {
+RRX_COLD void sparse_drain(TileState<NW, CW>& ts, int t, const SparseTail& q) {
     constexpr int ROWS = TILE_ROWS;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -1037,7 +1051,7 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
     uint32_t p = 0;
     uint32_t rs1 = 0;                   // tag of the current run if the lazy start of its matches is known, else 0
     SparseTail q;
-    q.kq = q.ks = q.nacc = q.drained = q.nruns = 0;
+    q.kq = q.ks = q.nacc = q.drained = q.nruns = q.over = 0;
     q.rt = 0ull;
     uint32_t bail = (!DONLY && ncand > SPARSE_MAX_CAND) ? 1u : 0u;
     uint32_t live = 0;                  // OR of the words of H
@@ -1214,7 +1228,11 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
         // no state to row t+1, and the tile keeps its fast tail.  If the run meets a candidate byte, outlives the queue or
         // the next row, the overrun is undone and the run's state at the row end becomes the row's exit as before.
         // (Not for the tile's last row: its exit travels through the look-back.)
+#ifdef RRX_NO_OVERRUN
+        const uint32_t over = 0u;
+#else
         const uint32_t over = (t < ROWS - 1 && rowend == (uint32_t)ROW_BYTES && p >= rowend && live != 0u && q.nacc < 4u) ? 1u : 0u;
+#endif
         if (RRX_WARP_ANY(over != 0u)) {
             uint32_t Hx[NW];
 #pragma unroll
@@ -1246,6 +1264,7 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
                 ovf |= (step && lv != 0u && (q.nacc >= 4u || p2 >= (uint32_t)ROW_BYTES - 1u)) ? 1u : 0u;   // outlives the queue / the next row
                 go = (step && !ovf) ? live : 0u;
             }
+            q.over = over;
             if (over) {
                 if (ovf) {                      // undo: the classic hand-over through the row's exit
                     q.kq = kq0; q.ks = ks0; q.nacc = na0;
@@ -1276,7 +1295,7 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
 // *qfree: a closed row's exit (sum_b, known only after the candidates have been followed) is certainly empty if the row
 // has no candidate byte at or after this position — what lets a tile publish its aggregate before it scans.
 template <int NW, class F, int CW>
-RRX_DEV uint32_t phase_d_kind(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, CW>& ts, int t, int* qfree) {
+RRX_COLD uint32_t phase_d_kind(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, CW>& ts, int t, int* qfree) {
     constexpr int ROWS = TILE_ROWS;
     const int nb = row_nbytes(sp, ts.row0, t);
     *qfree = 0;
@@ -1448,7 +1467,7 @@ template <int NW, int CW> RRX_DEV void widen(const uint32_t* c, uint32_t* full) 
 }
 
 template <int NW, class F, int CW>
-RRX_DEV void phase_s1(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, CW>& ts, bool any_open,
+RRX_COLD void phase_s1(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, CW>& ts, bool any_open,
                       SLocal<CW>& L) {
     constexpr int ROWS = TILE_ROWS;
     Comp<CW> rowc, nxt;
@@ -1502,7 +1521,7 @@ RRX_DEV void phase_s1(const ScanParams& sp, const ProgView& pv, const F& fw, Til
 
 // `acc` = composite of the whole shard before this tile.  Returns the tile's inclusive composite.
 template <int NW, class F, int CW>
-RRX_DEV void phase_s2(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, CW>& ts, const SLocal<CW>& L,
+RRX_COLD void phase_s2(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, CW>& ts, const SLocal<CW>& L,
                       const Comp<CW>& acc, Comp<CW>& inc) {
     using TS = TileState<NW, CW>;
     uint32_t E[CW];
@@ -1539,7 +1558,7 @@ RRX_DEV void phase_s2(const ScanParams& sp, const ProgView& pv, const F& fw, Til
 // ===== phase B: replay each row's prefix from its exact entry set (no injection) ====================
 // Returns the number of matches of the row.
 template <int NW, class F, int CW>
-RRX_DEV uint32_t phase_b(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, CW>& ts, int t,
+RRX_COLD uint32_t phase_b(const ScanParams& sp, const ProgView& pv, const F& fw, TileState<NW, CW>& ts, int t,
                          bool any_open) {
     constexpr int ROWS = TILE_ROWS;
     using TS = TileState<NW, CW>;
@@ -1597,7 +1616,7 @@ RRX_DEV uint32_t phase_b(const ScanParams& sp, const ProgView& pv, const F& fw, 
 // Backward walk from the accepting positions, starting with the byte at shard-local offset e-1; stops at the
 // first (= right-most) start that works: lazy.
 template <int NW, class F, int CW>
-RRX_DEV void resolve_and_write(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW, CW>& ts,
+RRX_COLD void resolve_and_write(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW, CW>& ts,
                                int64_t e, unsigned long long slot, uint32_t rank_in_tile) {
     uint32_t R[NW];
 #pragma unroll
@@ -1643,7 +1662,7 @@ RRX_DEV bool write_known(const ScanParams& sp, const TileState<NW, CW>& ts, uint
 
 // C1 (per lane): append the row's match ends to the tile's hit list (tile-relative end-1).
 // cnt[t] must hold the row's exclusive offset.  Only when the tile total fits the list.
-template <int NW, int CW> RRX_DEV void phase_c1_list(TileState<NW, CW>& ts, int t, uint32_t offset, const uint32_t* hit) {
+template <int NW, int CW> RRX_COLD void phase_c1_list(TileState<NW, CW>& ts, int t, uint32_t offset, const uint32_t* hit) {
     uint32_t k = offset;
     for (int q = 0; q < 4; q++) {
         uint32_t v = hit[q];
@@ -1656,7 +1675,7 @@ template <int NW, int CW> RRX_DEV void phase_c1_list(TileState<NW, CW>& ts, int 
 }
 // C2 (per lane): balanced — lane handles list entries lane, lane+32, ...
 template <int NW, class F, int CW>
-RRX_DEV void phase_c2_balanced(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW, CW>& ts, int lane,
+RRX_COLD void phase_c2_balanced(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW, CW>& ts, int lane,
                                uint32_t total, unsigned long long base) {
     for (uint32_t i = (uint32_t)lane; i < total; i += TILE_ROWS) {
         const uint32_t rel = ts.list[i];
@@ -1666,7 +1685,7 @@ RRX_DEV void phase_c2_balanced(const ScanParams& sp, const ProgView& pv, const F
 }
 // C2 fallback (per lane): every row resolves its own matches (tiles with more hits than the list holds).
 template <int NW, class F, int CW>
-RRX_DEV void phase_c2_rows(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW, CW>& ts, int t,
+RRX_COLD void phase_c2_rows(const ScanParams& sp, const ProgView& pv, const F& fw, const TileState<NW, CW>& ts, int t,
                            uint32_t offset, const uint32_t* hit, unsigned long long base) {
     unsigned long long slot = base + offset;
     const int64_t row_lo = ts.lo() + ((int64_t)t << ROW_SHIFT);

@@ -127,7 +127,7 @@ struct rrx_scanner {
     bool owns_out = true;
     JitKernel* jit = nullptr;        // run-time specialised kernel (owned by the process-wide cache)
     // Thread-owned programs have two specialised kernels (rrx_jit.h): lean and straddle.  A scanner starts lean; every
-    // rrx_scanner_result looks at how many tiles handed states from row to row (lean) / had a lane follow a run into the
+    // rrx_scanner_result looks at how many tiles left the fast tail (lean) / how many rows had their run followed into the
     // next row (straddle) and picks the kernel of the NEXT scan: above 1/8 of the tiles -> straddle, below 1/64 -> lean.
     JitKernel* jit_v[2] = {nullptr, nullptr};
     int variant = 0;

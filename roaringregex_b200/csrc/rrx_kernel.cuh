@@ -167,7 +167,7 @@ __device__ __forceinline__ void lookback_publish_fold(const ScanParams& sp, uint
     const uint32_t nblk = rest < 32u ? rest : 32u;
     Comp<NW> mine, x, nxt;
     old = __shfl_sync(FULL, old, 0);
-    if (old == nblk - 1) {                                  // fold the block aggregate, in tile order
+    if (RRX_UNLIKELY(old == nblk - 1)) {                    // fold the block aggregate, in tile order (1 tile in 32)
         comp_ident(mine);
         if ((uint32_t)lane < nblk) wait_comp<NW>(sp.st_a0, sp.f_a0, (size_t)(b << 5) + lane, mine);
         Comp<NW> fold;
@@ -197,7 +197,7 @@ __device__ __forceinline__ void lookback_wait(const ScanParams& sp, uint32_t til
     comp_ident(acc);
     if (tile == 0) return;
     wait_comp<NW>(sp.st_a0, sp.f_a0, (size_t)tile - 1, x);
-    if ((x.kind & K_TYPE) == K_CLOSED) { acc = x; return; }
+    if (!RRX_UNLIKELY((x.kind & K_TYPE) != K_CLOSED)) { acc = x; return; }
     // (a) the tiles before this one inside the block, nearest first
     comp_ident(mine);
     if ((uint32_t)lane < k) wait_comp<NW>(sp.st_a0, sp.f_a0, (size_t)(b << 5) + lane, mine);
@@ -419,7 +419,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         bool dense = true, published = false, agg_done = false;
         Comp<CW> agg, acc, inc;
         SparseTail tail;
-        tail.kq = tail.ks = tail.nacc = tail.nruns = tail.over = 0;
+        tail.kq = tail.ks = tail.nacc = tail.nruns = 0;
         tail.rt = 0ull;
         tail.drained = 1;
         if (fw.donly(pv) && fw.rs_n(pv) != 0u) {
@@ -451,6 +451,40 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             // Usually the last row's exit is provably empty before any candidate has been followed (no candidate byte
             // behind the point where nothing carried survives): the tile then publishes FIRST, and its successors find
             // its aggregate ready when they look back.
+#ifdef RRX_EAGER_KINDS
+            // (lean kernel: every row's kind up front, one inlined copy of phase_d_kind)
+            uint32_t cm[4];
+            int qfree;
+            phase_a_mask<NW>(ts, lane, fw.sp_cand(pv), cm);
+            const uint32_t kind = phase_d_kind<NW>(sp, pv, fw, ts, lane, &qfree);
+            const uint32_t behind = qfree >= ROW_BYTES ? 0u : ((qfree >> 5) == 0 ? (cm[0] >> (qfree & 31)) | cm[1] | cm[2] | cm[3]
+                                                             : (qfree >> 5) == 1 ? (cm[1] >> (qfree & 31)) | cm[2] | cm[3]
+                                                             : (qfree >> 5) == 2 ? (cm[2] >> (qfree & 31)) | cm[3] : (cm[3] >> (qfree & 31)));
+            const bool all_closed = __all_sync(FULL, kind == K_CLOSED) != 0;
+            const bool early = all_closed && __shfl_sync(FULL, behind, TILE_ROWS - 1) == 0u;
+            uint32_t arrived = 0;
+            dense = false;
+            if (early) {
+                uint32_t bl[CW];
+#pragma unroll
+                for (int w = 0; w < CW; w++) bl[w] = 0u;
+                comp_closed(agg, bl, 0);
+                arrived = lookback_publish_issue<CW>(sp, tile, agg, lane);
+                published = true;
+            }
+            phase_a_cand<NW, F, true>(sp, pv, fw, ts, lane, cm, tail);
+            __syncwarp();
+            if (early) {
+                lookback_publish_fold<CW>(sp, tile, arrived, lane);       // the arrival count has long come back
+            } else if (all_closed) {
+                uint32_t bl[CW];
+#pragma unroll
+                for (int w = 0; w < CW; w++) bl[w] = ts.sum_b[w * TILE_ROWS + (TILE_ROWS - 1)];
+                comp_closed(agg, bl, 0);
+                lookback_publish<CW>(sp, tile, agg, lane);
+                published = true;
+            }
+#else
             uint32_t cm[4];
             int qfree = 0;
             phase_a_mask<NW>(ts, lane, fw.sp_cand(pv), cm);
@@ -477,11 +511,13 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
 #pragma unroll
                 for (int w = 0; w < CW; w++) carried_in |= ts.sum_b[w * TILE_ROWS + lane - 1];
             }
-            if (__any_sync(FULL, carried_in != 0u) && carried_in != 0u) kind = phase_d_kind<NW>(sp, pv, fw, ts, lane, &qfree);
+            if (RRX_UNLIKELY(__any_sync(FULL, carried_in != 0u) != 0)) {
+                if (carried_in != 0u) kind = phase_d_kind<NW>(sp, pv, fw, ts, lane, &qfree);
+            }
             const bool rows_ok = __all_sync(FULL, kind == K_CLOSED) != 0;
             if (early) lookback_publish_fold<CW>(sp, tile, arrived, lane);       // the arrival count has long come back
-            if (rows_ok) {
-                if (!early) {
+            if (!RRX_UNLIKELY(!rows_ok)) {
+                if (RRX_UNLIKELY(!early)) {
                     uint32_t bl[CW];
 #pragma unroll
                     for (int w = 0; w < CW; w++) bl[w] = ts.sum_b[w * TILE_ROWS + (TILE_ROWS - 1)];
@@ -496,6 +532,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
                 agg_done = early;
                 __syncwarp();
             }
+#endif
         } else if (sp.sparse) {
             if (dense_left == 0) {
                 const bool closed = phase_a_exit<NW>(sp, pv, fw, ts, lane);
@@ -541,7 +578,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         // t-1's exit — phases S1/S2 have nothing to compute beyond the tile's entry set.
         bool any_open = false;
         SLocal<CW> L;
-        if (!published) {
+        if (RRX_UNLIKELY(!published)) {
             const uint32_t my_kind = ts.sum_kind[lane];
             any_open = __any_sync(FULL, my_kind == K_RANK1 || my_kind == K_HARD) != 0;
             __syncwarp();
@@ -584,19 +621,15 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             for (int w = 0; w < CW; w++) carried |= lane == 0 ? ts.misc[TS::M_ENTRY + w] : ts.sum_b[w * TILE_ROWS + lane - 1];
             // (only tiles that published early still have the rows' exits in sum_b: phase S1 rewrites them otherwise)
             fast = published && __all_sync(FULL, tail.simple() && carried == 0) != 0;
-            if (fw.donly(pv)) {
-                // what the scanner picks its next kernel by (ScanParams::straddle_tiles)
-#ifdef RRX_NO_OVERRUN
-                const bool straddle = __any_sync(FULL, lane != 0 && carried != 0u) != 0;
-#else
-                const bool straddle = __any_sync(FULL, tail.over != 0u) != 0;
+#if defined(RRX_NO_OVERRUN) && !defined(RRX_NO_COUNTER)
+            // lean kernel: a tile that leaves the fast tail counts towards the switch to the straddle kernel
+            // (ScanParams::straddle_tiles; on the slow path only — the fast path pays nothing for it)
+            if (!fast && fw.donly(pv) && lane == 0 && sp.straddle_tiles) atom_add_u32(sp.straddle_tiles, 1u);
 #endif
-                if (straddle && lane == 0 && sp.straddle_tiles) atom_add_u32(sp.straddle_tiles, 1u);
-            }
-            if (!fast) sparse_drain<NW>(ts, lane, tail);
+            if (RRX_UNLIKELY(!fast)) sparse_drain<NW>(ts, lane, tail);
             __syncwarp();
         }
-        if (fast) {
+        if (!RRX_UNLIKELY(!fast)) {
             uint32_t inc_c, total;
             if (__all_sync(FULL, tail.nacc <= 1u)) {       // the usual case: a vote and two popcounts
                 const uint32_t have = __ballot_sync(FULL, tail.nacc != 0u);

@@ -42,6 +42,14 @@
 #define RRX_WARP_ANY(x) (x)          // the emulator steps one lane at a time
 #endif
 
+// Branch hints: the compiler lays out what it is told is unlikely away from the hot instruction stream, and the
+// per-tile code of 32 de-phased warps has to fit the instruction cache (see RRX_COLD).
+#if defined(__CUDACC__) || defined(__GNUC__)
+#define RRX_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define RRX_UNLIKELY(x) (x)
+#endif
+
 #ifdef RRX_HOST_EMU
 struct uint4 { uint32_t x, y, z, w; };
 inline uint32_t atomicOr(uint32_t* p, uint32_t v) { uint32_t o = *p; *p |= v; return o; }
@@ -454,8 +462,8 @@ struct ScanParams {
     // 1 the tile holds none of the skip state's stop bytes, else 2 + tile-relative offset of its LAST one.  A backward
     // walk in the skip state that leaves its tile hops over whole tiles with it (see back_walk).  Zeroed per scan.
     volatile uint32_t* tile_stop;
-    // thread-owned scan: tiles that left the fast tail because a row handed a state to the next one (lean kernel) /
-    // tiles in which a lane followed a run into the next row (straddle kernel) — what the scanner picks its next kernel by
+    // thread-owned scan: tiles that left the fast tail (lean kernel) / rows whose run its lane followed into the next row
+    // (straddle kernel) — what the scanner picks its next kernel by
     uint32_t* straddle_tiles;
     unsigned long long ovf_base;
     uint32_t* err;
@@ -899,7 +907,6 @@ RRX_DEV bool phase_a_exit(const ScanParams& sp, const ProgView& pv, const F& fw,
 // lazy starts of the last four tagged runs (rt: 16 bits each, most recent lowest: start - row start + KS_BIAS).
 struct SparseTail {
     uint32_t kq, ks, nacc, drained, nruns;
-    uint32_t over;      // the lane followed a run into the next row
     unsigned long long rt;
     // lazy start (biased, see KS_BIAS) of the run with tag g, 0 if it is not on record any more
     RRX_DEV uint32_t start_of(uint32_t g) const {
@@ -944,6 +951,7 @@ RRX_COLD void sparse_drain(TileState<NW, CW>& ts, int t, const SparseTail& q) {
         const uint32_t e1 = (q.kq >> (8 * i)) & 0xffu;
         if (e1 && (uint32_t)i < q.nacc) {
             const uint32_t pos = e1 - 1, s16 = q.start_of((q.ks >> (8 * i)) & 0xffu);
+#ifndef RRX_NO_OVERRUN
             if (pos >= (uint32_t)ROW_BYTES) {
                 // an end found while overrunning into the next row: it belongs to that row's hit mask (another lane's
                 // words: atomic); its start is left to the backward walk
@@ -951,6 +959,9 @@ RRX_COLD void sparse_drain(TileState<NW, CW>& ts, int t, const SparseTail& q) {
                 continue;
             }
             atomicOr(ts.hits + (pos >> 5) * ROWS + t, 1u << (pos & 31));
+#else
+            ts.hits[(pos >> 5) * ROWS + t] |= 1u << (pos & 31);
+#endif
             if (s16) {
                 const uint32_t rec = (pos << 16) | s16;
                 if (ts.kst[2 * t] == KST_NONE) ts.kst[2 * t] = rec;
@@ -1051,7 +1062,7 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
     uint32_t p = 0;
     uint32_t rs1 = 0;                   // tag of the current run if the lazy start of its matches is known, else 0
     SparseTail q;
-    q.kq = q.ks = q.nacc = q.drained = q.nruns = q.over = 0;
+    q.kq = q.ks = q.nacc = q.drained = q.nruns = 0;
     q.rt = 0ull;
     uint32_t bail = (!DONLY && ncand > SPARSE_MAX_CAND) ? 1u : 0u;
     uint32_t live = 0;                  // OR of the words of H
@@ -1066,7 +1077,7 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
     ts.kst[2 * t] = ts.kst[2 * t + 1] = KST_NONE;
     while (RRX_WARP_ANY(work != 0)) {
         // ---- outer: the queue is full, or the lane is at a candidate byte (or jumps to its next one) ----
-        if (work != 0 && q.nacc >= 4) {
+        if (RRX_UNLIKELY(work != 0 && q.nacc >= 4)) {
             sparse_drain<NW>(ts, t, q);
             q.kq = q.ks = q.nacc = 0;
             q.drained = 1u;
@@ -1113,7 +1124,7 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
                             if (!DONLY && --budget < 0) { bail = 1u; break; }
                         }
                     }
-                    if (DONLY && !inj && alive) {
+                    if (RRX_UNLIKELY(DONLY && !inj && alive)) {
                         // the walk goes on before the row start: earlier rows of the tile, then global memory
                         // (once a walk somewhere has run out of budget the scan is void: let the grid drain quickly)
                         const int64_t row_lo = ts.lo() + ((int64_t)t << ROW_SHIFT);
@@ -1233,7 +1244,7 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
 #else
         const uint32_t over = (t < ROWS - 1 && rowend == (uint32_t)ROW_BYTES && p >= rowend && live != 0u && q.nacc < 4u) ? 1u : 0u;
 #endif
-        if (RRX_WARP_ANY(over != 0u)) {
+        if (RRX_UNLIKELY(RRX_WARP_ANY(over != 0u))) {
             uint32_t Hx[NW];
 #pragma unroll
             for (int w = 0; w < NW; w++) Hx[w] = H[w];
@@ -1264,8 +1275,9 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
                 ovf |= (step && lv != 0u && (q.nacc >= 4u || p2 >= (uint32_t)ROW_BYTES - 1u)) ? 1u : 0u;   // outlives the queue / the next row
                 go = (step && !ovf) ? live : 0u;
             }
-            q.over = over;
             if (over) {
+                // (straddle kernel: rows whose run was followed into the next row — ScanParams::straddle_tiles)
+                if (sp.straddle_tiles) atomicAdd(sp.straddle_tiles, 1u);
                 if (ovf) {                      // undo: the classic hand-over through the row's exit
                     q.kq = kq0; q.ks = ks0; q.nacc = na0;
 #pragma unroll

@@ -98,7 +98,7 @@ int run(const Program& prog, const uint8_t* text, uint64_t left_ctx, uint64_t le
         uint32_t sp_hits[ROWS][4], sp_b[ROWS][NW];
         uint32_t sp_kst[ROWS][2];
         SparseTail tails[ROWS];
-        for (int t = 0; t < ROWS; t++) { tails[t].kq = tails[t].ks = tails[t].nacc = tails[t].nruns = tails[t].over = 0; tails[t].rt = 0; tails[t].drained = 1; }
+        for (int t = 0; t < ROWS; t++) { tails[t].kq = tails[t].ks = tails[t].nacc = tails[t].nruns = 0; tails[t].rt = 0; tails[t].drained = 1; }
         bool published = false, all_closed_d = true;
         ts.misc[TS::M_ZVALID] = 0;
         if (h.donly && g_sparse_mode && h.rskip_n) {

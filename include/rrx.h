@@ -190,6 +190,39 @@ int rrx_scanner_copy_pending(rrx_scanner* s, void* host_out, uint64_t cap, uint6
 int rrx_continue_starts(const rrx_program* p, const uint8_t* d_text, uint64_t len, uint64_t left_context,
                         uint64_t base_offset, void* records_host, uint64_t n, int64_t* start_out, void* stream);
 
+/* ---- sharded scans over NCCL (csrc/rrx_dist.cu): SURVEY.md §8b `rrx_scan_sharded`, §8e -------------------------
+ * One contiguous byte range of the text per GPU, one process per GPU.  `nccl_comm` is the caller's ncclComm_t (passed
+ * as void*; librrx loads libnccl.so.2 at run time and uses the library already in the process).  A step, per rank:
+ * speculative scan of the shard, ONE ncclAllGather of [shard composite | counters | entry used] (a few hundred bytes
+ * per rank over NVLink), a one-thread kernel that folds the composites of the ranks to the left into this rank's exact
+ * entry set and flags, one small copy to pinned memory — all enqueued on `stream` by rrx_sharded_begin, no host
+ * round trip.  rrx_sharded_finish waits for that copy; if no rank needs more (no state crosses a shard boundary, no
+ * start walk leaves its halo) the speculative list is the result.  Otherwise all ranks together rescan with their
+ * exact entries (rounds of all-gather + fold) and hand start walks to the left neighbour; finish returns when done.
+ * Two buffer sets: begin(k+1) may be called before finish(k), so the host side of one step overlaps the next scan.
+ * left_context: bytes readable before d_text (the halo: the tail of the shard to the left), for start and
+ * verification walks that cross the shard's left edge.  Output stays sharded: rank order = text order. */
+typedef struct rrx_sharded rrx_sharded;
+typedef struct rrx_sharded_result {
+    uint64_t n_matches;         /* exact matches of this rank's shard */
+    const int64_t* d_matches;   /* device pairs (start,end), ascending end; valid until the buffer set is reused (two steps later) */
+    uint32_t rescans;           /* whole-shard rescans this step needed on this rank (0 in the common case) */
+    uint32_t patched_starts;    /* starts found by ranks to the left and patched into the list */
+    uint32_t flags;             /* internal status bits of the last exchange */
+    uint32_t reserved;
+    rrx_scanner* scanner;       /* the scanner that holds the list (for rrx_scanner_digest / copy_matches) */
+} rrx_sharded_result;
+int rrx_sharded_create(const rrx_program* p, uint64_t max_len, uint64_t match_capacity, void* nccl_comm, int rank, int nranks,
+                       rrx_sharded** out);
+int rrx_sharded_begin(rrx_sharded* s, const uint8_t* d_text, uint64_t len, uint64_t base_offset, uint64_t left_context, void* stream);
+int rrx_sharded_finish(rrx_sharded* s, rrx_sharded_result* out);
+/* begin + finish */
+int rrx_scan_sharded(rrx_sharded* s, const uint8_t* d_text, uint64_t len, uint64_t base_offset, uint64_t left_context, void* stream,
+                     rrx_sharded_result* out);
+int rrx_sharded_enable_timing(rrx_sharded* s, int on);
+float rrx_sharded_kernel_ms(rrx_sharded* s);          /* scan kernel of the last finished step (see rrx_scanner_kernel_ms) */
+void rrx_sharded_free(rrx_sharded* s);
+
 /* ---- parity at scale: digest of a device match list (csrc/rrx_hash.cu) --------------------------
  * digest[0] = matches with end <= end_limit, [1] = sum and [2] = xor over those of
  * sm64(sm64(start) + end) (splitmix64 finaliser), [3] = order violations in the WHOLE list

@@ -26,7 +26,7 @@ import numpy as np
 
 from . import _build
 
-__all__ = ["RRegex", "Match", "InvalidExpression", "RrxError", "Scanner", "lib", "corpus_iid", "corpus_records", "corpus_lines", "corpus_device"]
+__all__ = ["RRegex", "Match", "InvalidExpression", "RrxError", "Scanner", "lib", "corpus_iid", "corpus_records", "corpus_lines", "corpus_device", "NcclComm", "ShardedScanner"]
 
 RRX_OK, RRX_ERR_PARSE, RRX_ERR_CUDA, RRX_ERR_UNSUPPORTED, RRX_ERR_ARG = range(5)
 MODE_LAZY_V1, MODE_NO_OVERLAP = 0, 1
@@ -56,6 +56,11 @@ class _Result(C.Structure):
     _fields_ = [("n_matches", C.c_uint64), ("capacity", C.c_uint64), ("n_pending", C.c_uint64),
                 ("error_bits", C.c_uint32), ("launches", C.c_uint32), ("d_matches", C.c_void_p),
                 ("soft_bits", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class _ShardedResult(C.Structure):
+    _fields_ = [("n_matches", C.c_uint64), ("d_matches", C.c_void_p), ("rescans", C.c_uint32), ("patched_starts", C.c_uint32),
+                ("flags", C.c_uint32), ("reserved", C.c_uint32), ("scanner", C.c_void_p)]
 
 
 _LIB = None
@@ -110,6 +115,13 @@ def lib() -> C.CDLL:
         "rrx_fold_entries": (C.c_int, [vp, vp, u32, vp, vp]),
         "rrx_apply_summary": (C.c_int, [vp, vp, vp, vp]),
         "rrx_continue_starts": (C.c_int, [vp, vp, u64, u64, u64, vp, u64, vp, vp]),
+        "rrx_sharded_create": (C.c_int, [vp, u64, u64, vp, C.c_int, C.c_int, C.POINTER(vp)]),
+        "rrx_sharded_begin": (C.c_int, [vp, vp, u64, u64, u64, vp]),
+        "rrx_sharded_finish": (C.c_int, [vp, C.POINTER(_ShardedResult)]),
+        "rrx_scan_sharded": (C.c_int, [vp, vp, u64, u64, u64, vp, C.POINTER(_ShardedResult)]),
+        "rrx_sharded_enable_timing": (C.c_int, [vp, C.c_int]),
+        "rrx_sharded_kernel_ms": (C.c_float, [vp]),
+        "rrx_sharded_free": (None, [vp]),
         "rrx_digest_device": (C.c_int, [vp, u64, i64, vp, vp]),
         "rrx_scanner_digest": (C.c_int, [vp, i64, vp, vp]),
         "rrx_corpus_iid_device": (C.c_int, [vp, u64, u64, u64, vp, vp]),
@@ -435,3 +447,78 @@ def corpus_device(cfg, d_ptr: int, offset: int, length: int, stream: int = 0):
         corpus_lines(d_ptr, offset, length, cfg.seed, stream)
     else:
         corpus_records(d_ptr, offset, length, cfg.seed, stream)
+
+
+class NcclComm:
+    """A raw NCCL communicator (ncclComm_t) for rrx_sharded_*, made with libnccl.so.2 directly (ctypes): rank 0 draws
+    the unique id, `broadcast(bytes) -> bytes` (any side channel: torch.distributed, MPI, a file) hands it to the others.
+    The library is the one already in the process if there is one (e.g. torch's), which is also what librrx picks up."""
+
+    def __init__(self, rank: int, world: int, broadcast):
+        self.lib = C.CDLL("libnccl.so.2")
+        uid = C.create_string_buffer(128)
+        if rank == 0:
+            assert self.lib.ncclGetUniqueId(uid) == 0
+        raw = broadcast(bytes(uid.raw))
+        uid = C.create_string_buffer(raw, 128)
+
+        class _Uid(C.Structure):
+            _fields_ = [("internal", C.c_char * 128)]
+        u = _Uid()
+        C.memmove(C.byref(u), uid, 128)
+        self.comm = C.c_void_p()
+        self.lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, _Uid, C.c_int]
+        rc = self.lib.ncclCommInitRank(C.byref(self.comm), world, u, rank)
+        if rc != 0:
+            raise RrxError(f"ncclCommInitRank failed ({rc})")
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if self.comm:
+            self.lib.ncclCommDestroy.argtypes = [C.c_void_p]
+            self.lib.ncclCommDestroy(self.comm)
+            self.comm = None
+
+
+class ShardedScanner:
+    """rrx_sharded_* (include/rrx.h): the sharded scan of one rank's shard, exchange over NCCL included."""
+
+    def __init__(self, regex: RRegex, max_len: int, capacity: int, comm: NcclComm):
+        self.regex, self.comm = regex, comm
+        h = C.c_void_p()
+        _check(lib().rrx_sharded_create(regex._h, max_len, capacity, comm.comm, comm.rank, comm.world, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _LIB is not None:
+            _LIB.rrx_sharded_free(h)
+
+    def begin(self, d_ptr: int, length: int, base_offset: int, left_context: int = 0, stream: int = 0):
+        _check(lib().rrx_sharded_begin(self._h, d_ptr, length, base_offset, left_context, stream))
+
+    def finish(self) -> dict:
+        r = _ShardedResult()
+        _check(lib().rrx_sharded_finish(self._h, C.byref(r)))
+        return dict(n_matches=int(r.n_matches), d_matches=int(r.d_matches or 0), rescans=int(r.rescans),
+                    patched_starts=int(r.patched_starts), flags=int(r.flags), scanner=r.scanner)
+
+    def scan(self, d_ptr: int, length: int, base_offset: int, left_context: int = 0, stream: int = 0) -> dict:
+        self.begin(d_ptr, length, base_offset, left_context, stream)
+        return self.finish()
+
+    def matches(self, res: dict, stream: int = 0) -> np.ndarray:
+        out = np.empty((res["n_matches"], 2), dtype=np.int64)
+        _check(lib().rrx_scanner_copy_matches(res["scanner"], out.ctypes.data, res["n_matches"], stream))
+        return out
+
+    def digest(self, res: dict, end_limit: int = (1 << 62), stream: int = 0) -> tuple:
+        d = np.zeros(4, dtype=np.uint64)
+        _check(lib().rrx_scanner_digest(res["scanner"], end_limit, d.ctypes.data, stream))
+        return tuple(int(x) for x in d)
+
+    def enable_timing(self, on: bool = True):
+        _check(lib().rrx_sharded_enable_timing(self._h, int(on)))
+
+    def kernel_ms(self) -> float:
+        return float(lib().rrx_sharded_kernel_ms(self._h))

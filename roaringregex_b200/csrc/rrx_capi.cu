@@ -21,6 +21,9 @@ using namespace rrx;
 namespace {
 thread_local std::string g_err;
 int set_err(int code, const std::string& msg) { g_err = msg; return code; }
+}  // namespace
+int rrx_dist_set_err(int code, const std::string& msg) { return set_err(code, msg); }      // for rrx_dist.cu
+namespace {
 int cuda_err(cudaError_t e, const char* what) {
     return set_err(RRX_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }

@@ -305,70 +305,69 @@ def sub_record(rrx, torch, cfg, peak, prefix, sh, steps=3):
     return rec
 
 
+def make_nccl_comm(rrx, torch, dist, rank, world):
+    """A raw ncclComm_t for rrx_sharded_* (the unique id travels over torch.distributed)."""
+    cached = getattr(make_nccl_comm, "_c", None)
+    if cached is None:
+        def bcast(raw):
+            t = torch.tensor(list(raw), dtype=torch.uint8, device="cuda")
+            dist.broadcast(t, 0)
+            return bytes(t.cpu().tolist())
+        cached = make_nccl_comm._c = rrx.NcclComm(rank, world, bcast)
+    return cached
+
+
 def sub_record_sharded(rrx, torch, dist, cfg, peak, prefix, sh, rank, world, local, steps=3):
-    """Config 5 as BASELINE.json names it: ONE 64 GiB corpus cut into `world` contiguous shards (strong
-    scaling).  Sum/xor digests add up over the shards, so the whole-job digest must equal the 1-GPU one."""
-    from roaringregex_b200 import sharded
+    """Config 5 as BASELINE.json names it: ONE 64 GiB corpus cut into `world` contiguous shards (strong scaling), scanned
+    through the C ABI's sharded scan (rrx_sharded_*).  Sum/xor digests add up over the shards, so the whole-job digest
+    must equal the 1-GPU one."""
     size = (cfg.length // world) & ~4095
     off = rank * size
     halo = min(off, 1 << 20)
     regex = rrx.RRegex(cfg.pattern)
     d_buf, d_text = _scan_setup(rrx, torch, cfg, size, off, halo, sh)
-    comm = sharded.TorchComm(dist, torch.device("cuda", local))
     cap = max(1 << 16, size // 160)
     probe = rrx.Scanner(regex, size, cap)
     probe.scan(d_text.data_ptr(), size, off, halo, None, sh)
     cap = max(cap, probe.result(sh)["n_matches"] + (1 << 16))
     del probe
     torch.cuda.empty_cache()
-    be = sharded.DeviceBackend(regex, d_text.data_ptr(), size, off, halo, cap, sh)
+    ss = rrx.ShardedScanner(regex, size, cap, make_nccl_comm(rrx, torch, dist, rank, world))
+    ss.enable_timing(True)
     res = None
-    for _ in range(2):
-        res = sharded.scan_sharded(regex, be, comm, rank, world, fetch=False)
+    for _ in range(3):
+        res = ss.scan(d_text.data_ptr(), size, off, halo, sh)
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        res = sharded.scan_sharded(regex, be, comm, rank, world, fetch=False)
+    for k in range(steps):          # pipelined: begin k+1 before finish k
+        ss.begin(d_text.data_ptr(), size, off, halo, sh)
+        if k:
+            res = ss.finish()
+    res = ss.finish()
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) * 1e3 / steps
-    # digest of this rank's exact list (repaired head on the host + device tail), summed/xored over the ranks
-    from oracle import api as oracle_api
-    tail_sc = res.tail.handle
-    dg_tail = tail_sc.digest(1 << 62, sh)
-    head_dg = oracle_api.digest(res.head) if len(res.head) else (0, 0, 0, 0)
-    skip_dg = (0, 0, 0, 0)
-    if res.skip:
-        skip_dg = oracle_api.digest(be.head(res.tail, res.skip))
-    cnt = dg_tail[0] - skip_dg[0] + head_dg[0]
-    s = (dg_tail[1] - skip_dg[1] + head_dg[1]) % (1 << 64)
-    x = dg_tail[2] ^ skip_dg[2] ^ head_dg[2]
-    patched = len(res.patches)
+    k_ms = ss.kernel_ms()
+    dg = ss.digest(res, 1 << 62, sh)
     cf = closed_form_count(torch, cfg, d_text, size, off)
-    t = torch.tensor([cnt, s >> 32, s & 0xffffffff, dg_tail[3], cf[0], -1 if cf[1] is None else cf[1], res.rescans, patched, res.count],
-                     device="cuda", dtype=torch.int64)
+    t = torch.tensor([dg[0], dg[1] >> 32, dg[1] & 0xffffffff, dg[2] >> 32, dg[2] & 0xffffffff, dg[3], cf[0], -1 if cf[1] is None else cf[1],
+                      res["rescans"], res["patched_starts"], res["n_matches"]], device="cuda", dtype=torch.int64)
     g = [torch.zeros_like(t) for _ in range(world)]
     dist.all_gather(g, t)
-    tx = torch.tensor([x >> 32, x & 0xffffffff], device="cuda", dtype=torch.int64)
-    gx = [torch.zeros_like(tx) for _ in range(world)]
-    dist.all_gather(gx, tx)
-    tm = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    tm = torch.tensor([ms, k_ms], device="cuda", dtype=torch.float64)
     dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms = float(tm.item())
+    ms, k_ms = float(tm[0].item()), float(tm[1].item())
     g = [v.tolist() for v in g]
     total = sum(v[0] for v in g)
     ssum = sum((v[1] << 32) | v[2] for v in g) % (1 << 64)
     sx = 0
-    for v in gx:
-        hi, lo = v.tolist()
-        sx ^= (hi << 32) | lo
-    # closed form: q's after the corpus's first z.  Shard r counted q's after ITS first z; q's of shards right of
+    for v in g:
+        sx ^= (v[3] << 32) | v[4]
+    # closed form: q's after the corpus's first z.  Shard r counted the q's after ITS first z; the q's of shards right of
     # the globally first z that precede their own first z are owed too.
-    cf_total = sum(v[4] for v in g)
-    zs = [v[5] for v in g]
-    note = None
+    cf_total = sum(v[6] for v in g)
+    zs = [v[7] for v in g]
     if any(z >= 0 for z in zs):
         first_rank = next(i for i, z in enumerate(zs) if z >= 0)
-        # every shard of the synthetic corpus has a z within its first KiB; count the q's before it exactly
         lo_fix = torch.tensor([0], device="cuda", dtype=torch.int64)
         if rank > first_rank:
             zloc = (zs[rank] - off) if zs[rank] >= 0 else size
@@ -376,15 +375,16 @@ def sub_record_sharded(rrx, torch, dist, cfg, peak, prefix, sh, rank, world, loc
         dist.all_reduce(lo_fix)
         cf_total += int(lo_fix.item())
     full_bytes = size * world
-    rec = {"workload": f"{cfg.name}: regex {cfg.pattern!r}, ONE corpus of {full_bytes} bytes cut into {world} contiguous shards (strong scaling)",
+    rec = {"workload": f"{cfg.name}: regex {cfg.pattern!r}, ONE corpus of {full_bytes} bytes cut into {world} contiguous shards (strong scaling), "
+                       "scanned through rrx_sharded_* (C ABI; NCCL all-gather + fold on the device)",
            "bytes_total": full_bytes, "bytes_per_gpu": size, "matches": total, "value": full_bytes / (ms * 1e-3) / 1e9, "unit": "GB/s",
-           "ms_per_step": ms, "steps": steps, "scaling": "strong",
-           "roofline_frac_per_gpu": (size + 16 * total / world) / (ms * 1e-3) / 1e9 / peak,
-           "rescans_per_rank": [v[6] for v in g], "start_patches_per_rank": [v[7] for v in g],
-           "parity": {"hash_gpu": [total, f"{ssum:016x}", f"{sx:016x}"], "order_violations": sum(v[3] for v in g),
-                      "count_closed_form": cf_total, "ok": bool(total == cf_total and sum(v[3] for v in g) == 0 and total == sum(v[8] for v in g)),
+           "ms_per_step": ms, "kernel_ms": k_ms, "steps": steps, "scaling": "strong",
+           "roofline_frac_per_gpu": (size + 16 * total / world) / (k_ms * 1e-3) / 1e9 / peak,
+           "rescans_per_rank": [v[8] for v in g], "start_patches_per_rank": [v[9] for v in g],
+           "parity": {"hash_gpu": [total, f"{ssum:016x}", f"{sx:016x}"], "order_violations": sum(v[5] for v in g),
+                      "count_closed_form": cf_total, "ok": bool(total == cf_total and sum(v[5] for v in g) == 0 and total == sum(v[10] for v in g)),
                       "note": "sum/xor digests are order-free: this triple must equal config5's hash_gpu in the 1-GPU record"}}
-    del be, d_text, d_buf
+    del ss, d_text, d_buf
     return rec
 
 
@@ -447,22 +447,22 @@ def main():
         launches_per_step = res["launches"]
         is_jit = sc.is_jit
     else:
-        from roaringregex_b200 import sharded
-        comm = sharded.TorchComm(dist, torch.device("cuda", local))
+        # the C ABI's sharded scan (rrx_sharded_*, csrc/rrx_dist.cu): NCCL all-gather + fold on the device
+        ncomm = make_nccl_comm(rrx, torch, dist, rank, world)
         probe = rrx.Scanner(regex, size, cap)
         probe.scan(d_text.data_ptr(), size, off, halo, None, sh)
         cap = max(cap, probe.result(sh)["n_matches"] + (1 << 16))
+        is_jit = probe.is_jit
         del probe
-        be = sharded.DeviceBackend(regex, d_text.data_ptr(), size, off, halo, cap, sh)
+        be = rrx.ShardedScanner(regex, size, cap, ncomm)
         last = {}
 
         def step():
-            last["res"] = sharded.scan_sharded(regex, be, comm, rank, world, fetch=False)
+            last["res"] = be.scan(d_text.data_ptr(), size, off, halo, sh)
         for _ in range(max(args.warmup, 4)):
             step()
-        n_matches = last["res"].count
-        launches_per_step = 4 * (1 + (2 if last["res"].rescans == 1 else last["res"].rescans))
-        is_jit = be.scanner.is_jit
+        n_matches = last["res"]["n_matches"]
+        launches_per_step = 4 * (1 + last["res"]["rescans"]) + 1         # + the fold kernel
 
     def barrier():
         torch.cuda.synchronize()
@@ -479,9 +479,7 @@ def main():
         timed_scanner = sc
         sc.enable_timing(True)
     else:
-        for s_ in be.scanners:
-            if s_ is not None:
-                s_.enable_timing(True)
+        be.enable_timing(True)
     barrier()
     w0 = time.perf_counter()
     t_all0 = torch.cuda.Event(enable_timing=True); t_all1 = torch.cuda.Event(enable_timing=True)
@@ -495,16 +493,14 @@ def main():
         # Steps are software-pipelined: step k+1 is enqueued (scan kernels, message copy, all-gather,
         # D2H) before the host waits for step k's gathered messages, folds the entry sets and validates
         # the speculative scan.  Every step's collective and validation complete inside the timed region.
-        prev = None
-        for _ in range(args.steps):
-            tok = sharded.scan_sharded_begin(regex, be, comm)
-            if prev is not None:
-                last["res"] = sharded.scan_sharded_finish(regex, be, comm, rank, world, prev, fetch=False)
-                scan_kernel_ms.append(prev["scanner"].kernel_ms())
-            prev = tok
-        last["res"] = sharded.scan_sharded_finish(regex, be, comm, rank, world, prev, fetch=False)
-        scan_kernel_ms.append(prev["scanner"].kernel_ms())
-        assert last["res"].count == n_matches
+        for k in range(args.steps):
+            be.begin(d_text.data_ptr(), size, off, halo, sh)
+            if k:
+                last["res"] = be.finish()
+                scan_kernel_ms.append(be.kernel_ms())
+        last["res"] = be.finish()
+        scan_kernel_ms.append(be.kernel_ms())
+        assert last["res"]["n_matches"] == n_matches
     t_all1.record(stream)
     barrier()
     wall_ms = (time.perf_counter() - w0) * 1e3
@@ -599,7 +595,27 @@ def main():
         sub_keys = ([1, "2v", 3, 4, 5] if world == 1 else [5]) if key == 2 and not args.size else []
     elif args.sub != "none":
         sub_keys = [k if k in CONFIGS else int(k) for k in args.sub.split(",") if k]
-    sc = timed_scanner = step = be = prev = tok = comm = None        # release the headline's device buffers
+    # parity at N>1: the ranks' digests add / xor up to the digest of the whole list; count vs the closed form
+    if world > 1:
+        dg = be.digest(last["res"], 1 << 62, sh)
+        cf = closed_form_count(torch, cfg, d_text, size, 0) if off == 0 or cfg.mode == "iid" else None
+        if cfg.name == "config2":          # records are position-independent in kind: count this rank's records
+            from oracle import api as oracle_api
+            cf = oracle_api.records_valid(cfg.seed, (off + size) // 128) - oracle_api.records_valid(cfg.seed, off // 128)
+        t = torch.tensor([dg[0], dg[1] >> 32, dg[1] & 0xffffffff, dg[2] >> 32, dg[2] & 0xffffffff, dg[3], cf if isinstance(cf, int) else -1,
+                          last["res"]["rescans"]], device="cuda", dtype=torch.int64)
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        g = [v.tolist() for v in g]
+        tot, ssum, sx = sum(v[0] for v in g), sum((v[1] << 32) | v[2] for v in g) % (1 << 64), 0
+        for v in g:
+            sx ^= (v[3] << 32) | v[4]
+        cfs = [v[6] for v in g]
+        parity = {"hash_gpu": [tot, f"{ssum:016x}", f"{sx:016x}"], "order_violations": sum(v[5] for v in g),
+                  "count_closed_form": sum(cfs) if all(c >= 0 for c in cfs) else None, "rescans_per_rank": [v[7] for v in g],
+                  "note": "weak scaling: rank r scans bytes [r*size, (r+1)*size) of ONE corpus; sum/xor digests over the ranks = digest of the whole list"}
+        parity["ok"] = bool(tot == total_matches and parity["order_violations"] == 0 and (parity["count_closed_form"] in (None, tot)))
+    sc = timed_scanner = step = be = None        # release the headline's device buffers
     if world > 1:
         last.clear()
     d_text = d_buf = None
@@ -631,7 +647,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(cfg.name, size),
                      "kernel": "rrx_scan_jit" if is_jit else "rrx_scan_kernel", "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "step_ms_device": float(np.mean(kern_ms)),
                      "note": "kernel_ms: CUDA events around the scan kernel's launch alone; a step = 2 memsets + scan kernel + 3-kernel ordering pass"
-                             + ("" if world == 1 else " + message copy + NCCL all-gather + D2H of the gathered messages; steps software-pipelined (step k+1 enqueued before the host collects step k)"),
+                             + ("" if world == 1 else " + message copy + ncclAllGather + fold kernel + 160-byte status copy, through rrx_sharded_begin/finish (C ABI); steps pipelined (begin k+1 before finish k)"),
                      "peak_source": peak_src},
         "e2e": e2e, "gpu_launches": args.steps * launches_per_step, "clocks": clocks,
         "kernel_variant": "run-time specialised (NVRTC)" if is_jit else "pre-compiled generic",

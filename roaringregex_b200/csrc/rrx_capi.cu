@@ -657,6 +657,21 @@ int rrx_scanner_message_device(rrx_scanner* s, uint32_t* d_out, uint64_t cap_wor
     return RRX_OK;
 }
 
+// device pointers of the last scan's shard composite (1+3*NW words) and counter block (8 words): for rrx_dist.cu, which
+// packs its message with one kernel instead of copies
+void rrx_scanner_message_sources(rrx_scanner* s, const uint32_t** d_comp, const uint32_t** d_ctr) {
+    s = act(s);
+    *d_comp = s->d_shard;
+    *d_ctr = reinterpret_cast<const uint32_t*>(s->d_ctrl);
+}
+// where the last scan's ordered list lives and how many pairs fit — no synchronisation (rrx_dist.cu has the counts
+// from its own status block)
+void rrx_scanner_peek(rrx_scanner* s, const int64_t** d_matches, uint64_t* capacity) {
+    s = act(s);
+    *d_matches = reinterpret_cast<const int64_t*>(s->d_out);
+    *capacity = s->capacity;
+}
+
 // ---- one-shot convenience calls ----------------------------------------------------------------------
 int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, uint64_t base_offset,
                     int mode, rrx_matches** out, void* stream) {

@@ -30,6 +30,8 @@
 using namespace rrx;
 
 int rrx_dist_set_err(int code, const std::string& msg);      // rrx_capi.cu (thread-local error text)
+extern "C" void rrx_scanner_message_sources(rrx_scanner* s, const uint32_t** d_comp, const uint32_t** d_ctr);
+extern "C" void rrx_scanner_peek(rrx_scanner* s, const int64_t** d_matches, uint64_t* capacity);
 
 namespace {
 
@@ -108,6 +110,16 @@ cudaError_t launch_fold_status(uint32_t NW, const uint32_t* msgs, uint32_t msg_w
     return cudaGetLastError();
 }
 
+// the rank's message [composite | 8 counter words | entry used] in one launch
+struct UsedEntry { uint32_t w[RRX_NW_MAX]; };
+__global__ void pack_message_kernel(const uint32_t* __restrict__ comp, const uint32_t* __restrict__ ctr, const __grid_constant__ UsedEntry used,
+                                    uint32_t nw, uint32_t* __restrict__ msg) {
+    const uint32_t pw = 1 + 3 * nw, i = threadIdx.x;
+    if (i < pw) msg[i] = comp[i];
+    else if (i < pw + 8) msg[i] = ctr[i - pw];
+    else if (i < pw + 8 + nw) msg[i] = used.w[i - pw - 8];
+}
+
 __global__ void patch_starts_kernel(long long* pairs, const unsigned long long* idx, const long long* start, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) pairs[2 * idx[i]] = start[i];
@@ -127,6 +139,10 @@ struct rrx_sharded {
     uint32_t* d_status[2] = {nullptr, nullptr};
     uint32_t* h_status[2] = {nullptr, nullptr};     // pinned
     cudaEvent_t ev[2] = {nullptr, nullptr};
+    // The exchange (pack, all-gather, fold, status copy) runs on a stream of its own, behind an event of the caller's
+    // stream: with pipelined steps it overlaps the NEXT step's scan instead of standing in front of it.
+    cudaStream_t xs = nullptr;
+    cudaEvent_t ev_scan[2] = {nullptr, nullptr};
     int turn = 0;
     struct Step { const uint8_t* text; uint64_t len, base, left_ctx; void* stream; int slot; bool live; } step[2] = {};
     int oldest = 0;
@@ -148,7 +164,9 @@ void rrx_sharded_free(rrx_sharded* s) {
         cudaFree(s->d_msg[i]); cudaFree(s->d_all[i]); cudaFree(s->d_status[i]);
         if (s->h_status[i]) cudaFreeHost(s->h_status[i]);
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+        if (s->ev_scan[i]) cudaEventDestroy(s->ev_scan[i]);
     }
+    if (s->xs) cudaStreamDestroy(s->xs);
     delete s;
 }
 
@@ -169,23 +187,29 @@ int rrx_sharded_create(const rrx_program* p, uint64_t max_len, uint64_t capacity
         if (e == cudaSuccess) e = cudaMalloc(&s->d_status[i], ST_WORDS * 4);
         if (e == cudaSuccess) e = cudaMallocHost(&s->h_status[i], ST_WORDS * 4);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_scan[i], cudaEventDisableTiming);
+        if (e == cudaSuccess && !s->xs) e = cudaStreamCreateWithFlags(&s->xs, cudaStreamNonBlocking);
         if (e != cudaSuccess) { rrx_sharded_free(s); return rrx_dist_set_err(RRX_ERR_CUDA, std::string("rrx_sharded_create: ") + cudaGetErrorString(e)); }
     }
     *out = s;
     return RRX_OK;
 }
 
-// `used`: the entry set the scanner's current list was scanned with (NULL: the empty set)
+// `used`: the entry set the scanner's current list was scanned with (NULL: the empty set).  `st`: the stream the scan
+// was enqueued on; the exchange follows it on the side stream.
 static int enqueue_exchange(rrx_sharded* s, int slot, rrx_scanner* sc, const uint32_t* used, cudaStream_t st) {
-    int rc = rrx_scanner_message_device(sc, s->d_msg[slot], s->msg_words, st);
-    if (rc) return rc;
-    uint32_t* d_used = s->d_msg[slot] + 1 + 3 * s->NW + 8;
-    if (used) RRX_DCUDA(cudaMemcpyAsync(d_used, used, s->NW * 4, cudaMemcpyHostToDevice, st));
-    else RRX_DCUDA(cudaMemsetAsync(d_used, 0, s->NW * 4, st));
-    RRX_DNCCL(nccl().AllGather(s->d_msg[slot], s->d_all[slot], s->msg_words, ncclUint32, s->comm, st));
-    RRX_DCUDA(launch_fold_status(s->NW, s->d_all[slot], s->msg_words, (uint32_t)s->nranks, (uint32_t)s->rank, s->d_status[slot], st));
-    RRX_DCUDA(cudaMemcpyAsync(s->h_status[slot], s->d_status[slot], ST_WORDS * 4, cudaMemcpyDeviceToHost, st));
-    RRX_DCUDA(cudaEventRecord(s->ev[slot], st));
+    const uint32_t *d_comp = nullptr, *d_ctr = nullptr;
+    rrx_scanner_message_sources(sc, &d_comp, &d_ctr);
+    UsedEntry u;
+    for (uint32_t w = 0; w < RRX_NW_MAX; w++) u.w[w] = (used && w < s->NW) ? used[w] : 0u;
+    RRX_DCUDA(cudaEventRecord(s->ev_scan[slot], st));
+    RRX_DCUDA(cudaStreamWaitEvent(s->xs, s->ev_scan[slot], 0));
+    pack_message_kernel<<<1, 160, 0, s->xs>>>(d_comp, d_ctr, u, s->NW, s->d_msg[slot]);
+    RRX_DCUDA(cudaGetLastError());
+    RRX_DNCCL(nccl().AllGather(s->d_msg[slot], s->d_all[slot], s->msg_words, ncclUint32, s->comm, s->xs));
+    RRX_DCUDA(launch_fold_status(s->NW, s->d_all[slot], s->msg_words, (uint32_t)s->nranks, (uint32_t)s->rank, s->d_status[slot], s->xs));
+    RRX_DCUDA(cudaMemcpyAsync(s->h_status[slot], s->d_status[slot], ST_WORDS * 4, cudaMemcpyDeviceToHost, s->xs));
+    RRX_DCUDA(cudaEventRecord(s->ev[slot], s->xs));
     return RRX_OK;
 }
 
@@ -217,7 +241,11 @@ static int rescan_round(rrx_sharded* s, const rrx_sharded::Step& sp, rrx_scanner
     return rrx_scanner_scan(sc, sp.text, sp.len, sp.base, &o, sp.stream);
 }
 
-static int hand_over_pending(rrx_sharded* s, const rrx_sharded::Step& sp, rrx_scanner* sc, cudaStream_t st, uint32_t* patched) {
+static int hand_over_pending(rrx_sharded* s, const rrx_sharded::Step& sp, rrx_scanner* sc, cudaStream_t main_st, uint32_t* patched) {
+    // (every collective of the communicator goes to the side stream; the caller's stream is idle here — the step's
+    // event has been waited for — and is synchronised before the walks are continued on it)
+    cudaStream_t st = s->xs;
+    if (cudaStreamSynchronize(main_st) != cudaSuccess) return rrx_dist_set_err(RRX_ERR_CUDA, "pending hand-over: stream");
     // Start walks that ran off the left edge of a rank's readable text travel left, one rank per hop, until some rank
     // finds the start.  Fixed-size exchange: up to KMAX records per rank and hop.
     constexpr uint32_t KMAX = 64;
@@ -359,18 +387,17 @@ int rrx_sharded_finish(rrx_sharded* s, rrx_sharded_result* out) {
         int rc = hand_over_pending(s, sp, sc, st, &patched);
         if (rc) return rc;
     }
+    // counts come from the status block of the last exchange: no synchronisation with the caller's stream, on which the
+    // next step's scan may already be running
     out->n_matches = (uint64_t)hs[ST_MATCHES_LO] | ((uint64_t)hs[ST_MATCHES_HI] << 32);
     out->rescans = rescans;
     out->patched_starts = patched;
     out->flags = flags;
-    rrx_scan_result r;
-    int rc = rrx_scanner_result(sc, &r, sp.stream);
-    if (rc) return rc;
-    if (r.n_matches > r.capacity) return rrx_dist_set_err(RRX_ERR_ARG, "match buffer too small for this shard");
-    out->n_matches = r.n_matches;
-    out->d_matches = r.d_matches;
+    uint64_t capacity = 0;
+    rrx_scanner_peek(sc, &out->d_matches, &capacity);
+    if (out->n_matches > capacity) return rrx_dist_set_err(RRX_ERR_ARG, "match buffer too small for this shard");
     out->scanner = sc;
-    s->res_sc = sc; s->res_n = r.n_matches; s->res_rescans = rescans; s->res_patched = patched;
+    s->res_sc = sc; s->res_n = out->n_matches; s->res_rescans = rescans; s->res_patched = patched;
     return RRX_OK;
 }
 

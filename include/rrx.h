@@ -190,6 +190,12 @@ int rrx_scanner_copy_pending(rrx_scanner* s, void* host_out, uint64_t cap, uint6
 int rrx_continue_starts(const rrx_program* p, const uint8_t* d_text, uint64_t len, uint64_t left_context,
                         uint64_t base_offset, void* records_host, uint64_t n, int64_t* start_out, void* stream);
 
+/* Non-overlapping (finditer-style) view of the scanner's last list, with the carry that chains chunks and shards
+ * (SURVEY.md Appendix D.2): *carry_io = global offset from which matches may start (0, or the end of the last match
+ * selected in the text before this piece); on return the end of the last match selected here (unchanged if none).
+ * The selected matches are a new device list (*out, rrx_matches_free).  Shards pass the carry from rank to rank. */
+int rrx_scanner_no_overlap(rrx_scanner* s, int64_t* carry_io, rrx_matches** out, void* stream);
+
 /* ---- sharded scans over NCCL (csrc/rrx_dist.cu): SURVEY.md §8b `rrx_scan_sharded`, §8e -------------------------
  * One contiguous byte range of the text per GPU, one process per GPU.  `nccl_comm` is the caller's ncclComm_t (passed
  * as void*; librrx loads libnccl.so.2 at run time and uses the library already in the process).  A step, per rank:

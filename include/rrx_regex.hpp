@@ -10,6 +10,8 @@
 //                                                 reference's README promises and src/Iterator.cpp leaves
 //                                                 empty; `++` advances to the next LAZY-v1 match,
 //                                                 `*` returns it, or nullopt when exhausted
+//   IteratorWrapper get_nonoverlap_iter(char*)    NEW: the finditer-style view of the same list (SURVEY.md Appendix D.2:
+//                                                 p = 0; for (s,e) in LAZY-v1: if s >= p { emit; p = e }), filtered on the device
 //   Match{char* start; char* end; str()}          regex.h:100-105, half-open, pointers into the caller's text
 //   RegexIterator / IteratorWrapper / IterFactoryBase   regex.h:106-126 (virtual destructors added: C4 of
 //                                                 SURVEY.md Appendix C is undefined behaviour in the reference)
@@ -60,6 +62,7 @@ class IterFactoryBase {
 public:
     virtual IteratorWrapper get_acceptance_iter(char* c) = 0;
     virtual IteratorWrapper get_lazy_iter(char* c) = 0;
+    virtual IteratorWrapper get_nonoverlap_iter(char* c) = 0;
     virtual ~IterFactoryBase() {}
 };
 
@@ -101,6 +104,7 @@ public:
 class LazyIterator : public RegexIterator {
     const rrx_program* prog;
     char* text;
+    int mode;                              // RRX_MODE_LAZY_V1 or RRX_MODE_NO_OVERLAP
     std::shared_ptr<rrx_matches> list;     // produced by ONE device scan on first use, shared by copies
     const int64_t* pairs = nullptr;
     uint64_t count = 0;
@@ -108,14 +112,14 @@ class LazyIterator : public RegexIterator {
     void ensure() {
         if (list) return;
         rrx_matches* m = nullptr;
-        check(rrx_scan_host(prog, reinterpret_cast<const uint8_t*>(text), std::strlen(text), 0, RRX_MODE_LAZY_V1, &m));
+        check(rrx_scan_host(prog, reinterpret_cast<const uint8_t*>(text), std::strlen(text), 0, mode, &m));
         list = std::shared_ptr<rrx_matches>(m, rrx_matches_free);
         count = rrx_matches_count(m);
         pairs = rrx_matches_data(m);
         if (count && !pairs) throw std::runtime_error(rrx_last_error());
     }
 public:
-    LazyIterator(char* t, const rrx_program* p) : prog(p), text(t) {}
+    LazyIterator(char* t, const rrx_program* p, int mode_ = RRX_MODE_LAZY_V1) : prog(p), text(t), mode(mode_) {}
     RegexIterator& operator++(int) { ensure(); if (pos < (int64_t)count) pos++; return *this; }
     std::optional<Match> operator*() {
         ensure();
@@ -132,6 +136,7 @@ public:
     explicit Factory(const rrx_program* p) : prog(p) {}
     IteratorWrapper get_acceptance_iter(char* c) { return IteratorWrapper(new AcceptanceIterator(c, prog)); }
     IteratorWrapper get_lazy_iter(char* c) { return IteratorWrapper(new LazyIterator(c, prog)); }
+    IteratorWrapper get_nonoverlap_iter(char* c) { return IteratorWrapper(new LazyIterator(c, prog, RRX_MODE_NO_OVERLAP)); }
 };
 }  // namespace detail
 
@@ -147,6 +152,7 @@ public:
     }
     IteratorWrapper get_acceptance_iter(char* c) { return iter_factory->get_acceptance_iter(c); }
     IteratorWrapper get_lazy_iter(char* c) { return iter_factory->get_lazy_iter(c); }
+    IteratorWrapper get_nonoverlap_iter(char* c) { return iter_factory->get_nonoverlap_iter(c); }
 };
 
 }  // namespace Regex

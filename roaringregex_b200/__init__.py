@@ -124,6 +124,7 @@ def lib() -> C.CDLL:
         "rrx_sharded_free": (None, [vp]),
         "rrx_digest_device": (C.c_int, [vp, u64, i64, vp, vp]),
         "rrx_scanner_digest": (C.c_int, [vp, i64, vp, vp]),
+        "rrx_scanner_no_overlap": (C.c_int, [vp, C.POINTER(i64), C.POINTER(vp), vp]),
         "rrx_corpus_iid_device": (C.c_int, [vp, u64, u64, u64, vp, vp]),
         "rrx_corpus_records_device": (C.c_int, [vp, u64, u64, u64, vp]),
         "rrx_corpus_lines_device": (C.c_int, [vp, u64, u64, u64, vp]),
@@ -404,6 +405,14 @@ class Scanner:
         d = np.zeros(4, dtype=np.uint64)
         _check(lib().rrx_scanner_digest(self._h, end_limit, d.ctypes.data, stream))
         return tuple(int(x) for x in d)
+
+    def no_overlap(self, carry: int = 0, stream: int = 0):
+        """Non-overlapping view of the last scan's list, chained by `carry` (rrx_scanner_no_overlap).
+        -> ((M,2) int64 host array, new carry)"""
+        c = C.c_int64(carry)
+        h = C.c_void_p()
+        _check(lib().rrx_scanner_no_overlap(self._h, C.byref(c), C.byref(h), stream))
+        return _take_matches(h), int(c.value)
 
     def enable_timing(self, on: bool = True):
         _check(lib().rrx_scanner_enable_timing(self._h, int(on)))

@@ -1,10 +1,12 @@
 // C ABI of librrx.so (include/rrx.h).  Host C++ around the sm_100a kernels; no CPU scan path.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <thread>
 #include <mutex>
 #include <new>
 #include <string>
@@ -84,9 +86,21 @@ struct HostCtx {
     uint64_t sc_len = 0, sc_cap = 0;
     struct Pinned { int64_t* p; uint64_t pairs; };
     std::vector<Pinned> pool;           // free pinned buffers
+    // streaming ingestion (rrx_scan_host on long texts): a copy stream, one event per chunk, a second scanner sized for
+    // one chunk, and pinned bounce buffers for pageable input
+    cudaStream_t st_copy = nullptr;
+    std::vector<cudaEvent_t> ev_chunk;
+    rrx_scanner* sc_chunk = nullptr;
+    uint64_t scc_len = 0, scc_cap = 0;
+    uint8_t* bounce[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_bounce[3] = {nullptr, nullptr, nullptr};
+    uint64_t bounce_bytes = 0;
     ~HostCtx() {
         cudaFree(d_text);
         for (auto& b : pool) cudaFreeHost(b.p);
+        for (auto e : ev_chunk) cudaEventDestroy(e);
+        for (int i = 0; i < 3; i++) { if (bounce[i]) cudaFreeHost(bounce[i]); if (ev_bounce[i]) cudaEventDestroy(ev_bounce[i]); }
+        if (st_copy) cudaStreamDestroy(st_copy);
         if (st) cudaStreamDestroy(st);
     }
 };
@@ -179,6 +193,7 @@ void rrx_program_free(rrx_program* p) {
     if (!p) return;
     if (p->alt) { rrx_program_free(p->alt); p->alt = nullptr; }
     if (p->host && p->host->sc) { rrx_scanner_free(p->host->sc); p->host->sc = nullptr; }
+    if (p->host && p->host->sc_chunk) { rrx_scanner_free(p->host->sc_chunk); p->host->sc_chunk = nullptr; }
     delete p;
 }
 
@@ -717,6 +732,163 @@ int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, u
     return set_err(RRX_ERR_CUDA, "match buffer overflow after resize");
 }
 
+// ---- streaming host scan ------------------------------------------------------------------
+// The text is copied to the device in chunks on hc->st_copy (all copies enqueued up front for page-locked input; for
+// pageable input a producer thread moves each chunk through page-locked bounce buffers with a few memcpy threads, which
+// is what takes the copy from the driver's ~11 GB/s staging to the host's memcpy rate).  As soon as a chunk's event fires
+// it is scanned on hc->st with everything before it as left context and the previous chunk's exit state as entry; its
+// matches go to the page-locked result buffer while the next chunk is still in flight.  The list is identical to a
+// one-piece scan (chunk boundaries are shard boundaries with full left context).
+static int scan_host_streaming(const rrx_program* p, HostCtx* hc, const uint8_t* text, uint64_t len, uint64_t base_offset,
+                               uint64_t chunk, rrx_matches** out) {
+    const uint64_t nchunks = (len + chunk - 1) / chunk;
+    if (!hc->st_copy) RRX_CUDA(cudaStreamCreateWithFlags(&hc->st_copy, cudaStreamNonBlocking));
+    while (hc->ev_chunk.size() < nchunks) {
+        cudaEvent_t e;
+        RRX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        hc->ev_chunk.push_back(e);
+    }
+    cudaPointerAttributes attr;
+    bool pageable = true;
+    if (cudaPointerGetAttributes(&attr, text) == cudaSuccess) pageable = attr.type == cudaMemoryTypeUnregistered;
+    else cudaGetLastError();
+    std::atomic<uint64_t> produced(0);
+    std::atomic<int> prod_err(0);
+    std::thread producer;
+    if (!pageable) {
+        for (uint64_t k = 0; k < nchunks; k++) {
+            const uint64_t o = k * chunk, n = std::min(chunk, len - o);
+            RRX_CUDA(cudaMemcpyAsync(hc->d_text + o, text + o, n, cudaMemcpyHostToDevice, hc->st_copy));
+            RRX_CUDA(cudaEventRecord(hc->ev_chunk[k], hc->st_copy));
+        }
+        produced = nchunks;
+    } else {
+        const uint64_t piece = 16ull << 20;                  // bounce granularity
+        if (hc->bounce_bytes < piece) {
+            for (int i = 0; i < 3; i++) {
+                if (hc->bounce[i]) cudaFreeHost(hc->bounce[i]);
+                RRX_CUDA(cudaMallocHost(&hc->bounce[i], piece));
+                if (!hc->ev_bounce[i]) RRX_CUDA(cudaEventCreateWithFlags(&hc->ev_bounce[i], cudaEventDisableTiming));
+            }
+            hc->bounce_bytes = piece;
+        }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        producer = std::thread([=, &produced, &prod_err] {
+            cudaSetDevice(dev);
+            const unsigned nt = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+            uint64_t turn = 0;
+            for (uint64_t k = 0; k < nchunks && !prod_err; k++) {
+                const uint64_t o0 = k * chunk, n0 = std::min(chunk, len - o0);
+                for (uint64_t q = 0; q < n0; q += piece, turn++) {
+                    const int b = (int)(turn % 3);
+                    const uint64_t n = std::min(piece, n0 - q);
+                    if (turn >= 3 && cudaEventSynchronize(hc->ev_bounce[b]) != cudaSuccess) { prod_err = 1; break; }
+                    std::vector<std::thread> th;
+                    const uint64_t per = ((n + nt - 1) / nt + 4095) & ~4095ull;
+                    for (unsigned t = 0; t < nt; t++) {
+                        const uint64_t lo = t * per, hi = std::min(n, lo + per);
+                        if (lo < hi) th.emplace_back([=] { std::memcpy(hc->bounce[b] + lo, text + o0 + q + lo, hi - lo); });
+                    }
+                    for (auto& x : th) x.join();
+                    if (cudaMemcpyAsync(hc->d_text + o0 + q, hc->bounce[b], n, cudaMemcpyHostToDevice, hc->st_copy) != cudaSuccess ||
+                        cudaEventRecord(hc->ev_bounce[b], hc->st_copy) != cudaSuccess) { prod_err = 1; break; }
+                }
+                if (cudaEventRecord(hc->ev_chunk[k], hc->st_copy) != cudaSuccess) prod_err = 1;
+                produced = k + 1;
+            }
+        });
+    }
+    struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{producer};
+
+    const ProgHeader& h = p->prog.hdr();
+    uint64_t want_cap = chunk / 64 + 1024;
+    std::unique_ptr<rrx_matches> m(new rrx_matches);
+    m->owner = p->host;
+    uint64_t total = 0;
+    auto grow_result = [&](uint64_t need) -> int {         // page-locked result buffer with room for `need` pairs
+        if (m->pinned.p && m->pinned.pairs >= need) return RRX_OK;
+        HostCtx::Pinned nb = {nullptr, 0};
+        size_t best = hc->pool.size();
+        for (size_t i = 0; i < hc->pool.size(); i++)
+            if (hc->pool[i].pairs >= need && (best == hc->pool.size() || hc->pool[i].pairs < hc->pool[best].pairs)) best = i;
+        if (best != hc->pool.size()) { nb = hc->pool[best]; hc->pool.erase(hc->pool.begin() + (long)best); }
+        else {
+            const uint64_t pairs = need + need / 4 + 1024;
+            RRX_CUDA(cudaMallocHost(&nb.p, pairs * 16));
+            nb.pairs = pairs;
+        }
+        if (m->pinned.p) {
+            RRX_CUDA(cudaStreamSynchronize(hc->st));          // copies of earlier chunks' matches may still be in flight
+            std::memcpy(nb.p, m->pinned.p, total * 16);
+            if (hc->pool.size() < 4) hc->pool.push_back(m->pinned); else cudaFreeHost(m->pinned.p);
+        }
+        m->pinned = nb;
+        return RRX_OK;
+    };
+    int rc = grow_result(len / 200 + 4096);
+    if (rc) return rc;
+    uint32_t entry[RRX_NW_MAX];
+    for (uint32_t w = 0; w < RRX_NW_MAX; w++) entry[w] = 0u;
+    std::vector<uint32_t> summary(1 + 3 * (size_t)h.NW);
+    // A thread-owned program whose scan of some chunk fell back to the row-bounded scan (verification budget) starts over
+    // with the row-bounded scan for EVERY chunk: the two scans carry different things from chunk to chunk.
+    bool no_donly = false;
+    for (uint64_t k = 0; k < nchunks; k++) {
+        const uint64_t o = k * chunk, n = std::min(chunk, len - o);
+        while (produced.load() <= k && !prod_err.load()) std::this_thread::yield();
+        if (prod_err.load()) return set_err(RRX_ERR_CUDA, "streaming host scan: host-to-device copy failed");
+        RRX_CUDA(cudaStreamWaitEvent(hc->st, hc->ev_chunk[k], 0));
+        for (int attempt = 0;; attempt++) {
+            if (!hc->sc_chunk || hc->scc_len < chunk || hc->scc_cap < want_cap) {
+                if (hc->sc_chunk) { rrx_scanner_free(hc->sc_chunk); hc->sc_chunk = nullptr; }
+                rc = rrx_scanner_create(p, chunk, want_cap, &hc->sc_chunk);
+                if (rc) return rc;
+                hc->scc_len = chunk; hc->scc_cap = want_cap;
+            }
+            rrx_scan_opts so;
+            std::memset(&so, 0, sizeof(so));
+            so.left_context = o;                       // everything before the chunk is resident
+            so.entry = entry;
+            so.flags = no_donly ? RRX_SCAN_NO_DONLY : 0;
+            rc = rrx_scanner_scan(hc->sc_chunk, hc->d_text + o, n, base_offset + o, &so, hc->st);
+            rrx_scan_result r;
+            if (!rc) rc = rrx_scanner_result(hc->sc_chunk, &r, hc->st);
+            if (rc) return rc;
+            if (r.error_bits) return set_err(RRX_ERR_CUDA, "scan kernel reported error bits " + std::to_string(r.error_bits));
+            if (r.n_matches > r.capacity) {
+                if (attempt) return set_err(RRX_ERR_CUDA, "match buffer overflow after resize");
+                want_cap = r.n_matches + 1024;
+                continue;
+            }
+            if (!no_donly && rrx_scanner_used_fallback(hc->sc_chunk)) {
+                no_donly = true;
+                for (uint32_t w = 0; w < RRX_NW_MAX; w++) entry[w] = 0u;
+                total = 0;
+                k = (uint64_t)-1;                      // (the loop increment makes it 0)
+                break;
+            }
+            if (r.n_pending) return set_err(RRX_ERR_CUDA, "streaming host scan: a start walk left the resident text");
+            rc = grow_result(total + r.n_matches);
+            if (rc) return rc;
+            if (r.n_matches) RRX_CUDA(cudaMemcpyAsync(m->pinned.p + 2 * total, r.d_matches, r.n_matches * 16, cudaMemcpyDeviceToHost, hc->st));
+            total += r.n_matches;
+            // exit state of this chunk = entry of the next
+            rc = rrx_scanner_shard_summary(hc->sc_chunk, summary.data(), summary.size(), hc->st);
+            if (rc) return rc;
+            uint32_t nxt[RRX_NW_MAX];
+            apply_summary_host(h.NW, summary.data(), entry, nxt);
+            for (uint32_t w = 0; w < h.NW; w++) entry[w] = nxt[w];
+            break;
+        }
+    }
+    RRX_CUDA(cudaStreamSynchronize(hc->st));
+    m->count = total;
+    m->host_valid = true;
+    *out = m.release();
+    return RRX_OK;
+}
+
 int rrx_scan_host(const rrx_program* p, const uint8_t* text, uint64_t len, uint64_t base_offset,
                   int mode, rrx_matches** out) {
     if (!p || !out || (!text && len)) return set_err(RRX_ERR_ARG, "null argument");
@@ -741,6 +913,14 @@ int rrx_scan_host(const rrx_program* p, const uint8_t* text, uint64_t len, uint6
         const uint64_t cap = ((len + 16 + (1ull << 20) - 1) >> 20) << 20;
         RRX_CUDA(cudaMalloc(&hc->d_text, cap));
         hc->text_cap = cap;
+    }
+    // Long texts stream: the copy proceeds chunk by chunk on a stream of its own while the chunks that have arrived are
+    // scanned (state carried from chunk to chunk) and their matches copied back — see scan_host_streaming.
+    {
+        const char* ce = getenv("RRX_HOST_CHUNK");
+        const uint64_t chunk = ce ? (strtoull(ce, nullptr, 10) & ~4095ull) : (64ull << 20);
+        if (mode == RRX_MODE_LAZY_V1 && chunk >= (1ull << 20) && len >= 3 * chunk)
+            return scan_host_streaming(p, hc.get(), text, len, base_offset, chunk, out);
     }
     // the copy is enqueued first, so that whatever set-up follows overlaps it
     if (len) RRX_CUDA(cudaMemcpyAsync(hc->d_text, text, len, cudaMemcpyHostToDevice, hc->st));
@@ -863,6 +1043,41 @@ int rrx_scanner_digest(rrx_scanner* s, int64_t end_limit, uint64_t digest[4], vo
     if (rc) return rc;
     const uint64_t n = r.n_matches < r.capacity ? r.n_matches : r.capacity;
     return rrx_digest_device(r.d_matches, n, end_limit, digest, stream);
+}
+
+// Non-overlapping view of the scanner's last list, with the carry that chains chunks and shards (one
+// 8-byte "last selected end" passed left to right): keeps the matches with start >= *carry_io, in list order, each
+// selected match moving the carry to its end.
+int rrx_scanner_no_overlap(rrx_scanner* s, int64_t* carry_io, rrx_matches** out, void* stream) {
+    if (!s || !carry_io || !out) return set_err(RRX_ERR_ARG, "null argument");
+    rrx_scan_result r;
+    int rc = rrx_scanner_result(s, &r, stream);
+    if (rc) return rc;
+    if (r.error_bits) return set_err(RRX_ERR_CUDA, "scan kernel reported error bits " + std::to_string(r.error_bits));
+    if (r.n_matches > r.capacity) return set_err(RRX_ERR_ARG, "match buffer too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    std::unique_ptr<rrx_matches> m(new rrx_matches);
+    // matches that start before the carry cannot be selected and do not move it: drop them first (they form a
+    // prefix-closed condition only per match, so this is a plain filter), then the usual chain from the first survivor
+    longlong2* d_in2 = nullptr;
+    uint64_t n_in = 0;
+    cudaError_t ce = filter_start_ge(reinterpret_cast<const longlong2*>(r.d_matches), r.n_matches, *carry_io, &d_in2, &n_in, st);
+    if (ce != cudaSuccess) return cuda_err(ce, "rrx_scanner_no_overlap");
+    long long* d_in = reinterpret_cast<long long*>(d_in2);
+    long long* filtered = nullptr;
+    uint64_t nf = 0;
+    rc = filter_no_overlap(d_in, n_in, &filtered, &nf, st);
+    cudaFree(d_in);
+    if (rc) return rc;
+    m->d_pairs = filtered;
+    m->count = nf;
+    if (nf) {
+        long long last[2];
+        RRX_CUDA(cudaMemcpy(last, filtered + 2 * (nf - 1), 16, cudaMemcpyDeviceToHost));
+        *carry_io = last[1];
+    }
+    *out = m.release();
+    return RRX_OK;
 }
 
 int rrx_corpus_iid_device(uint8_t* d_out, uint64_t offset, uint64_t len, uint64_t seed, const uint8_t alpha[256], void* stream) {

@@ -85,4 +85,35 @@ cudaError_t launch_no_overlap(const longlong2* in, uint64_t n, longlong2* out, u
     return cudaGetLastError();
 }
 
+// Matches with start >= carry, in list order (the first step of the non-overlapping view of a chunk or shard that
+// inherits the "last selected end" of the text before it).  Allocates *out (cudaFree); synchronises `st`.
+struct StartGE {
+    long long c;
+    __host__ __device__ bool operator()(const longlong2& m) const { return m.x >= c; }
+};
+cudaError_t filter_start_ge(const longlong2* in, uint64_t n, long long carry, longlong2** out, uint64_t* n_out, cudaStream_t st) {
+    *out = nullptr;
+    *n_out = 0;
+    if (n == 0) return cudaSuccess;
+    if (n >= 0x7fffffffull) return cudaErrorInvalidValue;
+    size_t tb = 0;
+    unsigned long long* d_cnt = nullptr;
+    void* tmp = nullptr;
+    longlong2* d_out = nullptr;
+    cub::DeviceSelect::If((void*)nullptr, tb, in, d_out, d_cnt, (int)n, StartGE{carry}, st);
+    cudaError_t e = cudaMalloc(&tmp, tb + 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, n * 16);
+    if (e == cudaSuccess) e = cudaMalloc(&d_cnt, 8);
+    if (e == cudaSuccess) e = cub::DeviceSelect::If(tmp, tb, in, d_out, d_cnt, (int)n, StartGE{carry}, st);
+    unsigned long long cnt = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(tmp);
+    cudaFree(d_cnt);
+    if (e != cudaSuccess) { cudaFree(d_out); return e; }
+    *out = d_out;
+    *n_out = cnt;
+    return cudaSuccess;
+}
+
 }  // namespace rrx

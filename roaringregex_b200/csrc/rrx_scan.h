@@ -17,6 +17,7 @@ cudaError_t launch_accepts(uint32_t NW, const uint32_t* d_prog, const uint8_t* d
 size_t no_overlap_workspace_bytes(uint64_t n);
 cudaError_t launch_no_overlap(const longlong2* in, uint64_t n, longlong2* out, unsigned long long* d_n_out, void* workspace,
                               size_t workspace_bytes, cudaStream_t st);
+cudaError_t filter_start_ge(const longlong2* in, uint64_t n, long long carry, longlong2** out, uint64_t* n_out, cudaStream_t st);
 void fold_entry_host(uint32_t NW, const uint32_t* summaries, uint32_t n, uint32_t rank, uint32_t* entry_out, int* exact);
 void apply_summary_host(uint32_t NW, const uint32_t* s, const uint32_t* entry, uint32_t* out);
 cudaError_t launch_digest(const long long* d_pairs, uint64_t n, int64_t end_limit, unsigned long long* d_out4, cudaStream_t st);

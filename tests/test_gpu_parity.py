@@ -398,3 +398,74 @@ def test_offsets_beyond_4gib(rrx, oracle_api, torch_cuda):
         want = want[want[:, 1] > off + lo]
         sel = got[(got[:, 1] > off + lo) & (got[:, 1] <= off + lo + W)]
         assert np.array_equal(sel, want), lo
+
+
+def test_streaming_host_scan(rrx, oracle_api, torch_cuda, monkeypatch):
+    """rrx_scan_host on texts of several chunks (chunked H2D overlapped with scanning, state carried from chunk to
+    chunk; pageable input through pinned bounce buffers): identical to the oracle's one-piece list, for every config,
+    pinned and pageable host memory, chunk size forced down to 1 MiB so that small texts have many chunks."""
+    torch = torch_cuda
+    monkeypatch.setenv("RRX_HOST_CHUNK", str(1 << 20))
+    for cid, n in ((1, 5 << 20), (2, 9 << 20), ("2v", 9 << 20), (3, 7 << 20), (4, 4 << 20), (5, 9 << 20)):
+        cfg = CONFIGS[cid]
+        text = cpu_corpus(cfg, 0, n + 12345)
+        want = oracle_api.Oracle(cfg.pattern).lazy_matches(text)
+        r = rrx.RRegex(cfg.pattern)
+        got = r.scan_host(text)                                   # pageable numpy buffer
+        assert np.array_equal(got, want), (cid, "pageable")
+        pinned = torch.from_numpy(text).pin_memory()
+        got = r.scan_host(pinned.numpy())
+        assert np.array_equal(got, want), (cid, "pinned")
+        old = rrx.RRegex(cfg.pattern, rrx.COMPILE_NO_DONLY)
+        assert np.array_equal(old.scan_host(text), want), (cid, "row-bounded scan")
+    # the unbounded carry across every chunk, and a match whose start lies many chunks back
+    text = bytearray(b"a" * (6 << 20))
+    text[5] = ord("z")
+    text[-7] = ord("q")
+    want = oracle_api.Oracle("(x|y)*z.*q").lazy_matches(bytes(text))
+    assert want.tolist() == [[5, len(text) - 6]]
+    for flags in (0, rrx.COMPILE_NO_DONLY):
+        assert np.array_equal(rrx.RRegex("(x|y)*z.*q", flags).scan_host(bytes(text)), want), flags
+    # default chunk size (64 MiB) on a 300 MiB text
+    monkeypatch.delenv("RRX_HOST_CHUNK")
+    cfg = CONFIGS[2]
+    n = 300 << 20
+    d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    rrx.corpus_device(cfg, d.data_ptr(), 0, n)
+    host = d.cpu().numpy()
+    r = rrx.RRegex(cfg.pattern)
+    whole = r.scan_device(d.data_ptr(), n)
+    assert np.array_equal(r.scan_host(host), whole)
+
+
+def test_no_overlap_view_chunked(rrx, oracle_api, torch_cuda):
+    """rrx_scanner_no_overlap: the non-overlapping view computed piece by piece, the 8-byte carry (end of the last
+    selected match) passed from piece to piece, equals the oracle's filter over the whole text."""
+    torch = torch_cuda
+    rnd = random.Random(9)
+    text = bytearray(b"a" * 300000)
+    text[3] = ord("z")
+    for i in range(50, len(text), 211):
+        text[i] = ord("q")
+    cases = [("(x|y)*z.*q", bytes(text)), ("(a|b)*a(a|b){3}c", bytes(rnd.choices(b"abc", k=200000))), ("[ab]+c", bytes(rnd.choices(b"abc ", k=150000)))]
+    for cid, n in ((2, 3 << 20), (5, 2 << 20), (3, 2 << 20)):
+        cases.append((CONFIGS[cid].pattern, cpu_corpus(CONFIGS[cid], 0, n)))
+    for pat, txt in cases:
+        txt = np.frombuffer(bytes(txt), dtype=np.uint8)
+        want = oracle_api.Oracle(pat).no_overlap_matches(txt)
+        r = rrx.RRegex(pat)
+        d = torch.from_numpy(txt.copy()).cuda()
+        n = len(txt)
+        cuts = [0, (n // 3) & ~127, (2 * n // 3) & ~127, n]
+        sc = rrx.Scanner(r, n, n // 2 + 1024)
+        entry = np.zeros(r.info["words"], dtype=np.uint32)
+        from roaringregex_b200 import sharded
+        carry, parts = 0, []
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            sc.scan(d.data_ptr() + lo, hi - lo, lo, lo, entry)
+            assert sc.result()["error_bits"] == 0
+            entry = sharded.apply_summary(r, sc.shard_summary(), entry)
+            part, carry = sc.no_overlap(carry)
+            parts.append(part)
+        got = np.concatenate(parts)
+        assert got.shape == want.shape and np.array_equal(got, want), pat

@@ -370,7 +370,7 @@ def sub_record_sharded(rrx, torch, dist, cfg, peak, prefix, sh, rank, world, loc
         first_rank = next(i for i, z in enumerate(zs) if z >= 0)
         lo_fix = torch.tensor([0], device="cuda", dtype=torch.int64)
         if rank > first_rank:
-            zloc = (zs[rank] - off) if zs[rank] >= 0 else size
+            zloc = zs[rank] if zs[rank] >= 0 else size          # (closed_form_count reports shard-local offsets)
             lo_fix[0] = int((d_text[:zloc] == ord("q")).sum())
         dist.all_reduce(lo_fix)
         cf_total += int(lo_fix.item())
@@ -569,7 +569,8 @@ def main():
         del d_tmp
         e2e = {"value": e_size * world / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": e_size, "d2h_bytes_per_step": 16 * n_e,
                "bytes_scanned_per_rank": e_size, "ms_per_step": dt * 1e3, "pinned_h2d_copy_alone_gbs": h2d_gbs,
-               "call": "rrx_scan_host (C ABI) on a pinned host buffer: H2D copy, scan kernels, D2H of the match list into pinned memory"}
+               "call": "rrx_scan_host (C ABI) on a pinned host buffer: streaming ingestion — H2D in 64 MiB chunks on a copy stream, every chunk "
+                       "scanned as it arrives (state carried), its matches copied back to pinned memory"}
         if world == 1:
             # the same call on PAGEABLE memory — what the C++ drop-in's getline buffer is (src/test/main.cpp:17-26)
             pg = np.array(host_np, copy=True)

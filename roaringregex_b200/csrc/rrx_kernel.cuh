@@ -257,6 +257,57 @@ __device__ __forceinline__ unsigned long long reserve_segment(const ScanParams& 
 #define RRX_T(i)
 #endif
 
+// The slow tail of a tile — rows that received carried states, matches whose lazy start is not known yet: replay,
+// count, reserve, hit list, start walks — as ONE out-of-line function with by-value arguments.  It runs for a small
+// minority of the tiles; out of line it stays out of the instruction-cache lines the hot path lives in
+// (RRX_SLOW_INLINE puts it back, A/B).
+#ifdef RRX_SLOW_INLINE
+#define RRX_SLOW __device__ __forceinline__
+#else
+#define RRX_SLOW __device__ __noinline__
+#endif
+template <int NW, int CW, class F>
+RRX_SLOW void slow_tail(const ScanParams& sp, ProgView pv, F fw, TileState<NW, CW> ts, int lane, bool any_open, uint32_t tile) {
+    using TS = TileState<NW, CW>;
+        const uint32_t c = phase_b<NW>(sp, pv, fw, ts, lane, any_open);
+        // exclusive offsets of the rows' matches inside the tile
+        uint32_t inc_c = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, inc_c, d);
+            if (lane >= d) inc_c += v;
+        }
+        const uint32_t total = __shfl_sync(FULL, inc_c, 31);
+        const uint32_t offset = inc_c - c;
+        
+        // reserve the tile's segment of the staging list; the hit list is built while the atomic is in flight
+        unsigned long long base = 0;
+        if (lane == 0) base = reserve_segment(sp, tile, total);
+        
+        if (total) {
+            uint32_t hit[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) hit[q] = ts.hits[q * TILE_ROWS + lane];
+            __syncwarp();                 // every lane is done with the row summaries: reuse as hit list
+            const bool fits = total <= (uint32_t)TS::LIST_CAP;
+            if (fits) phase_c1_list<NW>(ts, lane, offset, hit);
+            __syncwarp();
+            if (lane == 0) {
+                sp.tile_seg[tile] = base;
+                sp.tile_cnt[tile] = total;
+            }
+            base = __shfl_sync(FULL, base, 0);
+            if (fits) {
+                phase_c2_balanced<NW>(sp, pv, fw, ts, lane, total, base);
+            } else {
+                phase_c2_rows<NW>(sp, pv, fw, ts, lane, offset, hit, base);
+            }
+        } else if (lane == 0) {
+            sp.tile_seg[tile] = 0;
+            sp.tile_cnt[tile] = 0;
+        }
+}
+
 // NW: words of a state set.  CW: words of a carried set (composites, row exits, look-back payloads); NW unless the
 // kernel is specialised for a thread-owned program with fewer dominated words (rrx_prog.h CW).
 template <int NW, int CW, class F, int WARPS>
@@ -678,43 +729,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
             }
             phase_tail_fast<NW>(sp, ts, lane, tail, base + (inc_c - tail.nacc));
         } else {
-            const uint32_t c = phase_b<NW>(sp, pv, fw, ts, lane, any_open);
-            // exclusive offsets of the rows' matches inside the tile
-            uint32_t inc_c = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(FULL, inc_c, d);
-                if (lane >= d) inc_c += v;
-            }
-            const uint32_t total = __shfl_sync(FULL, inc_c, 31);
-            const uint32_t offset = inc_c - c;
-            RRX_T(5)
-            // reserve the tile's segment of the staging list; the hit list is built while the atomic is in flight
-            unsigned long long base = 0;
-            if (lane == 0) base = reserve_segment(sp, tile, total);
-            RRX_T(6)
-            if (total) {
-                uint32_t hit[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) hit[q] = ts.hits[q * TILE_ROWS + lane];
-                __syncwarp();                 // every lane is done with the row summaries: reuse as hit list
-                const bool fits = total <= (uint32_t)TS::LIST_CAP;
-                if (fits) phase_c1_list<NW>(ts, lane, offset, hit);
-                __syncwarp();
-                if (lane == 0) {
-                    sp.tile_seg[tile] = base;
-                    sp.tile_cnt[tile] = total;
-                }
-                base = __shfl_sync(FULL, base, 0);
-                if (fits) {
-                    phase_c2_balanced<NW>(sp, pv, fw, ts, lane, total, base);
-                } else {
-                    phase_c2_rows<NW>(sp, pv, fw, ts, lane, offset, hit, base);
-                }
-            } else if (lane == 0) {
-                sp.tile_seg[tile] = 0;
-                sp.tile_cnt[tile] = 0;
-            }
+            slow_tail<NW, CW, F>(sp, pv, fw, ts, lane, any_open, tile);
         }
         __syncwarp();
         RRX_T(7)

@@ -5,6 +5,10 @@
  * (file:line relative to the RoaringRegex tree).  librrx.so has NO CPU scanning path: every
  * rrx_scan* call runs the sm_100a kernels or fails with RRX_ERR_CUDA.
  *
+ * Anchors: `^` / `$` hold at the ends of the text handed to a one-shot call (rrx_scan_host / rrx_scan_device): the
+ * text is framed by one virtual 0x00 byte on each side that only the anchor positions consume (the
+ * reference compiles them to a transition on 0x00 that it never feeds, so there they never match).
+ *
  * Match semantics: "LAZY-v1" (DESIGN.md / SURVEY.md Appendix D): for every end offset e such that
  * some text[s:e], s<e, is in the language, exactly one match (max such s, e); ascending e.
  * Offsets are 64-bit, half-open, global (base_offset + position in the buffer).

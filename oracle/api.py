@@ -103,6 +103,29 @@ class Oracle:
                 return out[:m].copy()
             cap = int(m)
 
+    def lazy_matches_anchored(self, text) -> np.ndarray:
+        """LAZY-v1 with working anchors (the extension DESIGN.md §8 defines; the reference never matches them,
+        regex.h:157): the text is framed by ONE virtual 0x00 on each side which only the anchor atoms consume; the list
+        of the framed text is mapped back to text coordinates (virtual bytes clipped), empty matches dropped, one match
+        per end (the one with the larger start).  The text must not contain 0x00."""
+        buf = _as_u8(text)
+        n = len(buf)
+        assert not (buf == 0).any()
+        framed = np.concatenate([np.zeros(1, np.uint8), buf, np.zeros(1, np.uint8)])
+        o = Oracle.__new__(Oracle)
+        o.pattern, o.raw = self.pattern, self.raw.anchored_view()
+        o._table, o._finals = o.raw.export_table()
+        o._s = _RawNFA(o.raw.n, o.raw.words(), o.raw.init, o._table.ctypes.data, o._finals.ctypes.data)
+        m = o.lazy_matches(framed, base=-1)
+        if len(m) == 0:
+            return m
+        s, e = np.maximum(m[:, 0], 0), np.minimum(m[:, 1], n)
+        best = {}
+        for a, b in zip(s.tolist(), e.tolist()):
+            if a < b and best.get(b, -1) < a:
+                best[b] = a
+        return np.array([[best[b], b] for b in sorted(best)], dtype=np.int64).reshape(-1, 2)
+
     def no_overlap_matches(self, text, base: int = 0) -> np.ndarray:
         """The non-overlapping view of the LAZY-v1 list."""
         m = np.ascontiguousarray(self.lazy_matches(text, base))

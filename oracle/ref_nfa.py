@@ -85,6 +85,35 @@ class RawNFA:
         fin = np.array([(self.finals >> (64 * w)) & mask for w in range(W)], dtype=np.uint64)
         return tab, fin
 
+    def anchored_view(self) -> "RawNFA":
+        """The same automaton with its byte-0x00 transitions restricted to ANCHOR atoms (`^`, `$`: Parser.cpp:142-146
+        compiles both to a literal 0x00), for scanning a text framed by virtual 0x00 bytes: `.` and negated classes,
+        which also contain 0x00, must not consume those.  An anchor atom's own final state t* is entered on byte 0 and
+        on no other byte; the construction (skip<bwd>, NFA.cc:108-137) copies every transition into t* to the states
+        that follow the atom, so a byte-0 edge s -> T belongs to the anchor iff s enters t* on byte 0 and every source
+        of t* on byte 0 also enters T on byte 0.  (Limitation: a broad class in alternation with an anchor AND with the
+        same continuation — `(^|.)a` — cannot be told apart from the tables alone and keeps its edge; the tests avoid it.)"""
+        incoming = defaultdict(int)
+        for (s, c), v in self.fwd.items():
+            for t in _bits(v):
+                incoming[t] |= 1 << c
+        own = [t for t, m in incoming.items() if m == 1]
+        pre = {t: self.bwd.get((t, 0), 0) for t in own}
+        fwd, bwd = {}, defaultdict(int)
+        for (s, c), v in self.fwd.items():
+            if c == 0:
+                keep = 0
+                for T in _bits(v):
+                    srcT = self.bwd.get((T, 0), 0)
+                    if any((p >> s) & 1 and (p & ~srcT) == 0 for p in pre.values()):
+                        keep |= 1 << T
+                v = keep
+            if v:
+                fwd[(s, c)] = v
+                for t in _bits(v):
+                    bwd[(t, c)] |= 1 << s
+        return RawNFA(self.n, self.init, self.finals, fwd, dict(bwd))
+
     def dump_forward(self):
         """{state: {byte: sorted targets}} for non-empty forward rows (what NFA::print shows)."""
         out = defaultdict(dict)

@@ -259,7 +259,7 @@ static rrx_scanner* act(rrx_scanner* s) { return (s && s->use_alt && s->alt) ? s
 void rrx_scanner_free(rrx_scanner* s) {
     if (!s) return;
     if (s->alt) { rrx_scanner_free(s->alt); s->alt = nullptr; }
-    cudaFree(s->d_prog); cudaFree(s->d_ctrl); cudaFree(s->d_tpay);
+    cudaFree(s->d_prog); cudaFree(s->d_ctrl);          // (d_tpay lives inside d_ctrl's allocation)
     if (s->owns_out) cudaFree(s->d_out);
     cudaFree(s->d_stage); cudaFree(s->d_tile_seg); cudaFree(s->d_tile_cnt); cudaFree(s->d_chunk);
     cudaFree(s->d_shard); cudaFree(s->d_pending);
@@ -317,8 +317,9 @@ int rrx_scanner_create_ex(const rrx_program* p, uint64_t max_len, uint64_t capac
     RRX_CUDA(cudaMalloc(&s->d_prog, p->prog.blob.size() * 4));
     RRX_CUDA(cudaMemcpy(s->d_prog, p->prog.blob.data(), p->prog.blob.size() * 4, cudaMemcpyHostToDevice));
     s->ctrl_bytes = ctrl_layout(s->max_tiles, nullptr);
-    RRX_CUDA(cudaMalloc(&s->d_ctrl, s->ctrl_bytes));
-    RRX_CUDA(cudaMalloc(&s->d_tpay, (2 * s->max_tiles + 2 * ((s->max_tiles + 31) / 32)) * (1 + 3 * (size_t)h.NW) * 4));
+    // control block and look-back payloads in ONE allocation: a scan places the payloads right behind the part of the
+    // control block it uses, so that one memset zeroes both (payloads with the ready bit inside need it)
+    RRX_CUDA(cudaMalloc(&s->d_ctrl, s->ctrl_bytes + 256 + (2 * s->max_tiles + 2 * ((s->max_tiles + 31) / 32)) * (1 + 3 * (size_t)h.NW) * 4));
     RRX_CUDA(cudaMalloc(&s->d_out, s->capacity * 16));
     // staging list: fixed slots for tiles with few matches (at most capacity/2, see rrx_scanner_scan) in
     // front of an overflow area that can hold every match
@@ -327,6 +328,7 @@ int rrx_scanner_create_ex(const rrx_program* p, uint64_t max_len, uint64_t capac
     RRX_CUDA(cudaMalloc(&s->d_tile_cnt, s->max_tiles * 4));
     RRX_CUDA(cudaMalloc(&s->d_chunk, ((s->max_tiles + 1023) / 1024 + 1) * 8));
     RRX_CUDA(cudaMalloc(&s->d_shard, (1 + 3 * (size_t)h.NW) * 4));
+    if (h.n_anchor) s->pending_cap = 1u << 16;      // a start-anchored thread that is carried far ends every one of its matches' start walks at the text start
     RRX_CUDA(cudaMalloc(&s->d_pending, sizeof(PendingStart) * s->pending_cap));
     RRX_CUDA(cudaMallocHost(&s->h_ctr, 32 + 4 * (1 + 3 * (size_t)RRX_NW_MAX)));
     {
@@ -458,6 +460,7 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     sp.tile_stop = (h.donly && h.rskip_n) ? reinterpret_cast<volatile uint32_t*>(c + off[5]) : nullptr;
     sp.tile_seg = s->d_tile_seg;
     sp.tile_cnt = s->d_tile_cnt;
+    s->d_tpay = reinterpret_cast<uint32_t*>(c + ((used + 255) & ~(size_t)255));
     sp.st_a0 = s->d_tpay;
     sp.st_i0 = sp.st_a0 + T * PW;
     sp.st_a1 = sp.st_i0 + T * PW;
@@ -480,9 +483,9 @@ int rrx_scanner_scan(rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64
     s->launches = 0;
     s->last_base = (int64_t)base_offset;
     s->h_shard_valid = false;
-    RRX_CUDA(cudaMemsetAsync(s->d_ctrl, 0, used, st));
-    if (cw == 1)        // one-word composites keep the ready bit inside their 16-byte words
-        RRX_CUDA(cudaMemsetAsync(s->d_tpay, 0, (2 * T + 2 * B) * PW * 4, st));
+    // one memset: the control block, and — one-word composites keep the ready bit inside their 16-byte words — the
+    // look-back payloads behind it
+    RRX_CUDA(cudaMemsetAsync(s->d_ctrl, 0, cw == 1 ? ((used + 255) & ~(size_t)255) + (2 * T + 2 * B) * PW * 4 : used, st));
     if (sp.num_tiles == 0) {
         // empty text: identity transfer function, no matches
         uint32_t ident[1 + 3 * RRX_NW_MAX] = {K_IDENT};
@@ -589,10 +592,13 @@ int rrx_scanner_copy_pending(rrx_scanner* s, void* host_out, uint64_t cap, uint6
         // (tile, rank in tile) -> index in the ordered match list: the ordering pass left every tile's
         // offset in d_tile_seg
         PendingStart* recs = reinterpret_cast<PendingStart*>(host_out);
+        uint64_t t_lo = ~0ull, t_hi = 0;
+        for (uint64_t i = 0; i < n; i++) { const uint64_t t = recs[i].match_index >> 32; t_lo = t < t_lo ? t : t_lo; t_hi = t > t_hi ? t : t_hi; }
+        std::vector<unsigned long long> segs(t_hi - t_lo + 1);          // the tiles' offsets in the ordered list, one copy
+        RRX_CUDA(cudaMemcpy(segs.data(), s->d_tile_seg + t_lo, segs.size() * 8, cudaMemcpyDeviceToHost));
         for (uint64_t i = 0; i < n; i++) {
             const uint64_t tile = recs[i].match_index >> 32, rank = recs[i].match_index & 0xffffffffull;
-            unsigned long long off = 0;
-            RRX_CUDA(cudaMemcpy(&off, s->d_tile_seg + tile, 8, cudaMemcpyDeviceToHost));
+            const unsigned long long off = segs[tile - t_lo];
             recs[i].match_index = off + rank;
             recs[i].next_offset += s->last_base;          // shard-local -> global
         }
@@ -687,18 +693,28 @@ void rrx_scanner_peek(rrx_scanner* s, const int64_t** d_matches, uint64_t* capac
     *capacity = s->capacity;
 }
 
+// (anchors: defined further down)
+static bool anchor_entry(const rrx_program* p, uint32_t* entry);
+static int anchor_fixups(const rrx_program* p, rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64_t base, const uint32_t* entry,
+                         const rrx_scan_result& r, void* stream, int* extra, int64_t* extra_pair);
+static int anchor_merge_extra(long long* d_pairs, uint64_t* count, const int64_t* ep);
+
 // ---- one-shot convenience calls ----------------------------------------------------------------------
 int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, uint64_t base_offset,
                     int mode, rrx_matches** out, void* stream) {
     if (!p || !out) return set_err(RRX_ERR_ARG, "null argument");
     if (mode != RRX_MODE_LAZY_V1 && mode != RRX_MODE_NO_OVERLAP) return set_err(RRX_ERR_ARG, "unknown mode");
     uint64_t cap = len / 64 + 1024;
+    uint32_t aentry[RRX_NW_MAX];
+    const bool anchored = p->prog.hdr().n_anchor != 0;
+    const bool a_entry = anchor_entry(p, aentry);
     for (int attempt = 0; attempt < 2; attempt++) {
         rrx_scanner* s = nullptr;
-        int rc = rrx_scanner_create(p, len, cap, &s);
+        int rc = rrx_scanner_create(p, len, cap + 1, &s);          // (+1: room for the match of a trailing anchor)
         if (rc) return rc;
         rrx_scan_opts o;
         std::memset(&o, 0, sizeof(o));
+        if (a_entry) o.entry = aentry;
         rc = rrx_scanner_scan(s, d_text, len, base_offset, &o, stream);
         rrx_scan_result r;
         if (!rc) rc = rrx_scanner_result(s, &r, stream);
@@ -707,13 +723,23 @@ int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, u
             rrx_scanner_free(s);
             return set_err(RRX_ERR_CUDA, "scan kernel reported error bits " + std::to_string(r.error_bits));
         }
-        if (r.n_matches <= r.capacity) {
+        if (r.n_matches <= cap) {
+            int extra = 0;
+            int64_t ep[2];
+            if (anchored) {
+                rc = anchor_fixups(p, s, d_text, len, base_offset, aentry, r, stream, &extra, ep);
+                if (rc) { rrx_scanner_free(s); return rc; }
+            }
             rrx_matches* m = new rrx_matches;
             m->count = r.n_matches;
             rrx_scanner* owner = act(s);              // the list may live in the fallback scanner
             m->d_pairs = owner->d_out;
             owner->owns_out = false;
             rrx_scanner_free(s);
+            if (extra) {
+                rc = anchor_merge_extra(m->d_pairs, &m->count, ep);
+                if (rc) { rrx_matches_free(m); return rc; }
+            }
             if (mode == RRX_MODE_NO_OVERLAP) {
                 long long* filtered = nullptr;
                 uint64_t nf = 0;
@@ -730,6 +756,122 @@ int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, u
         rrx_scanner_free(s);
     }
     return set_err(RRX_ERR_CUDA, "match buffer overflow after resize");
+}
+
+// ---- anchors ---------------------------------------------------------------------------------
+// `^` / `$` are positions whose class is exactly {0x00} (the reference's construction, Parser.cpp:142-146).  The one-shot
+// calls frame the text with one virtual 0x00 on each side that only those positions consume:
+//   leading byte  = an entry set for the scan: first ∩ anch ("the state after the virtual byte");
+//                   a lazy start walk that reaches the text start and could consume the virtual byte there started at
+//                   offset 0 (pending records are resolved on the host);
+//   trailing byte = one virtual step from the text's exit state; if it accepts, one more match ends at `len`, its lazy
+//                   start found by the ordinary backward walk (rrx_continue_starts) from the byte before.
+// Matches are reported in text coordinates (the virtual bytes are clipped); empty matches are not reported.
+namespace {
+struct AnchorView {
+    const ProgHeader* h;
+    const uint32_t* b;
+    uint32_t NW;
+    bool meets(const uint32_t* x, uint32_t off) const { uint32_t o = 0; for (uint32_t w = 0; w < NW; w++) o |= x[w] & b[off + w]; return o != 0; }
+    void rows(const uint32_t* S, uint32_t off_rows, uint32_t* out) const {            // OR of the table rows of the set bits of S
+        for (uint32_t w = 0; w < NW; w++) out[w] = 0;
+        for (uint32_t k = 0; k < h->P; k++)
+            if ((S[k >> 5] >> (k & 31)) & 1u) for (uint32_t w = 0; w < NW; w++) out[w] |= b[off_rows + k * NW + w];
+    }
+};
+}  // namespace
+
+// entry set that stands for the leading virtual byte (all zero if the program has no start anchor)
+static bool anchor_entry(const rrx_program* p, uint32_t* entry) {
+    const ProgHeader& h = p->prog.hdr();
+    const uint32_t* b = p->prog.blob.data();
+    bool any = false;
+    for (uint32_t w = 0; w < RRX_NW_MAX; w++) entry[w] = 0;
+    if (!h.n_anchor) return false;
+    for (uint32_t w = 0; w < h.NW; w++) { entry[w] = b[h.off_first + w] & b[h.off_anch + w]; any = any || entry[w]; }
+    return any;
+}
+
+// After the scan of a whole text [0,len) with anchor_entry() as entry: resolve walks that reached the text start,
+// take the trailing virtual step.  *extra = 1 and extra_pair = (start,end) if one more match ends at base+len.
+static int anchor_fixups(const rrx_program* p, rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64_t base, const uint32_t* entry,
+                         const rrx_scan_result& r, void* stream, int* extra, int64_t* extra_pair) {
+    const ProgHeader& h = p->prog.hdr();
+    AnchorView av{&h, p->prog.blob.data(), h.NW};
+    *extra = 0;
+    uint32_t fa[RRX_NW_MAX];                            // first ∩ anch
+    for (uint32_t w = 0; w < h.NW; w++) fa[w] = av.b[h.off_first + w] & av.b[h.off_anch + w];
+    rrx_scanner* sa = act(s);
+    // (a) start walks that ran off the text start
+    if (r.n_pending) {
+        std::vector<PendingStart> recs(r.n_pending);
+        uint64_t n = 0;
+        int rc = rrx_scanner_copy_pending(s, recs.data(), recs.size(), &n, stream);
+        if (rc) return rc;
+        if (n != r.n_pending) return set_err(RRX_ERR_CUDA, "too many start walks reach the text start");
+        const long long st0 = (long long)base;
+        for (uint64_t i = 0; i < n; i++) {
+            uint32_t o = 0;
+            for (uint32_t w = 0; w < h.NW; w++) o |= recs[i].R[w] & fa[w];
+            if (!o) return set_err(RRX_ERR_CUDA, "a start walk left the text without a start anchor to end at");
+            RRX_CUDA(cudaMemcpyAsync(sa->d_out + 2 * recs[i].match_index, &st0, 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        }
+        RRX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    }
+    if (len == 0) return RRX_OK;
+    // (b) the trailing virtual byte
+    std::vector<uint32_t> summary(1 + 3 * (size_t)h.NW);
+    int rc = rrx_scanner_shard_summary(s, summary.data(), summary.size(), stream);
+    if (rc) return rc;
+    uint32_t S[RRX_NW_MAX], f[RRX_NW_MAX], V[RRX_NW_MAX], x[RRX_NW_MAX], R[RRX_NW_MAX];
+    apply_summary_host(h.NW, summary.data(), entry, S);
+    // the scan's own exit set may lack states outside the dominated set (thread-owned programs): those cannot reach an
+    // accepting anchor position in one step (its predecessors are dominated), so they do not matter here
+    av.rows(S, h.off_follow, f);
+    bool acc = false, any_x = false, only_virtual = false;
+    for (uint32_t w = 0; w < h.NW; w++) {
+        V[w] = (f[w] | av.b[h.off_first + w]) & av.b[h.off_anch + w];
+        if (V[w] & av.b[h.off_accept + w]) acc = true;
+        x[w] = av.b[h.off_accept + w] & av.b[h.off_anch + w];
+        any_x = any_x || x[w];
+        if (x[w] & av.b[h.off_first + w]) only_virtual = true;      // the lazy (shortest) match is the virtual byte alone: empty
+    }
+    if (!acc || !any_x || only_virtual) return RRX_OK;
+    av.rows(x, h.off_rfollow, R);
+    PendingStart rec;
+    std::memset(&rec, 0, sizeof(rec));
+    rec.next_offset = (int64_t)(base + len) - 1;
+    for (uint32_t w = 0; w < h.NW; w++) rec.R[w] = R[w];
+    int64_t start = -1;
+    rc = rrx_continue_starts(p, d_text, len, 0, base, &rec, 1, &start, stream);
+    if (rc) return rc;
+    if (start == -1) {                                   // reached the text start: the leading virtual byte
+        uint32_t o = 0;
+        for (uint32_t w = 0; w < h.NW; w++) o |= rec.R[w] & fa[w];
+        if (!o) return RRX_OK;
+        start = (int64_t)base;
+    }
+    if (start < 0 || start >= (int64_t)(base + len)) return RRX_OK;
+    *extra = 1;
+    extra_pair[0] = start;
+    extra_pair[1] = (int64_t)(base + len);
+    return RRX_OK;
+}
+
+// merge the match of the trailing virtual byte into the ordered device list (room for one more pair is guaranteed by the
+// callers): LAZY-v1 keeps one match per end, the one with the larger start
+static int anchor_merge_extra(long long* d_pairs, uint64_t* count, const int64_t* ep) {
+    if (*count) {
+        long long last[2];
+        RRX_CUDA(cudaMemcpy(last, d_pairs + 2 * (*count - 1), 16, cudaMemcpyDeviceToHost));
+        if (last[1] == ep[1]) {
+            if (ep[0] > last[0]) RRX_CUDA(cudaMemcpy(d_pairs + 2 * (*count - 1), ep, 8, cudaMemcpyHostToDevice));
+            return RRX_OK;
+        }
+    }
+    RRX_CUDA(cudaMemcpy(d_pairs + 2 * *count, ep, 16, cudaMemcpyHostToDevice));
+    (*count)++;
+    return RRX_OK;
 }
 
 // ---- streaming host scan ------------------------------------------------------------------
@@ -919,12 +1061,15 @@ int rrx_scan_host(const rrx_program* p, const uint8_t* text, uint64_t len, uint6
     {
         const char* ce = getenv("RRX_HOST_CHUNK");
         const uint64_t chunk = ce ? (strtoull(ce, nullptr, 10) & ~4095ull) : (64ull << 20);
-        if (mode == RRX_MODE_LAZY_V1 && chunk >= (1ull << 20) && len >= 3 * chunk)
+        if (mode == RRX_MODE_LAZY_V1 && chunk >= (1ull << 20) && len >= 3 * chunk && p->prog.hdr().n_anchor == 0)
             return scan_host_streaming(p, hc.get(), text, len, base_offset, chunk, out);
     }
     // the copy is enqueued first, so that whatever set-up follows overlaps it
     if (len) RRX_CUDA(cudaMemcpyAsync(hc->d_text, text, len, cudaMemcpyHostToDevice, hc->st));
     uint64_t want_cap = len / 64 + 1024;
+    uint32_t aentry[RRX_NW_MAX];
+    const bool anchored = p->prog.hdr().n_anchor != 0;
+    const bool a_entry = anchor_entry(p, aentry);
     for (int attempt = 0; attempt < 2; attempt++) {
         if (!hc->sc || hc->sc_len < len || hc->sc_cap < want_cap) {
             if (hc->sc) { rrx_scanner_free(hc->sc); hc->sc = nullptr; }
@@ -935,15 +1080,26 @@ int rrx_scan_host(const rrx_program* p, const uint8_t* text, uint64_t len, uint6
         }
         rrx_scan_opts o;
         std::memset(&o, 0, sizeof(o));
+        if (a_entry) o.entry = aentry;
         int rc = rrx_scanner_scan(hc->sc, hc->d_text, len, base_offset, &o, hc->st);
         rrx_scan_result r;
         if (!rc) rc = rrx_scanner_result(hc->sc, &r, hc->st);
         if (rc) return rc;
         if (r.error_bits) return set_err(RRX_ERR_CUDA, "scan kernel reported error bits " + std::to_string(r.error_bits));
-        if (r.n_matches > r.capacity) { want_cap = r.n_matches + 1024; continue; }    // exact size known now: scan again
+        if (r.n_matches + 1 > r.capacity) { want_cap = r.n_matches + 1024; continue; }    // exact size known now: scan again
         std::unique_ptr<rrx_matches> m(new rrx_matches);
         m->count = r.n_matches;
         m->owner = hc;
+        if (anchored) {
+            int extra = 0;
+            int64_t ep[2];
+            rc = anchor_fixups(p, hc->sc, hc->d_text, len, base_offset, aentry, r, hc->st, &extra, ep);
+            if (rc) return rc;
+            if (extra) {
+                rc = anchor_merge_extra(act(hc->sc)->d_out, &m->count, ep);
+                if (rc) return rc;
+            }
+        }
         long long* filtered = nullptr;
         if (mode == RRX_MODE_NO_OVERLAP) {
             uint64_t nf = 0;

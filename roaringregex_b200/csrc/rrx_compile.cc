@@ -313,6 +313,7 @@ bool merge_round(std::vector<Pos>& v) {
                 key.push_back((uint32_t)v[k].cls[1]); key.push_back((uint32_t)(v[k].cls[1] >> 32));
             } else {
                 key.push_back(v[k].first ? 1u : 0u);
+                key.push_back((v[k].cls[0] == 1ull && v[k].cls[1] == 0ull) ? 1u : 0u);     // an anchor (class {0x00}) only merges with anchors
                 for (uint32_t w = 0; w < (n + 31) / 32; w++) key.push_back(pred[k].word(w));
             }
             for (uint32_t w = 0; w < (n + 31) / 32; w++) key.push_back(v[k].follow.word(w));
@@ -801,9 +802,11 @@ Program build_program(const Automaton& a, const std::string& pattern, bool reduc
     // supported state-set widths: 1,2,4,8,16,32 words of 32 bits
     uint32_t NW = 1;
     while (NW * 32 < P) NW *= 2;
-    if (allow_donly && NW > 1) {
+    if (NW > 1) {
         // Multi-word automaton: number the positions a cut dominates FIRST (stable otherwise), so that everything
         // the thread-owned scan carries fits the first CW words (rrx_prog.h).  Renumbering changes no language.
+        // (Done whether or not the thread-owned scan is allowed: a scanner's fallback program must number the positions
+        // like its primary one — entry sets and composites pass between the two.)
         Bits first0(P), accept0(P);
         std::vector<Bits> fol0(P, Bits(P)), rfol0(P, Bits(P));
         for (uint32_t k = 0; k < P; k++) { if (pos[k].first) first0.add(k); if (pos[k].accept) accept0.add(k); }
@@ -910,6 +913,7 @@ Program build_program(const Automaton& a, const std::string& pattern, bool reduc
     h.off_follow = take(P * NW); h.off_rfollow = take(P * NW);
     h.off_rows = take(P * NW); h.off_rrows = take(P * NW);
     h.off_rfull = take(P * NW);
+    h.off_anch = take(NW);
     h.total_words = off;
 
     Program pr;
@@ -927,6 +931,12 @@ Program build_program(const Automaton& a, const std::string& pattern, bool reduc
             put_bits(pr.blob, o + NW, cut.groups[g].pred, NW);
             pr.blob[o + 2 * NW] = cut.groups[g].flags;
         }
+    }
+    {
+        Bits anch(P);
+        for (uint32_t k = 0; k < P; k++) if (pos[k].cls[0] == 1ull && pos[k].cls[1] == 0ull) anch.add(k);
+        put_bits(pr.blob, h.off_anch, anch, NW);
+        reinterpret_cast<ProgHeader*>(pr.blob.data())->n_anchor = anch.count();
     }
     if (rskip.n) put_bits(pr.blob, h.off_rskip, rskip.F, NW);
     if (fskip.n) put_bits(pr.blob, h.off_fskip, fskip.G, NW);

@@ -64,7 +64,11 @@ struct ProgHeader {
     // for the program keeps its composites, row summaries and look-back payloads CW words wide.  Generic kernels
     // use NW.  (Everything that leaves the scanner — shard summaries, entry sets — stays NW words wide.)
     uint32_t CW;
-    uint32_t pad2[2];
+    // Anchors.  The reference compiles `^` and `$` to a transition on byte 0x00 (Parser.cpp:142-146) that its iterator
+    // never feeds.  Here the text is framed by ONE virtual 0x00 on each side which only those positions consume:
+    // off_anch = the positions whose class is exactly {0x00} (NW words), n_anchor their number.  The one-shot scan
+    // calls turn the leading virtual byte into an entry set and the trailing one into a final virtual step (rrx_capi.cu).
+    uint32_t n_anchor, off_anch;
 };
 constexpr uint32_t RRX_MAX_GROUPS = 4;
 

@@ -469,3 +469,34 @@ def test_no_overlap_view_chunked(rrx, oracle_api, torch_cuda):
             parts.append(part)
         got = np.concatenate(parts)
         assert got.shape == want.shape and np.array_equal(got, want), pat
+
+
+def test_anchors(rrx, oracle_api, torch_cuda):
+    """`^` and `$`: the one-shot scan calls frame the text with one virtual 0x00 on each side that
+    only the anchor positions consume; the oracle does the same on the reference's tables (lazy_matches_anchored).
+    Multi-line texts: the anchors hold at the text's ends only, as in POSIX ERE without REG_NEWLINE."""
+    torch = torch_cuda
+    rnd = random.Random(12)
+    pats = ["^ab", "ab$", "^ab$", "(^|x)ab", "(x|^)ab", "ab($|c)", "^a+b|cd$", "^.*b", "[^x]b$", "^(ab|cd)*e", "(ab|cd)*e$",
+            "^[a-z]+@[a-z]+\\.(com|org|net)", "[a-z]+@[a-z]+\\.(com|org|net)$", "^a{1,100}b", "a{1,100}b$", "a*$", "^", "$", "^$", "x^a", "a$b"]
+    texts = [b"", b"a", b"ab", b"ab xab ab", b"abc ab", b"aab cd aab cd", b"ab\nab\nab", b"abab" * 50 + b"e",
+             b"bob@example.com and ann@site.org", b"zed@q.net", b"a" * 300 + b"b", b"cdabe cd"]
+    for n in (127, 128, 129, 4096, 5000, 70000):
+        texts.append(bytes(rnd.choices(b"abcde x\n", k=n)))
+        texts.append(b"ab" + bytes(rnd.choices(b"abcd \n", k=n)) + b"ab")
+    for pat in pats:
+        o = oracle_api.Oracle(pat)
+        for flags in (0, rrx.COMPILE_NO_DONLY):
+            r = rrx.RRegex(pat, flags)
+            for txt in texts:
+                want = o.lazy_matches_anchored(txt)
+                got = r.scan_host(txt)
+                assert got.shape == want.shape and np.array_equal(got, want), (pat, flags, txt[:40], got[:4].tolist(), want[:4].tolist())
+                if len(txt):
+                    d = torch.tensor(np.frombuffer(txt, dtype=np.uint8), device="cuda")
+                    assert np.array_equal(r.scan_device(d.data_ptr(), len(txt)), want), (pat, flags, "device")
+    # a long text: the anchored thread of `^.*b` is carried through every tile
+    txt = b"a" * 200000 + b"b" + b"a" * 1000 + b"b"
+    for pat in ("^.*b", "a.*b$", "^a*b"):
+        want = oracle_api.Oracle(pat).lazy_matches_anchored(txt)
+        assert np.array_equal(rrx.RRegex(pat).scan_host(txt), want), pat

@@ -245,6 +245,7 @@ def _scan_sharded(regex: RRegex, backend, comm, rank: int, world: int, fetch: bo
     else:
         spec, first_gather = backend.scan(backend.len, None, fetch, **kw), None     # speculative: empty entry
     advertised, result, last_entry = spec, None, None
+    consumed = False              # a whole-shard rescan has overwritten the speculative scan's device buffers
     for _round in range(max(world, 1)):
         if _round == 0 and first_gather is not None:
             gathered = first_gather
@@ -260,9 +261,10 @@ def _scan_sharded(regex: RRegex, backend, comm, rank: int, world: int, fetch: bo
         if result is None or not np.array_equal(entry, last_entry):
             last_entry = entry
             if entry.any():
-                result = _repair(regex, backend, spec, entry, fetch, kw)
+                result = _repair(regex, backend, spec, entry, fetch, kw, force_full=consumed)
                 if result.rescans == 2:
                     advertised = result.tail                      # now computed with the exact entry
+                    consumed = True                               # later rounds must not splice onto the stale speculative list
             else:
                 result = ShardResult(spec.n, np.zeros((0, 2), np.int64), 0, spec, 0,
                                      [("tail", i, nxt, R) for i, nxt, R in spec.pending])
@@ -274,7 +276,13 @@ def _scan_sharded(regex: RRegex, backend, comm, rank: int, world: int, fetch: bo
     return result
 
 
-def _repair(regex, backend, spec: ShardScan, entry: np.ndarray, fetch: bool, kw: dict) -> ShardResult:
+def _repair(regex, backend, spec: ShardScan, entry: np.ndarray, fetch: bool, kw: dict, force_full: bool = False) -> ShardResult:
+    if force_full:
+        kw2 = dict(kw)
+        if isinstance(backend, DeviceBackend) and spec.handle is not None:
+            kw2["scanner"] = spec.handle
+        full = backend.scan(backend.len, entry, fetch, **kw2)
+        return ShardResult(full.n, np.zeros((0, 2), np.int64), 0, full, 2, [("tail", i, nxt, R) for i, nxt, R in full.pending])
     window = min(backend.len, PREFIX_WINDOW)
     if window < backend.len:
         window -= window % 4096

@@ -99,3 +99,28 @@ def test_lazy_against_python_re(oracle_api):
                         want.append([s, e])
                         break
             assert o.lazy_matches(t.encode()).tolist() == want, (pat, t)
+
+
+def test_anchored_oracle_against_python_re(oracle_api):
+    """The anchored extension of the oracle (virtual 0x00 bytes that only anchor atoms consume) against a brute force
+    with Python `re`: `^X` = X matching from offset 0 only, `X$` = X matching up to the text's end only."""
+    import random
+    import re
+    rnd = random.Random(3)
+    for body, alpha in [("ab", b"ab "), ("a+b", b"ab "), ("(ab|cd)*e", b"abcde "), ("[a-c]+x", b"abcx "), ("a.c", b"abc\n")]:
+        rx = re.compile(body.encode(), re.S)
+        for _ in range(40):
+            n = rnd.randint(0, 40)
+            t = bytes(rnd.choices(alpha, k=n))
+            for kind, pat in (("^", "^" + body), ("$", body + "$"), ("^$", "^" + body + "$")):
+                want = []
+                for e in range(1, n + 1):
+                    if "$" in kind and e != n:
+                        continue
+                    starts = [0] if "^" in kind else range(e - 1, -1, -1)
+                    for s in starts:
+                        if s < e and rx.fullmatch(t[s:e]):
+                            want.append([s, e])
+                            break
+                got = oracle_api.Oracle(pat).lazy_matches_anchored(t).tolist()
+                assert got == want, (pat, t, got, want)

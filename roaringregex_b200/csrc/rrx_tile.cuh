@@ -995,6 +995,25 @@ template <int NW, int CW>
 RRX_DEV void phase_a_mask(const TileState<NW, CW>& ts, int t, uint32_t cand, uint32_t* cm) {
     const uint32_t C4 = cand * 0x01010101u;
     const uint32_t* rw = reinterpret_cast<const uint32_t*>(ts.text + t * ROW_PITCH);
+    // (RRX_ROLL_MASKS: the quarter loop is NOT unrolled — a quarter of the static code; the per-tile code of 32 de-phased
+    // warps has to fit the instruction cache, see RRX_COLD)
+#ifdef RRX_ROLL_MASKS
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        uint32_t acc = 0, w8[8];
+        row_words8(rw, q, w8);
+#pragma unroll
+        for (int j = 7; j >= 0; j--) {
+            const uint32_t x = w8[j] ^ C4;
+            const uint32_t y = (x | 0x80808080u) - 0x01010101u;
+            const uint32_t f = ~(y | x) & 0x80808080u;
+            acc = fshl(f * 0x00204081u, acc, 4);
+        }
+        c0 = q == 0 ? acc : c0; c1 = q == 1 ? acc : c1; c2 = q == 2 ? acc : c2; c3 = q == 3 ? acc : c3;
+    }
+    cm[0] = c0; cm[1] = c1; cm[2] = c2; cm[3] = c3;
+#else
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         uint32_t acc = 0, w8[8];
@@ -1008,6 +1027,7 @@ RRX_DEV void phase_a_mask(const TileState<NW, CW>& ts, int t, uint32_t cand, uin
         }
         cm[q] = acc;
     }
+#endif
 }
 
 // Stop-byte mask of row t for the reverse skip state (stop bytes b0/b1 of rrx_prog.h rskip, and every byte >= 0x80):
@@ -1016,6 +1036,30 @@ template <int NW, int CW>
 RRX_DEV void phase_z_mask(TileState<NW, CW>& ts, int t, uint32_t rs_bytes, uint32_t rs_n, uint32_t* zm) {
     const uint32_t B0 = (rs_bytes & 0xffu) * 0x01010101u, B1 = ((rs_bytes >> 8) & 0xffu) * 0x01010101u;
     const uint32_t* rw = reinterpret_cast<const uint32_t*>(ts.text + t * ROW_PITCH);
+#ifdef RRX_ROLL_MASKS
+    uint32_t z0 = 0, z1 = 0, z2 = 0, z3 = 0;
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+        uint32_t acc = 0, w8[8];
+        row_words8(rw, q, w8);
+#pragma unroll
+        for (int j = 7; j >= 0; j--) {
+            const uint32_t wv = w8[j];
+            const uint32_t x0 = wv ^ B0;
+            uint32_t f = ~(((x0 | 0x80808080u) - 0x01010101u) | x0);
+            if (rs_n > 1u) {
+                const uint32_t x1 = wv ^ B1;
+                f |= ~(((x1 | 0x80808080u) - 0x01010101u) | x1);
+            }
+            f = (f | wv) & 0x80808080u;
+            acc = fshl(f * 0x00204081u, acc, 4);
+        }
+        z0 = q == 0 ? acc : z0; z1 = q == 1 ? acc : z1; z2 = q == 2 ? acc : z2; z3 = q == 3 ? acc : z3;
+        ts.zmask[q * TILE_ROWS + t] = acc;
+    }
+    zm[0] = z0; zm[1] = z1; zm[2] = z2; zm[3] = z3;
+    return;
+#endif
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         uint32_t acc = 0, w8[8];

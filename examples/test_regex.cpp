@@ -1,44 +1,41 @@
-// The reference's interactive driver (RoaringRegex src/test/main.cpp:13-35), against the drop-in
-// header: line 1 = text, line 2 = pattern; prints the automaton summary, the whole-string answer
-// with the reference's stopwatch placement, and — what its README promises — all lazy matches.
+// A small command-line front end for the drop-in header: reads a text line and a pattern line from stdin (the same
+// input the reference's interactive driver takes, RoaringRegex src/test/main.cpp — that file itself compiles
+// unchanged against include/compat/regex.h, see tests/test_cpp_dropin.py) and prints the automaton summary, the
+// whole-string answer, every lazy match, and the non-overlapping view.  Written for this repository.
 //   g++ -std=c++17 -I include examples/test_regex.cpp -L roaringregex_b200 -lrrx -Wl,-rpath,$PWD/roaringregex_b200 -o test_regex
 #include <chrono>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
 #include <iostream>
+#include <string>
 
 #include "rrx_regex.hpp"
 
-using namespace Regex;
+namespace {
+void list_matches(Regex::IteratorWrapper it, const char* label, char* text) {
+    for (it++; (*it).has_value(); it++) {
+        Regex::Match m = **it;
+        std::cout << label << " [" << (m.start - text) << "," << (m.end - text) << "): " << m.str() << std::endl;
+    }
+}
+}  // namespace
+
 int main() {
-    char* text = NULL;
-    char* pattern = NULL;
-    size_t len;
-    if (getline(&text, &len, stdin) == -1 || getline(&pattern, &len, stdin) == -1) return -1;
-    text[strlen(text) - 1] = '\0';
-    pattern[strlen(pattern) - 1] = '\0';
+    std::string text, pattern;
+    if (!std::getline(std::cin, text) || !std::getline(std::cin, pattern)) return -1;
     try {
-        RRegex r(pattern);
-        auto start_time = std::chrono::high_resolution_clock::now();
-        auto acceptance_iter = r.get_acceptance_iter(text)++;
-        bool is_match = (*acceptance_iter).has_value();
-        auto end_time = std::chrono::high_resolution_clock::now();
-        acceptance_iter.print();
-        std::cout << "is match? " << is_match << std::endl;
-        std::cout << "time: " << std::chrono::duration_cast<std::chrono::milliseconds>(end_time - start_time).count() << "ms\n";
-        auto it = r.get_lazy_iter(text);
-        for (it++; (*it).has_value(); it++) {
-            Match m = **it;
-            std::cout << "match [" << (m.start - text) << "," << (m.end - text) << "): " << m.str() << std::endl;
-        }
+        Regex::RRegex regex(pattern.c_str());
+        char* t = text.data();
+        const auto t0 = std::chrono::steady_clock::now();
+        Regex::IteratorWrapper acc = regex.get_acceptance_iter(t);
+        acc++;
+        const bool whole = (*acc).has_value();
+        const auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count();
+        acc.print();
+        std::cout << "is match? " << whole << std::endl << "time: " << ms << "ms" << std::endl;
+        list_matches(regex.get_lazy_iter(t), "match", t);
+        list_matches(regex.get_nonoverlap_iter(t), "non-overlapping", t);
     } catch (const std::runtime_error& e) {
         std::cout << "error: " << e.what() << std::endl;
-        free(text);
-        free(pattern);
         return 2;
     }
-    free(text);
-    free(pattern);
     return 0;
 }

@@ -562,10 +562,30 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
 #pragma unroll
                 for (int w = 0; w < CW; w++) carried_in |= ts.sum_b[w * TILE_ROWS + lane - 1];
             }
+            // (ONE more inlined copy of phase_d_kind, entered at most twice: rows that receive a state; then, if some row that
+            // matters is open or the tile is partial, every remaining row — the general composition wants all kinds)
+            bool rows_ok = true, have_kind = edge;
+#ifdef RRX_KIND_PASSES
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                const bool mine = !have_kind && (pass == 1 || carried_in != 0u);
+                if (RRX_UNLIKELY(__any_sync(FULL, mine) != 0)) {
+                    if (mine) { kind = phase_d_kind<NW>(sp, pv, fw, ts, lane, &qfree); have_kind = true; }
+                }
+                if (pass == 0) {
+                    rows_ok = __all_sync(FULL, kind == K_CLOSED) != 0;
+                    if (!RRX_UNLIKELY(!rows_ok)) break;
+                }
+            }
+#else
             if (RRX_UNLIKELY(__any_sync(FULL, carried_in != 0u) != 0)) {
                 if (carried_in != 0u) kind = phase_d_kind<NW>(sp, pv, fw, ts, lane, &qfree);
             }
-            const bool rows_ok = __all_sync(FULL, kind == K_CLOSED) != 0;
+            rows_ok = __all_sync(FULL, kind == K_CLOSED) != 0;
+            if (RRX_UNLIKELY(!rows_ok)) {
+                if (!edge && carried_in == 0u) phase_d_kind<NW>(sp, pv, fw, ts, lane, &qfree);
+            }
+#endif
             if (early) lookback_publish_fold<CW>(sp, tile, arrived, lane);       // the arrival count has long come back
             if (!RRX_UNLIKELY(!rows_ok)) {
                 if (RRX_UNLIKELY(!early)) {
@@ -577,9 +597,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
                 }
                 published = true;
             } else {
-                // a row that matters is open, or the tile is partial: the general composition (phase S) wants every row's
-                // kind; an aggregate published early stands (it is what the composition will find)
-                if (!edge && carried_in == 0u) phase_d_kind<NW>(sp, pv, fw, ts, lane, &qfree);
+                // an aggregate published early stands (it is what the general composition will find)
                 agg_done = early;
                 __syncwarp();
             }

@@ -727,7 +727,11 @@ RRX_COLD WalkResult back_walk(const ScanParams& sp, const ProgView& pv, const F&
             uint32_t d = 0;
 #pragma unroll
             for (int w = 0; w < NW; w++) d |= R[w] ^ fw.rs_F(pv, w);
+#ifdef RRX_ZMASK_ALWAYS
+            if (d == 0) {
+#else
             if (d == 0 && ts.misc[TileState<NW, CW>::M_ZVALID]) {
+#endif
                 // the tile's stop-byte masks answer "last stop byte at or before rel" in a few instructions
                 uint32_t row = (uint32_t)rel >> ROW_SHIFT, pos = (uint32_t)rel & (ROW_BYTES - 1), w = pos >> 5;
                 uint32_t m = ts.zmask[w * TILE_ROWS + row] & (0xffffffffu >> (31u - (pos & 31u)));
@@ -742,7 +746,9 @@ RRX_COLD WalkResult back_walk(const ScanParams& sp, const ProgView& pv, const F&
                 }
                 rel = (int)(row * ROW_BYTES + w * 32u + (31u - (uint32_t)clz32(m)));
                 c = ts.rel_byte((uint32_t)rel);
-            } else if (d == 0) {
+            }
+#ifndef RRX_ZMASK_ALWAYS        // (kernels that always have the masks do not carry the word-wise walk)
+            else if (d == 0) {
                 // bytes down to a word boundary, then whole words (SWAR: does the word hold b0, b1 or a
                 // byte >= 0x80?), then the bytes of the word that does
                 while (c != b0 && c != b1 && c < 128u && rel > 0 && (rel & 3) != 0) { rel--; c = ts.rel_byte((uint32_t)rel); }
@@ -765,6 +771,7 @@ RRX_COLD WalkResult back_walk(const ScanParams& sp, const ProgView& pv, const F&
                 }
                 if (c != b0 && c != b1 && c < 128u) { rel = -1; break; }      // ran to the tile start inside F
             }
+#endif
         }
         load_B<NW>(pv, c, Bc);
         uint32_t m = 0;

@@ -264,7 +264,9 @@ def sub_record(rrx, torch, cfg, peak, prefix, sh, steps=3):
     size = cfg.length
     regex = rrx.RRegex(cfg.pattern)
     d_buf, d_text = _scan_setup(rrx, torch, cfg, size, 0, 0, sh)
-    cap = max(1 << 16, size // (48 if cfg.mode != "iid" else 160))
+    # match capacity as rrx_scan_device sizes it (one pair per 64 bytes): half of it is handed out as fixed staging slots,
+    # 32 per 4 KiB tile, so that tiles with the corpora's 15-16 matches need no allocation
+    cap = max(1 << 16, size // 64)
     sc = rrx.Scanner(regex, size, cap)
     sc.scan(d_text.data_ptr(), size, 0, 0, None, sh)
     res = sc.result(sh)
@@ -326,7 +328,7 @@ def sub_record_sharded(rrx, torch, dist, cfg, peak, prefix, sh, rank, world, loc
     halo = min(off, 1 << 20)
     regex = rrx.RRegex(cfg.pattern)
     d_buf, d_text = _scan_setup(rrx, torch, cfg, size, off, halo, sh)
-    cap = max(1 << 16, size // 160)
+    cap = max(1 << 16, size // 64)
     probe = rrx.Scanner(regex, size, cap)
     probe.scan(d_text.data_ptr(), size, off, halo, None, sh)
     cap = max(cap, probe.result(sh)["n_matches"] + (1 << 16))

@@ -500,3 +500,26 @@ def test_anchors(rrx, oracle_api, torch_cuda):
     for pat in ("^.*b", "a.*b$", "^a*b"):
         want = oracle_api.Oracle(pat).lazy_matches_anchored(txt)
         assert np.array_equal(rrx.RRegex(pat).scan_host(txt), want), pat
+
+
+def test_scanner_picks_its_kernel_variant(rrx, oracle_api, torch_cuda):
+    """A thread-owned program has a lean and a straddle kernel; the scanner starts lean and switches by what the previous
+    scan saw: aligned records stay lean, variable-length lines (matches straddling rows) move to straddle — and back.
+    Both give the oracle's list."""
+    torch = torch_cuda
+    n = 40 << 20
+    r = rrx.RRegex(CONFIGS[2].pattern)
+    sc = rrx.Scanner(r, n, n // 48, jit=True)
+    o = oracle_api.Oracle(CONFIGS[2].pattern)
+    seen = []
+    for key in (2, "2v", "2v", 2, 2):
+        cfg = CONFIGS[key]
+        d = torch.empty(n + 64, dtype=torch.uint8, device="cuda")
+        rrx.corpus_device(cfg, d.data_ptr(), 0, n)
+        sc.scan(d.data_ptr(), n)
+        res = sc.result()
+        assert res["error_bits"] == 0
+        seen.append(sc.kernel_variant)
+        want = o.lazy_matches(cpu_corpus(cfg, 0, 4 << 20))
+        assert np.array_equal(sc.matches()[:len(want)], want), key
+    assert seen == [0, 1, 1, 0, 0], seen

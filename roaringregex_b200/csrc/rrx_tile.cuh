@@ -1296,12 +1296,16 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
         const uint32_t over = (t < ROWS - 1 && rowend == (uint32_t)ROW_BYTES && p >= rowend && live != 0u && q.nacc < 4u) ? 1u : 0u;
 #endif
         if (RRX_UNLIKELY(RRX_WARP_ANY(over != 0u))) {
+            // The next row has to be a full row of the text: behind the end of the text the staged bytes are fill bytes,
+            // the run would seem to die there, and the state alive at the end of the text — the shard's exit, which the
+            // next shard enters with — would be lost.  (Tested here, off the per-tile path.)
+            const uint32_t ov = (over != 0u && row_nbytes(sp, ts.row0, t + 1) == ROW_BYTES) ? 1u : 0u;
             uint32_t Hx[NW];
 #pragma unroll
             for (int w = 0; w < NW; w++) Hx[w] = H[w];
             const uint32_t kq0 = q.kq, ks0 = q.ks, na0 = q.nacc;
             const SmemBytes rb2(rp + ROW_PITCH);
-            uint32_t p2 = 0, ovf = 0, go = over ? live : 0u;
+            uint32_t p2 = 0, ovf = 0, go = ov ? live : 0u;
             while (RRX_WARP_ANY(go != 0u)) {
                 const uint32_t c = rb2.at(p2);
                 load_B<NW>(pv, c, Bc);
@@ -1326,7 +1330,7 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
                 ovf |= (step && lv != 0u && (q.nacc >= 4u || p2 >= (uint32_t)ROW_BYTES - 1u)) ? 1u : 0u;   // outlives the queue / the next row
                 go = (step && !ovf) ? live : 0u;
             }
-            if (over) {
+            if (ov) {
                 // (straddle kernel: rows whose run was followed into the next row — ScanParams::straddle_tiles)
                 if (sp.straddle_tiles) atomicAdd(sp.straddle_tiles, 1u);
                 if (ovf) {                      // undo: the classic hand-over through the row's exit

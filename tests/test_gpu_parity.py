@@ -241,6 +241,41 @@ def test_sharded_on_device(rrx, oracle_api, torch_cuda, cfg_id):
         assert np.array_equal(got, want), (cfg_id, world)
 
 
+@pytest.mark.parametrize("jit", [False, True])
+def test_shard_ending_on_a_row_boundary_inside_a_tile(rrx, oracle_api, torch_cuda, monkeypatch, jit):
+    """A run alive at the last byte of a shard whose last row is full but not its tile's last: the state at the end of
+    the text is the shard's exit (the straddle kernel must not follow the run into a row that does not exist).
+    jit=False: the pre-compiled kernels (built with the straddle code); jit=True: the straddle variant, forced."""
+    torch = torch_cuda
+    import random
+    if jit:
+        monkeypatch.setenv("RRX_JIT_VARIANT", "1")
+    rnd = random.Random(5)
+    n = 9000
+    for pat, alpha, wts in [("a.", b"abc\xe9\x80", [200, 1, 1, 1, 200]), ("y[a-z]+q", b"abcxyzq ", [40, 1, 5, 200, 40, 1, 200, 1]),
+                            ("[a-z]+z[a-z]+", b"abcxyzq ", [1, 5, 5, 200, 1, 5, 200, 5]), ("c[a-z]+", b"ab@.com ", [1, 5, 1, 200, 200, 200, 1, 1])]:
+        o = oracle_api.Oracle(pat)
+        r = rrx.RRegex(pat)
+        sc = rrx.Scanner(r, n, n + 64, jit=jit)
+        nw = r.info["words"]
+        for cut in (128, 1920, 4480):
+            for _ in range(3):
+                text = np.frombuffer(bytes(rnd.choices(alpha, weights=wts, k=n)), dtype=np.uint8)
+                want = o.lazy_matches(text)
+                d = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+                d[:n] = torch.from_numpy(text.copy()).cuda()
+                sc.scan(d.data_ptr(), cut)
+                assert sc.result()["error_bits"] == 0
+                left = sc.matches()
+                comp = sc.shard_summary()
+                assert comp[0] & 0xff in (0, 1)
+                sc.scan(d.data_ptr() + cut, n - cut, base_offset=cut, left_context=cut, entry=comp[1:1 + nw].copy())
+                res = sc.result()
+                assert res["error_bits"] == 0 and res["n_pending"] == 0
+                got = np.concatenate([left, sc.matches()])
+                assert np.array_equal(got, want), (pat, cut, jit)
+
+
 def test_sharded_start_scan_travels_through_all_shards(rrx, oracle_api, torch_cuda, monkeypatch):
     from roaringregex_b200 import sharded
     monkeypatch.setattr(sharded, "PREFIX_WINDOW", 8192)

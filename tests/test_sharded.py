@@ -201,6 +201,20 @@ def test_unaligned_cuts_with_static_closed_patterns(rrx, oracle_api):
             assert np.array_equal(got, o.lazy_matches(text)), (pat, n, cuts)
 
 
+def test_run_alive_at_the_end_of_a_full_last_row(rrx, oracle_api):
+    """A shard that ends on a row boundary inside a tile, with a run alive at its last byte: the lane must not follow
+    the run into the (non-existent) next row — the state at the end of the text is the shard's exit (fuzz_emu find)."""
+    rnd = random.Random(5)
+    for pat, alpha, wts in [("a.", b"abc\xe9\x80", [200, 1, 1, 1, 200]), ("y[a-z]+q", b"abcxyzq ", [40, 1, 5, 200, 40, 1, 200, 1]),
+                            ("[a-z]+z[a-z]+", b"abcxyzq ", [1, 5, 5, 200, 1, 5, 200, 5]), ("(b[a-z]+)*", b"abc\n", [200, 200, 40, 5])]:
+        o = oracle_api.Oracle(pat)
+        for cut in (128, 1920):
+            for _ in range(2):
+                text = np.frombuffer(bytes(rnd.choices(alpha, weights=wts, k=2600)), dtype=np.uint8)
+                got, _ = run_world(rrx, pat, text, 2, halo=rnd.choice([0, 128, cut]), cuts=[0, cut, 2600])
+                assert np.array_equal(got, o.lazy_matches(text)), (pat, cut)
+
+
 def _gloo_worker(rank, world, port, pattern, n, seed, q):
     import torch.distributed as dist
     import roaringregex_b200 as rrx

@@ -31,6 +31,15 @@ int cuda_err(cudaError_t e, const char* what) {
 }
 #define RRX_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_err(e_, #call); } while (0)
 
+// cudaMemcpy from pageable host memory returns once the bytes sit in the driver's staging buffer: the DMA into device memory
+// runs on the legacy default stream and may still be in flight.  The scans run on non-blocking streams, which do not wait
+// for that stream — so an upload that a scan depends on is followed by a synchronisation of the legacy stream.
+// (Seen as an empty match list from the first rrx_scan_host call of a program on a busy GPU: scripts/fuzz_gpu.py.)
+static cudaError_t upload_sync(void* dst, const void* src, size_t bytes) {
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    return e == cudaSuccess ? cudaStreamSynchronize(cudaStreamLegacy) : e;
+}
+
 // Control block of a scan over T tiles (B = ceil(T/32) blocks); everything in it is zeroed before
 // the scan: [-,err,total[2],n_matches | pad | ticket (its own 128-byte line: every tile of the grid adds to it, nothing
 // else should wait behind those atomics) | f_a0[T] f_i0[T] f_a1[B] f_i1[B] st_arrive[B] tile_stop[T]].
@@ -315,7 +324,7 @@ int rrx_scanner_create_ex(const rrx_program* p, uint64_t max_len, uint64_t capac
     if (s->max_tiles == 0) s->max_tiles = 1;
     s->capacity = capacity ? capacity : 1;
     RRX_CUDA(cudaMalloc(&s->d_prog, p->prog.blob.size() * 4));
-    RRX_CUDA(cudaMemcpy(s->d_prog, p->prog.blob.data(), p->prog.blob.size() * 4, cudaMemcpyHostToDevice));
+    RRX_CUDA(upload_sync(s->d_prog, p->prog.blob.data(), p->prog.blob.size() * 4));
     s->ctrl_bytes = ctrl_layout(s->max_tiles, nullptr);
     // control block and look-back payloads in ONE allocation: a scan places the payloads right behind the part of the
     // control block it uses, so that one memset zeroes both (payloads with the ready bit inside need it)
@@ -865,11 +874,11 @@ static int anchor_merge_extra(long long* d_pairs, uint64_t* count, const int64_t
         long long last[2];
         RRX_CUDA(cudaMemcpy(last, d_pairs + 2 * (*count - 1), 16, cudaMemcpyDeviceToHost));
         if (last[1] == ep[1]) {
-            if (ep[0] > last[0]) RRX_CUDA(cudaMemcpy(d_pairs + 2 * (*count - 1), ep, 8, cudaMemcpyHostToDevice));
+            if (ep[0] > last[0]) RRX_CUDA(upload_sync(d_pairs + 2 * (*count - 1), ep, 8));
             return RRX_OK;
         }
     }
-    RRX_CUDA(cudaMemcpy(d_pairs + 2 * *count, ep, 16, cudaMemcpyHostToDevice));
+    RRX_CUDA(upload_sync(d_pairs + 2 * *count, ep, 16));
     (*count)++;
     return RRX_OK;
 }

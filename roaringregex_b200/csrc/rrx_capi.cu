@@ -31,6 +31,16 @@ int cuda_err(cudaError_t e, const char* what) {
 }
 #define RRX_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_err(e_, #call); } while (0)
 
+// Pending-start slots for scanners created by this thread, when larger than the default: the one-shot calls on anchored
+// programs set it after a scan whose start walks reached the text start more often than the default list holds
+// (`^.*b` on a text full of `b`), create the scanner (and, through it, its fallback scanner) again and rescan.
+thread_local uint32_t t_pending_cap_want = 0;
+struct PendingCapScope {
+    explicit PendingCapScope(uint32_t want) { t_pending_cap_want = want; }
+    ~PendingCapScope() { t_pending_cap_want = 0; }
+};
+constexpr uint64_t PENDING_CAP_MAX = 1ull << 24;
+
 // cudaMemcpy from pageable host memory returns once the bytes sit in the driver's staging buffer: the DMA into device memory
 // runs on the legacy default stream and may still be in flight.  The scans run on non-blocking streams, which do not wait
 // for that stream — so an upload that a scan depends on is followed by a synchronisation of the legacy stream.
@@ -338,6 +348,7 @@ int rrx_scanner_create_ex(const rrx_program* p, uint64_t max_len, uint64_t capac
     RRX_CUDA(cudaMalloc(&s->d_chunk, ((s->max_tiles + 1023) / 1024 + 1) * 8));
     RRX_CUDA(cudaMalloc(&s->d_shard, (1 + 3 * (size_t)h.NW) * 4));
     if (h.n_anchor) s->pending_cap = 1u << 16;      // a start-anchored thread that is carried far ends every one of its matches' start walks at the text start
+    if (t_pending_cap_want > s->pending_cap) s->pending_cap = t_pending_cap_want;   // (one-shot calls that saw the list overflow)
     RRX_CUDA(cudaMalloc(&s->d_pending, sizeof(PendingStart) * s->pending_cap));
     RRX_CUDA(cudaMallocHost(&s->h_ctr, 32 + 4 * (1 + 3 * (size_t)RRX_NW_MAX)));
     {
@@ -717,7 +728,9 @@ int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, u
     uint32_t aentry[RRX_NW_MAX];
     const bool anchored = p->prog.hdr().n_anchor != 0;
     const bool a_entry = anchor_entry(p, aentry);
-    for (int attempt = 0; attempt < 2; attempt++) {
+    uint32_t pend_want = 0;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        PendingCapScope pcs(pend_want);
         rrx_scanner* s = nullptr;
         int rc = rrx_scanner_create(p, len, cap + 1, &s);          // (+1: room for the match of a trailing anchor)
         if (rc) return rc;
@@ -728,6 +741,12 @@ int rrx_scan_device(const rrx_program* p, const uint8_t* d_text, uint64_t len, u
         rrx_scan_result r;
         if (!rc) rc = rrx_scanner_result(s, &r, stream);
         if (rc) { rrx_scanner_free(s); return rc; }
+        if (anchored && r.error_bits == ERR_PENDING_OVERFLOW && !pend_want && r.n_pending < PENDING_CAP_MAX) {
+            pend_want = (uint32_t)r.n_pending + 1;      // the kernel counted them all: rescan with room for every one
+            if (r.n_matches > cap) cap = r.n_matches;
+            rrx_scanner_free(s);
+            continue;
+        }
         if (r.error_bits) {
             rrx_scanner_free(s);
             return set_err(RRX_ERR_CUDA, "scan kernel reported error bits " + std::to_string(r.error_bits));
@@ -801,6 +820,12 @@ static bool anchor_entry(const rrx_program* p, uint32_t* entry) {
     return any;
 }
 
+// the matches whose start walk ended at the leading virtual byte start at the text start
+__global__ void set_starts_kernel(long long* pairs, const unsigned long long* idx, uint64_t n, long long start) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pairs[2 * idx[i]] = start;
+}
+
 // After the scan of a whole text [0,len) with anchor_entry() as entry: resolve walks that reached the text start,
 // take the trailing virtual step.  *extra = 1 and extra_pair = (start,end) if one more match ends at base+len.
 static int anchor_fixups(const rrx_program* p, rrx_scanner* s, const uint8_t* d_text, uint64_t len, uint64_t base, const uint32_t* entry,
@@ -818,14 +843,23 @@ static int anchor_fixups(const rrx_program* p, rrx_scanner* s, const uint8_t* d_
         int rc = rrx_scanner_copy_pending(s, recs.data(), recs.size(), &n, stream);
         if (rc) return rc;
         if (n != r.n_pending) return set_err(RRX_ERR_CUDA, "too many start walks reach the text start");
-        const long long st0 = (long long)base;
+        std::vector<unsigned long long> idx(n);
         for (uint64_t i = 0; i < n; i++) {
             uint32_t o = 0;
             for (uint32_t w = 0; w < h.NW; w++) o |= recs[i].R[w] & fa[w];
             if (!o) return set_err(RRX_ERR_CUDA, "a start walk left the text without a start anchor to end at");
-            RRX_CUDA(cudaMemcpyAsync(sa->d_out + 2 * recs[i].match_index, &st0, 8, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+            idx[i] = recs[i].match_index;
         }
-        RRX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        unsigned long long* d_idx = nullptr;
+        RRX_CUDA(cudaMalloc(&d_idx, n * 8));
+        cudaError_t e = cudaMemcpyAsync(d_idx, idx.data(), n * 8, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+        if (e == cudaSuccess) {
+            set_starts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sa->d_out, d_idx, n, (long long)base);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+        cudaFree(d_idx);
+        if (e != cudaSuccess) return cuda_err(e, "anchored starts");
     }
     if (len == 0) return RRX_OK;
     // (b) the trailing virtual byte
@@ -1079,7 +1113,9 @@ int rrx_scan_host(const rrx_program* p, const uint8_t* text, uint64_t len, uint6
     uint32_t aentry[RRX_NW_MAX];
     const bool anchored = p->prog.hdr().n_anchor != 0;
     const bool a_entry = anchor_entry(p, aentry);
-    for (int attempt = 0; attempt < 2; attempt++) {
+    uint32_t pend_want = 0;
+    for (int attempt = 0; attempt < 3; attempt++) {
+        PendingCapScope pcs(pend_want);
         if (!hc->sc || hc->sc_len < len || hc->sc_cap < want_cap) {
             if (hc->sc) { rrx_scanner_free(hc->sc); hc->sc = nullptr; }
             const uint64_t sl = hc->text_cap - 16;
@@ -1094,6 +1130,13 @@ int rrx_scan_host(const rrx_program* p, const uint8_t* text, uint64_t len, uint6
         rrx_scan_result r;
         if (!rc) rc = rrx_scanner_result(hc->sc, &r, hc->st);
         if (rc) return rc;
+        if (anchored && r.error_bits == ERR_PENDING_OVERFLOW && !pend_want && r.n_pending < PENDING_CAP_MAX) {
+            pend_want = (uint32_t)r.n_pending + 1;      // the kernel counted them all: new scanner with room for every one
+            if (r.n_matches + 1 > want_cap) want_cap = r.n_matches + 1024;
+            rrx_scanner_free(hc->sc);
+            hc->sc = nullptr;
+            continue;
+        }
         if (r.error_bits) return set_err(RRX_ERR_CUDA, "scan kernel reported error bits " + std::to_string(r.error_bits));
         if (r.n_matches + 1 > r.capacity) { want_cap = r.n_matches + 1024; continue; }    // exact size known now: scan again
         std::unique_ptr<rrx_matches> m(new rrx_matches);

@@ -5,6 +5,8 @@ RRX_JIT_VARIANT=1 in a second process, straddle), and two-shard scans chained th
 documented redo when the thread-owned scan asks for it.  TEST INFRASTRUCTURE: the oracle is the checker here.
 
     python scripts/fuzz_gpu.py --seed 1 --minutes 3 [--jit-every 12]
+    python scripts/fuzz_gpu.py --seed 1 --minutes 3 --mode extra      # anchors ^ $ and the non-overlapping view (one-shot calls)
+    RRX_HOST_CHUNK=1048576 python scripts/fuzz_gpu.py --seed 1 --minutes 3 --mode stream   # streaming host ingestion, 3-6 MiB texts
 """
 import argparse
 import os
@@ -57,14 +59,105 @@ def two_shards(torch, r, sc, d, text, n, cut, ctx, want, stats):
     return None
 
 
+def np_text(rng, letters, wts, n):
+    p = np.asarray(wts, dtype=np.float64)
+    return rng.choice(np.frombuffer(letters, dtype=np.uint8), size=n, p=p / p.sum()).astype(np.uint8)
+
+
+def other_modes(a, torch):
+    """extra: anchored patterns and RRX_MODE_NO_OVERLAP through rrx_scan_host / rrx_scan_device, thread-owned and
+    row-bounded programs.  stream: rrx_scan_host on texts of several chunks (RRX_HOST_CHUNK), pageable and pinned."""
+    rnd = random.Random(a.seed)
+    rng = np.random.default_rng(a.seed)
+    stats = dict(cases=0, anchored=0, no_overlap=0, stream=0, failures=0)
+    t_end = time.time() + 60 * a.minutes
+    it = 0
+    while time.time() < t_end and stats["failures"] < 20:
+        it += 1
+        letters = rnd.choice(ALPHABETS)
+        pat = regex(rnd, letters)
+        ls = [chr(c) for c in letters if chr(c).isalnum()]
+        anchored = a.mode == "extra" and rnd.random() < 0.5
+        if anchored:
+            pat = rnd.choice(["^" + pat, pat + "$", "^" + pat + "$", "(^|" + rnd.choice(ls) + ")" + pat, pat + "($|" + rnd.choice(ls) + ")"])
+        try:
+            o = oracle_api.Oracle(pat)
+        except Exception:
+            continue
+        if o.n_raw > 500:
+            continue
+        progs = []
+        try:
+            for flags in (0, rrx.COMPILE_NO_DONLY):
+                progs.append(rrx.RRegex(pat, flags))
+        except rrx.RrxError as e:
+            stats["failures"] += 1
+            print("FAIL", "seed", a.seed, "iter", it, ("compile", pat, str(e)), flush=True)
+            continue
+        for _ in range(3):
+            wts = [rnd.choice([1, 1, 5, 40, 200]) for _ in letters]
+            if a.mode == "stream":
+                n = rnd.choice([3 << 20, (3 << 20) + 1, (4 << 20) + 4097, (5 << 20) - 1, 6 << 20])
+            else:
+                n = rnd.choice([0, 1, 2, 127, 128, 129, 700, 4095, 4096, 4097, 9000, 33000, 70000])
+            text = np_text(rng, letters, wts, n)
+            tb = text.tobytes()
+            want = o.lazy_matches_anchored(tb) if anchored else o.lazy_matches(tb)
+            if len(want) > (1 << 21):
+                continue
+            stats["cases"] += 1
+            bad = None
+            for k, r in enumerate(progs):
+                try:
+                    got = r.scan_host(text)
+                except rrx.RrxError as e:
+                    bad = ("scan_host error", k, str(e))
+                    break
+                if got.shape != want.shape or not np.array_equal(got, want):
+                    bad = ("scan_host", k, len(got), len(want))
+                    break
+                if a.mode == "stream":
+                    stats["stream"] += 1
+                    pinned = torch.from_numpy(text.copy()).pin_memory()
+                    got = r.scan_host(pinned.numpy())
+                    if got.shape != want.shape or not np.array_equal(got, want):
+                        bad = ("scan_host pinned", k, len(got), len(want))
+                        break
+                    continue
+                stats["anchored"] += int(anchored)
+                if n:
+                    d = torch.from_numpy(text.copy()).cuda()
+                    got = r.scan_device(d.data_ptr(), n)
+                    if got.shape != want.shape or not np.array_equal(got, want):
+                        bad = ("scan_device", k, len(got), len(want))
+                        break
+                if not anchored:
+                    stats["no_overlap"] += 1
+                    wn = o.no_overlap_matches(tb)
+                    got = r.scan_host(text, 0, rrx.MODE_NO_OVERLAP)
+                    if got.shape != wn.shape or not np.array_equal(got, wn):
+                        bad = ("no_overlap", k, len(got), len(wn))
+                        break
+            if bad:
+                stats["failures"] += 1
+                print("FAIL", "seed", a.seed, "iter", it, (pat, letters, wts, n) + tuple(bad), flush=True)
+                np.save(os.path.join(ROOT, "gpurun_out", f"fuzz_gpu_fail_{a.mode}_{a.seed}_{it}.npy"), text)
+                break
+    print("fuzz_gpu", a.mode, "seed", a.seed, "chunk_env", os.environ.get("RRX_HOST_CHUNK", ""), stats, flush=True)
+    return 1 if stats["failures"] else 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--minutes", type=float, default=3.0)
     ap.add_argument("--jit-every", type=int, default=12, help="every k-th pattern also runs on a run-time specialised scanner")
+    ap.add_argument("--mode", default="base", choices=["base", "extra", "stream"])
     a = ap.parse_args()
     import torch
     assert torch.cuda.is_available(), "needs a CUDA device"
+    if a.mode != "base":
+        return other_modes(a, torch)
     rnd = random.Random(a.seed)
     stats = dict(cases=0, jit=0, shards=0, shard_fallback=0, pending_overflow=0, open_summary=0, failures=0)
     t_end = time.time() + 60 * a.minutes

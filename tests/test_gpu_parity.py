@@ -535,6 +535,17 @@ def test_anchors(rrx, oracle_api, torch_cuda):
     for pat in ("^.*b", "a.*b$", "^a*b"):
         want = oracle_api.Oracle(pat).lazy_matches_anchored(txt)
         assert np.array_equal(rrx.RRegex(pat).scan_host(txt), want), pat
+    # more start walks reaching the text start than the default pending list holds (65,536): the one-shot calls rescan
+    # with a list sized by the count the kernel reported
+    txt = b"b" * 70000
+    want = oracle_api.Oracle("^.*b").lazy_matches_anchored(txt)
+    assert len(want) == 70000 and want[:, 0].max() == 0
+    for flags in (0, rrx.COMPILE_NO_DONLY):
+        r = rrx.RRegex("^.*b", flags)
+        assert np.array_equal(r.scan_host(txt), want), flags
+        assert np.array_equal(r.scan_host(txt[:100]), want[:100]), flags           # the grown scanner is reused
+        d = torch.tensor(np.frombuffer(txt, dtype=np.uint8), device="cuda")
+        assert np.array_equal(r.scan_device(d.data_ptr(), len(txt)), want), (flags, "device")
 
 
 def test_scanner_picks_its_kernel_variant(rrx, oracle_api, torch_cuda):

@@ -305,7 +305,10 @@ int rrx_program_jit_compile(const rrx_program* p, const char* path) {
     if (!jit_applicable(p->prog)) return set_err(RRX_ERR_UNSUPPORTED, "automata that need per-source row tables are not specialised");
     std::vector<char> cubin;
     std::string err;
-    if (!jit_compile_cubin(p->prog, &cubin, &err)) return set_err(RRX_ERR_CUDA, err);
+    // (RRX_JIT_VARIANT=1: the straddle kernel of a thread-owned program instead of the lean one, as in rrx_scanner_create_ex)
+    const char* v = getenv("RRX_JIT_VARIANT");
+    const int variant = (v && v[0] == '1' && p->prog.hdr().donly) ? 1 : 0;
+    if (!jit_compile_cubin(p->prog, &cubin, &err, variant)) return set_err(RRX_ERR_CUDA, err);
     if (path) {
         FILE* f = fopen(path, "wb");
         if (!f) return set_err(RRX_ERR_ARG, "cannot open output file");

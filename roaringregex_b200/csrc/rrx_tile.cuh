@@ -537,6 +537,14 @@ RRX_DEV int row_nbytes(const ScanParams& sp, uint64_t row0, int t) {
     return rem >= ROW_BYTES ? ROW_BYTES : (int)rem;
 }
 
+// the same, clamped to TWO rows: 2 * ROW_BYTES <=> rows t and t+1 are both full rows of the text
+RRX_DEV uint32_t row_nbytes2(const ScanParams& sp, uint64_t row0, int t) {
+    const uint64_t lo = (row0 + (uint64_t)t) << ROW_SHIFT;
+    if (lo >= sp.len) return 0u;
+    const uint64_t rem = sp.len - lo;
+    return rem >= 2u * ROW_BYTES ? 2u * ROW_BYTES : (uint32_t)rem;
+}
+
 // Known lazy starts travel as 16-bit values: start offset relative to the row start, biased by KS_BIAS (a start
 // found by a verification walk may lie in an earlier row or tile); 0 = not known.
 constexpr uint32_t KST_NONE = 0xffffffffu;
@@ -1094,7 +1102,13 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
     constexpr int ROWS = TILE_ROWS;
     const uint32_t ngr = fw.sp_ngroups(pv), cand = fw.sp_cand(pv);
     const uint8_t* rp = ts.text + t * ROW_PITCH;
+#ifdef RRX_NO_OVERRUN
     const uint32_t rowend = DONLY ? (uint32_t)row_nbytes(sp, ts.row0, t) : (uint32_t)ROW_BYTES;
+#else
+    // bytes of the text from the start of row t on, clamped to two rows: 256 <=> row t AND row t+1 are full rows
+    const uint32_t rem2 = DONLY ? row_nbytes2(sp, ts.row0, t) : 2u * ROW_BYTES;
+    const uint32_t rowend = rem2 < (uint32_t)ROW_BYTES ? rem2 : (uint32_t)ROW_BYTES;
+#endif
     int ncand = popc32(cm[0]) + popc32(cm[1]) + popc32(cm[2]) + popc32(cm[3]);
 
     // (2) runs of dominated states.  Two nested warp-uniform loops (every lane iterates until all
@@ -1293,13 +1307,13 @@ RRX_DEV bool phase_a_cand(const ScanParams& sp, const ProgView& pv, const F& fw,
 #ifdef RRX_NO_OVERRUN
         const uint32_t over = 0u;
 #else
-        const uint32_t over = (t < ROWS - 1 && rowend == (uint32_t)ROW_BYTES && p >= rowend && live != 0u && q.nacc < 4u) ? 1u : 0u;
+        // Only into a FULL row of the text (rem2): behind the end of the text the staged bytes are fill bytes, the run would
+        // seem to die there, and the state alive at the end of the text — the shard's exit, which the next shard enters
+        // with — would be lost.
+        const uint32_t over = (t < ROWS - 1 && rem2 == 2u * ROW_BYTES && p >= rowend && live != 0u && q.nacc < 4u) ? 1u : 0u;
 #endif
         if (RRX_UNLIKELY(RRX_WARP_ANY(over != 0u))) {
-            // The next row has to be a full row of the text: behind the end of the text the staged bytes are fill bytes,
-            // the run would seem to die there, and the state alive at the end of the text — the shard's exit, which the
-            // next shard enters with — would be lost.  (Tested here, off the per-tile path.)
-            const uint32_t ov = (over != 0u && row_nbytes(sp, ts.row0, t + 1) == ROW_BYTES) ? 1u : 0u;
+            const uint32_t ov = over;
             uint32_t Hx[NW];
 #pragma unroll
             for (int w = 0; w < NW; w++) Hx[w] = H[w];

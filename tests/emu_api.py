@@ -10,7 +10,9 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB = os.path.join(HERE, "emu", "_build", "librrx_emu.so")
+# RRX_EMU_DEFS="A B=1": extra #defines for the emulator build (the same switches RRX_JIT_DEFS gives the kernels)
+EMU_DEFS = os.environ.get("RRX_EMU_DEFS", "").split()
+LIB = os.path.join(HERE, "emu", "_build", "librrx_emu" + "".join("_" + d.replace("=", "-") for d in EMU_DEFS) + ".so")
 SRCS = [os.path.join(HERE, "emu", "rrx_emu.cc"), os.path.join(ROOT, "roaringregex_b200", "csrc", "rrx_compile.cc")]
 DEPS = SRCS + [os.path.join(ROOT, "roaringregex_b200", "csrc", f) for f in ("rrx_tile.cuh", "rrx_compile.h", "rrx_prog.h")]
 
@@ -19,7 +21,7 @@ def build():
     if os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in DEPS):
         return
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", LIB] + SRCS, check=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas"] + ["-D" + d for d in EMU_DEFS] + ["-o", LIB] + SRCS, check=True)
 
 
 @functools.lru_cache(maxsize=None)

@@ -145,3 +145,24 @@ def test_specialised_kernel_compiles_without_gpu(rrx, tmp_path):
         assert rw.info["words"] == words and "__funnelshift_l" in rw.jit_source()
         rw.jit_compile(str(out))
         assert out.stat().st_size > 10000
+
+
+def test_both_kernel_variants_compile_for_every_config(rrx, tmp_path, monkeypatch):
+    """Thread-owned programs have a lean and a straddle kernel (rrx_jit.h): both must compile for sm_100a."""
+    from roaringregex_b200.configs import CONFIGS
+    sizes = {}
+    for variant in ("0", "1"):
+        monkeypatch.setenv("RRX_JIT_VARIANT", variant)
+        for cid in (1, 2, 3, 4, 5):
+            r = rrx.RRegex(CONFIGS[cid].pattern)
+            assert r.info["donly"] == 1
+            out = tmp_path / f"k{cid}_{variant}.cubin"
+            try:
+                r.jit_compile(str(out))
+            except rrx.RrxError as e:
+                if "NVRTC could not be loaded" in str(e):
+                    pytest.skip("no NVRTC on this machine")
+                raise
+            sizes[(cid, variant)] = out.stat().st_size
+    assert all(v > 10000 for v in sizes.values())
+    assert any(sizes[(c, "0")] != sizes[(c, "1")] for c in (1, 2, 3, 4, 5))      # the variants are different kernels

@@ -3,11 +3,15 @@
 // `ProgJit` policy that has the automaton's masks and shifts baked in as immediates).
 //
 // One persistent CTA per SM; every WARP walks tiles (32 rows of 128 B) in ticket order:
-//   load   8 x 128-bit coalesced loads per lane -> shared memory rows (132-byte pitch); or already there,
-//          copied asynchronously (cp.async) during the previous tile's fast tail
-//   A      sparse variant (automata with a cut): exit sets first (aggregate published at once when all rows
-//          are closed), then candidate-driven match ends with known lazy starts; dense variant: every
-//          lane scans its row from the empty set (register state word(s))
+//   load   8 x 128-bit coalesced loads per lane -> shared memory rows (pitch RRX_ROW_PITCH: 144 bytes for the
+//          thread-owned kernels — 16-byte aligned rows, 128-bit row loads —, 132 otherwise); or already there,
+//          copied asynchronously (16-byte cp.async) during the previous tile's fast tail
+//   A      thread-owned variant (program header `donly`: a single-byte cut whose dominated states are all that is
+//          ever carried): candidate mask (+ stop-byte mask for skip-state walks), candidate-driven match ends with
+//          verified lazy starts, row kinds decided lazily (lean kernel: eagerly, no run followed into the next row);
+//          row-bounded variant (cut, but entry sets outside the dominated set): exit sets first, aggregate published
+//          at once when all rows are closed, then the candidates; dense variant: every lane scans its row from the
+//          empty set (register state word(s))
 //   S      row transfer functions composed; tile aggregate published; two-level decoupled
 //          look-back over predecessor tiles yields the tile's exact entry set
 //   B      rows replay their prefix from the exact entry (dies within a few bytes unless the
@@ -410,7 +414,7 @@ __device__ __forceinline__ void rrx_scan_body(const ScanParams& sp) {
         ts.row0 = (uint64_t)tile * TILE_ROWS;
         RRX_T(0)
         // ---- stage the tile: 8 x 128-bit loads per lane (fully coalesced), stored as 4 words each
-        //      into the 132-byte-pitch rows (bank-conflict-free: see ROW_PITCH) ----------------------
+        //      into the rows (pitch ROW_PITCH: one 128-bit store per chunk when the pitch is 16-byte aligned) -
         {
             const int64_t g0 = ts.lo();
             uint4 v[8];

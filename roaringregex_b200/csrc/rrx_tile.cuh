@@ -66,10 +66,11 @@ constexpr int TILE_BYTES = TILE_ROWS * ROW_BYTES;     // 4 KiB
 // Rows are staged in shared memory 132 bytes apart: lane t reading byte p of ITS row touches bank
 // (33t + p/4) mod 32 = (t + p/4) mod 32, so the 32 lanes of a warp stepping through their rows in
 // lock-step never collide, for byte, word or any other same-offset access.
-// (Kernels that stage tiles with bulk copies — cp.async.bulk needs 16-byte aligned destinations — are compiled with
-// RRX_ROW_PITCH 144: 128-bit loads of the same 16-byte chunk of 8 consecutive rows are conflict-free, same-offset
-// 32-bit accesses of all 32 lanes 4-way.  The candidate scan reads rows with 128-bit loads and bytes at scattered
-// offsets, so it does not care; the dense row scan does, and keeps 132.)
+// (The run-time specialised thread-owned kernels — and any kernel that stages tiles with bulk copies, which need 16-byte
+// aligned destinations — are compiled with RRX_ROW_PITCH 144: 128-bit loads of the same 16-byte chunk of 8 consecutive
+// rows are conflict-free, same-offset 32-bit accesses of all 32 lanes 4-way.  The candidate scan reads rows with 128-bit
+// loads and bytes at scattered offsets, so it does not care; the dense row scan does, and keeps 132 — as do the
+// pre-compiled kernels.)
 #ifndef RRX_ROW_PITCH
 #define RRX_ROW_PITCH 132
 #endif
